@@ -1,0 +1,160 @@
+/* nls_b200.h — C ABI of the B200-native Neo LS-SVM hot path (libnls_b200.so).
+ *
+ * The reference (lsorber/neo-ls-svm v0.3.0) is pure Python and has no FFI layer; the boundary it
+ * exposes for this path is the sklearn estimator `NeoLSSVM` (src/neo_ls_svm/_neo_ls_svm.py:43).
+ * These entry points are what a maintainer of the reference would bind (ctypes, see
+ * INTEGRATION.md) to replace the NumPy/SciPy bodies cited on each function.
+ *
+ * Conventions
+ *   - extern "C"; every function returns 0 on success and a negative nls_status on failure;
+ *     nls_last_error() returns a thread-local, human-readable message.  No C++ exceptions cross.
+ *   - All array arguments are caller-owned DEVICE pointers on the context's device unless the
+ *     function name ends in `_host`.  Matrices are row-major FP64; complex values are interleaved
+ *     (re, im) doubles, i.e. NumPy complex128 layout.
+ *   - Work is enqueued on the stream given at context creation (torch's current stream in the
+ *     Python host layer).  Functions do not synchronise unless they return host scalars.
+ *   - One context per process per GPU; multi-GPU runs are one process per GPU and the caller sums
+ *     the documented partial results with an NCCL all-reduce between calls.
+ *   - There is no CPU fallback: every entry point needs an sm_100a device.
+ */
+#ifndef NLS_B200_H
+#define NLS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nls_ctx nls_ctx;
+
+typedef enum {
+  NLS_OK = 0,
+  NLS_ERR_INVALID = -1, /* bad argument */
+  NLS_ERR_CUDA = -2,    /* CUDA runtime / driver error */
+  NLS_ERR_ALLOC = -3,   /* device allocation failed */
+  NLS_ERR_SOLVER = -4,  /* eigensolver did not converge */
+  NLS_ERR_ARCH = -5     /* device is not sm_100 */
+} nls_status;
+
+/* Library version (major*10000 + minor*100 + patch). */
+int nls_version(void);
+/* Thread-local message describing the last failure on this thread. */
+const char* nls_last_error(void);
+
+/* Create / destroy a context bound to `device`, enqueueing on `stream` (a cudaStream_t, may be 0). */
+int nls_ctx_create(int device, void* stream, nls_ctx** out);
+int nls_ctx_destroy(nls_ctx* ctx);
+/* Rows per internal chunk (default 32768); affects scratch size only, never results' meaning. */
+int nls_ctx_set_chunk_rows(nls_ctx* ctx, int64_t rows);
+/* Kernels of this library launched through `ctx` so far (for bench.py's gpu_launches). */
+int64_t nls_ctx_launch_count(const nls_ctx* ctx);
+/* Device milliseconds spent in the dominant GEMM kernels since the last reset (CUDA events on the
+ * context's stream; only collected when enabled because it adds event records). */
+int nls_ctx_profile(nls_ctx* ctx, int enable);
+int nls_ctx_profile_read(nls_ctx* ctx, double* ms_out /* [NLS_PROF_N] */, int64_t* launches_out /* [NLS_PROF_N] */);
+enum { NLS_PROF_FEATURE_MAP = 0, NLS_PROF_GRAM = 1, NLS_PROF_PROJECT = 2, NLS_PROF_SWEEP = 3,
+       NLS_PROF_VARIANCE = 4, NLS_PROF_OTHER = 5, NLS_PROF_N = 6 };
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 1 — feature map.  Replaces AffineFeatureMap.transform (_affine_feature_map.py:72-92) +
+ * RandomFourierFeatures.transform (_feature_maps.py:153-203):
+ *     z = (x - shift) W,   phi = [exp(-1j z)/sqrt(D) | 1]
+ * X: n x d, shift: d, W: d x D (= A_/scale^T), phi_out: n x (D+1) complex128.
+ * ------------------------------------------------------------------------------------------- */
+int nls_feature_map(nls_ctx* ctx, const double* X, int64_t n, int d, const double* shift,
+                    const double* W, int D, double* phi_out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 2 — primal Gram.  Replaces _neo_ls_svm.py:112-114 and :127:
+ *     A = (S phi)^H (S phi) (Hermitian, exactly symmetrised),  b = (S phi)^H (s*y)
+ * for the local rows.  s must already be normalised by the GLOBAL weight sum (:110).
+ * A_out: m x m complex128 (m = D+1), b_out: m complex128.  Partial over rows: all-reduce(sum).
+ * ------------------------------------------------------------------------------------------- */
+int nls_primal_gram(nls_ctx* ctx, const double* X, const double* y, const double* s, int64_t n,
+                    int d, const double* shift, const double* W, int D, double* A_out,
+                    double* b_out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 3 — Hermitian eigendecomposition.  Replaces scipy.linalg.eigh at _neo_ls_svm.py:120:
+ *     lam, Q = eigh(scale * A)   (ascending lam, Q[:, k] the k-th eigenvector)
+ * A: m x m complex128 (only needs to be Hermitian), lam_out: m, Q_out: m x m complex128.
+ * ------------------------------------------------------------------------------------------- */
+int nls_heev(nls_ctx* ctx, const double* A, int m, double scale, double* lam_out, double* Q_out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Small replicated solves between the stages (O(m^2) / O(m^3), every rank computes the same).
+ * ------------------------------------------------------------------------------------------- */
+/* v = Q^H b inv_c (_neo_ls_svm.py:121, :129) when b != NULL (else v_out is read as input), and
+ * beta_eig = Q (v / (lam + gamma)) (:175) when beta_eig_out != NULL.  All complex128, length m. */
+int nls_primal_coeffs(nls_ctx* ctx, const double* Q, const double* lam, const double* b, int m,
+                      double inv_c, double gamma, double* v_out, double* beta_eig_out);
+/* Replaces cho_factor / cho_solve at _neo_ls_svm.py:177-178: U_out (m x m complex128, upper
+ * triangle valid, M = U^H U as scipy.linalg.cho_factor returns it) for M = A + diag_shift * I, and
+ * beta_out = M^-1 b when b != NULL. */
+int nls_cholesky_solve(nls_ctx* ctx, const double* A, int m, double diag_shift, const double* b,
+                       double* U_out, double* beta_out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 4 — leave-one-out sweep.  Replaces _neo_ls_svm.py:128-165 for the local rows:
+ *     T = phi Q;  P = Re(T * v);  H = s^2 |T|^2 inv_c;  loo = (P r - y) / (1 - H r),
+ *     r[k, g] = 1 / (gammas[g] + lam[k]);  classifier clip (:153-155);
+ *     sums_out[0, g] = sum_i s_i |loo_ig|                        (loo_errors_gammas_, :158)
+ *     sums_out[1, g] = sum_i s_i (|loo_ig| >= 1)                  (classifier only, :160)
+ *     sums_out[2, g] = sum_i s_i max(0, |loo_ig| - 1)             (classifier only, :161)
+ * v = Q^H b inv_c (:121, :129), inv_c = n_global * m (:117-118).  sums_out: 3 x G, partial over
+ * rows: all-reduce(sum); the caller takes the argmin (:159-165).
+ * ------------------------------------------------------------------------------------------- */
+int nls_primal_loo_sweep(nls_ctx* ctx, const double* X, const double* y, const double* s,
+                         int64_t n, int d, const double* shift, const double* W, int D,
+                         const double* Q, const double* lam, const double* v, double inv_c,
+                         const double* gammas, int G, int is_classifier, double* sums_out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 4c — per-row outputs at the selected gamma.  Replaces _neo_ls_svm.py:167-187:
+ *     sigma2_i   = sum_k |T_ik|^2 inv_c / (lam_k + gamma)      (= phi_i (gamma C + A)^-1 phi_i^H, :184)
+ *     leverage_i = s_i^2 sigma2_i                              (:169)
+ *     loo_i      = (Re(phi_i beta_eig) - y_i) / (1 - leverage_i), yhat_loo_i = y_i + loo_i (:149-150)
+ *     loo_res_i  = classifier-clipped loo_i                    (:153-155, :167)
+ *     resid_i    = Re(phi_i beta) - y_i, classifier-clipped    (:179-182)
+ *     loo_std_i  = sqrt(sigma2_i + (s_i sigma2_i)^2 / (1 - leverage_i))   (:186-187)
+ * beta_eig = Q (v / (lam + gamma)) (:175); beta = Cholesky re-solve (:177-178).  All outputs: n.
+ * ------------------------------------------------------------------------------------------- */
+int nls_primal_finalize(nls_ctx* ctx, const double* X, const double* y, const double* s, int64_t n,
+                        int d, const double* shift, const double* W, int D, const double* Q,
+                        const double* lam, double inv_c, double gamma, const double* beta_eig,
+                        const double* beta, int is_classifier, double* loo_res_out,
+                        double* yhat_loo_out, double* leverage_out, double* resid_out,
+                        double* loo_std_out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 5 — batched predict / predict_std.  Replaces decision_function (_neo_ls_svm.py:663-665)
+ * and predict_std (:467-469, :477) with one pass over phi(x):
+ *     yhat_i = Re(phi_i beta);   sigma_i = sqrt( sum_k |(phi_i B)_k|^2 w_k )
+ * B (m x m complex128) and w (m) describe (gamma C + A)^-1 = B diag(w) B^H: either the
+ * eigenbasis (B = Q, w = inv_c/(lam+gamma)) or the inverse Cholesky factor (B = U^-1, w = 1).
+ * yhat_out / sigma_out may be NULL to skip that output.
+ * ------------------------------------------------------------------------------------------- */
+int nls_primal_predict(nls_ctx* ctx, const double* X, int64_t n, int d, const double* shift,
+                       const double* W, int D, const double* beta, const double* B,
+                       const double* w, double* yhat_out, double* sigma_out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 5c — conformal quantile epilogue.  Replaces the per-row part of predict_quantiles
+ * (_neo_ls_svm.py:566-600).  beta_abs / beta_rel: F x Q coefficient matrices of the two coherent
+ * quantile regressors (F = 3 for a regressor: [sigma, |yhat|, 1]; F = 2 for a classifier:
+ * [sigma, 1]); bias_*: Q.  Regressor: out is n x Q.  Classifier: iso_x/iso_y (n_iso isotonic
+ * thresholds) are applied per quantile and out is n x Q x 2 ([1 - p reversed | p], :600).
+ * ------------------------------------------------------------------------------------------- */
+int nls_quantile_epilogue(nls_ctx* ctx, const double* yhat, const double* sigma, int64_t n,
+                          const double* beta_abs, const double* beta_rel, const double* bias_abs,
+                          const double* bias_rel, int Q, int is_regressor, const double* iso_x,
+                          const double* iso_y, int n_iso, double* out);
+
+/* Micro-benchmarks used for the roofline denominators (bench.py / profiles/). */
+int nls_bench_dmma_peak(nls_ctx* ctx, int iters, double* tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NLS_B200_H */

@@ -1,0 +1,726 @@
+// nls_b200.cu — host side of libnls_b200.so: context, scratch management, stage drivers and the
+// C ABI declared in include/nls_b200.h.  sm_100a only; there is no CPU fallback.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cusolverDn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/nls_b200.h"
+#include "ops.cuh"
+#include "small_kernels.cuh"
+
+using namespace nls;
+
+// ---------------------------------------------------------------------------------------------
+// Errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                            \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return fail(NLS_ERR_CUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define SOLVER_TRY(expr)                                                                          \
+  do {                                                                                            \
+    cusolverStatus_t _s = (expr);                                                                 \
+    if (_s != CUSOLVER_STATUS_SUCCESS)                                                            \
+      return fail(NLS_ERR_SOLVER, "%s failed at %s:%d: status %d", #expr, __FILE__, __LINE__, (int)_s); \
+  } while (0)
+
+#define NLS_TRY(expr)          \
+  do {                         \
+    int _r = (expr);           \
+    if (_r != NLS_OK) return _r; \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Context
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct ProfSpan {
+  cudaEvent_t a, b;
+  int kind;
+};
+
+struct nls_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  int64_t chunk_rows = 32768;
+  int64_t launches = 0;
+  bool use_tma = true;
+  EncodeTiledFn encode = nullptr;
+  cusolverDnHandle_t solver = nullptr;
+  // scratch (grow-only, zero-filled when (re)allocated)
+  DevBuf xc, wt, psi, psiT, pu, bt, rt, small, part, gram_ws, border, rowtmp, solver_ws, solver_mat;
+  // profiling
+  bool prof = false;
+  std::vector<ProfSpan> spans;
+  double prof_ms[NLS_PROF_N] = {0};
+  int64_t prof_n[NLS_PROF_N] = {0};
+};
+
+static int ensure(nls_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (b.bytes >= bytes && b.p) return NLS_OK;
+  if (b.p) {
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaFree(b.p));
+    b.p = nullptr;
+    b.bytes = 0;
+  }
+  cudaError_t e = cudaMalloc(&b.p, bytes);
+  if (e != cudaSuccess) return fail(NLS_ERR_ALLOC, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+  b.bytes = bytes;
+  CUDA_TRY(cudaMemsetAsync(b.p, 0, bytes, ctx->stream));
+  return NLS_OK;
+}
+
+static inline long long round_up(long long x, long long q) { return (x + q - 1) / q * q; }
+static inline int grid_for(long long total, int block = 256, int cap = 148 * 16) {
+  long long g = (total + block - 1) / block;
+  return (int)std::max<long long>(1, std::min<long long>(g, cap));
+}
+
+struct ProfScope {
+  nls_ctx* ctx;
+  int kind;
+  ProfSpan span;
+  bool on;
+  ProfScope(nls_ctx* c, int k) : ctx(c), kind(k), on(c->prof) {
+    if (on) {
+      cudaEventCreate(&span.a);
+      cudaEventCreate(&span.b);
+      span.kind = kind;
+      cudaEventRecord(span.a, ctx->stream);
+    }
+  }
+  ~ProfScope() {
+    if (on) {
+      cudaEventRecord(span.b, ctx->stream);
+      ctx->spans.push_back(span);
+    }
+  }
+};
+
+static int check_launch(nls_ctx* ctx, const char* what) {
+  ctx->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(NLS_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  return NLS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tensor maps and GEMM launch
+// ---------------------------------------------------------------------------------------------
+static int make_map(nls_ctx* ctx, CUtensorMap* map, const Operand& op, int box_rows, long long total_rows) {
+  if (!ctx->use_tma) {
+    memset(map, 0, sizeof *map);
+    return NLS_OK;
+  }
+  if ((reinterpret_cast<uintptr_t>(op.ptr) & 15) || (op.ld & 1))
+    return fail(NLS_ERR_INVALID, "TMA operand must be 16-byte aligned with an even pitch");
+  cuuint64_t dims[2] = {(cuuint64_t)op.kext, (cuuint64_t)total_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)op.ld * 8};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(op.ptr), dims, strides, box,
+                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(NLS_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return NLS_OK;
+}
+
+// `rows_a_total` / `rows_b_total`: row extent of the whole 2-D array each map describes (all planes).
+// For MODE_DUAL_A/COMPLEX the K extent of the map covers both planes when plane_dk != 0.
+template <int MODE, class Op>
+static int launch_gemm(nls_ctx* ctx, const typename Op::Params& p, dim3 grid, long long rows_a_total,
+                       long long rows_b_total, int kind, const char* name) {
+  using T = ModeTraits<MODE>;
+  Operand a = p.A, b = p.B;
+  // The tensor map's inner extent must span plane b when it lives at a K offset.
+  Operand am = a, bm = b;
+  if (T::A_PLANES == 2 && a.plane_dk) am.kext = a.plane_dk + a.kext;
+  if (T::B_PLANES == 2 && b.plane_dk) bm.kext = b.plane_dk + b.kext;
+  CUtensorMap mapA, mapB;
+  NLS_TRY(make_map(ctx, &mapA, am, BM, rows_a_total));
+  NLS_TRY(make_map(ctx, &mapB, bm, BN, rows_b_total));
+  ProfScope scope(ctx, kind);
+  if (ctx->use_tma) {
+    auto kern = gemm_kernel<MODE, Op, true>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
+      attr_set = true;
+    }
+    kern<<<grid, GEMM_THREADS, T::SMEM_BYTES, ctx->stream>>>(mapA, mapB, p);
+  } else {
+    auto kern = gemm_kernel<MODE, Op, false>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
+      attr_set = true;
+    }
+    kern<<<grid, GEMM_THREADS, T::SMEM_BYTES, ctx->stream>>>(mapA, mapB, p);
+  }
+  return check_launch(ctx, name);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage drivers (internal)
+// ---------------------------------------------------------------------------------------------
+struct MapGeom {
+  int d, D, dpad;
+  int Dp;   // K padding of the planar chunk (multiple of 16)
+  int DpT;  // row padding of each plane of the transposed chunk (multiple of 128)
+  int m, Np;
+  long long ldp;  // pitch of P/U/r^T rows (multiple of 16)
+};
+
+static MapGeom geom(int d, int D) {
+  MapGeom g;
+  g.d = d;
+  g.D = D;
+  g.dpad = (int)round_up(d, 16);
+  g.Dp = (int)round_up(D, 16);
+  g.DpT = (int)round_up(D, 128);
+  g.m = D + 1;
+  g.Np = (int)round_up(D + 1, 64);
+  g.ldp = round_up(D + 1, 16);
+  return g;
+}
+
+// W (d x D) -> W^T (D x dpad) scratch.
+static int prep_weights(nls_ctx* ctx, const MapGeom& g, const double* W) {
+  NLS_TRY(ensure(ctx, ctx->wt, (size_t)g.D * g.dpad * 8));
+  NLS_TRY(ensure(ctx, ctx->xc, (size_t)ctx->chunk_rows * g.dpad * 8));
+  transpose_w_kernel<<<grid_for((long long)g.D * g.dpad), 256, 0, ctx->stream>>>(W, g.d, g.D, g.dpad,
+                                                                                (double*)ctx->wt.p);
+  return check_launch(ctx, "transpose_w_kernel");
+}
+
+// Feature map of `rows` rows starting at X into `out` with the given layout.
+static int feature_chunk(nls_ctx* ctx, const MapGeom& g, const double* X, const double* shift, int rows, int layout,
+                         double* out, long long ld, int plane_stride, const double* row_scale) {
+  center_rows_kernel<<<grid_for((long long)rows * g.dpad), 256, 0, ctx->stream>>>(X, shift, rows, g.d, g.dpad,
+                                                                                 (double*)ctx->xc.p);
+  NLS_TRY(check_launch(ctx, "center_rows_kernel"));
+  OpFeatureMap::Params p;
+  p.A = Operand{(const double*)ctx->xc.p, g.dpad, rows, g.d, 0, 0};
+  p.B = Operand{(const double*)ctx->wt.p, g.dpad, g.D, g.d, 0, 0};
+  p.n_rows = rows;
+  p.D = g.D;
+  p.layout = layout;
+  p.inv_sqrt_D = 1.0 / sqrt((double)g.D);
+  p.row_scale = row_scale;
+  p.out = out;
+  p.ld = ld;
+  p.plane_stride = plane_stride;
+  dim3 grid((g.D + BN - 1) / BN, (rows + BM - 1) / BM);
+  return launch_gemm<MODE_REAL, OpFeatureMap>(ctx, p, grid, rows, g.D, NLS_PROF_FEATURE_MAP, "feature_map");
+}
+
+// Basis planes B^T (2Np x Dp) + constant-feature bias from a numpy-layout m x m complex basis.
+struct BasisScratch {
+  double *bt, *bias_r, *bias_i, *v_r, *v_i, *w;
+};
+static int prep_basis(nls_ctx* ctx, const MapGeom& g, const double* B, BasisScratch* out) {
+  const size_t bt_bytes = (size_t)2 * g.Np * g.Dp * 8;
+  NLS_TRY(ensure(ctx, ctx->bt, bt_bytes));
+  NLS_TRY(ensure(ctx, ctx->small, (size_t)8 * g.Np * 8));
+  double* sm = (double*)ctx->small.p;
+  out->bt = (double*)ctx->bt.p;
+  out->bias_r = sm;
+  out->bias_i = sm + g.Np;
+  out->v_r = sm + 2 * g.Np;
+  out->v_i = sm + 3 * g.Np;
+  out->w = sm + 4 * g.Np;
+  dim3 grid((g.m + 31) / 32, (g.m + 31) / 32), block(32, 8);
+  split_basis_kernel<<<grid, block, 0, ctx->stream>>>(B, g.m, g.D, g.Np, g.Dp, out->bt, out->bias_r, out->bias_i);
+  return check_launch(ctx, "split_basis_kernel");
+}
+
+static Operand psi_operand(nls_ctx* ctx, const MapGeom& g, int rows) {
+  return Operand{(const double*)ctx->psi.p, 2LL * g.Dp, rows, g.D, 0, g.Dp};
+}
+static Operand basis_operand(const MapGeom& g, const double* bt) {
+  return Operand{bt, g.Dp, 2 * g.Np, g.D, g.Np, 0};
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI: context
+// ---------------------------------------------------------------------------------------------
+extern "C" int nls_version(void) { return 100; }
+extern "C" const char* nls_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int nls_ctx_create(int device, void* stream, nls_ctx** out) {
+  if (!out) return fail(NLS_ERR_INVALID, "out is null");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(NLS_ERR_ARCH, "device %d is sm_%d%d; this library only contains sm_100a code", device, prop.major,
+                prop.minor);
+  nls_ctx* ctx = new nls_ctx();
+  ctx->device = device;
+  ctx->stream = (cudaStream_t)stream;
+  ctx->sm_count = prop.multiProcessorCount;
+  const char* env = getenv("NLS_NO_TMA");
+  ctx->use_tma = !(env && env[0] == '1');
+  env = getenv("NLS_CHUNK_ROWS");
+  if (env && atoll(env) > 0) ctx->chunk_rows = round_up(atoll(env), 128);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    delete ctx;
+    return fail(NLS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  }
+  ctx->encode = (EncodeTiledFn)fn;
+  if (cusolverDnCreate(&ctx->solver) != CUSOLVER_STATUS_SUCCESS) {
+    delete ctx;
+    return fail(NLS_ERR_SOLVER, "cusolverDnCreate failed");
+  }
+  cusolverDnSetStream(ctx->solver, ctx->stream);
+  *out = ctx;
+  return NLS_OK;
+}
+
+extern "C" int nls_ctx_destroy(nls_ctx* ctx) {
+  if (!ctx) return NLS_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf* bufs[] = {&ctx->xc, &ctx->wt, &ctx->psi, &ctx->psiT, &ctx->pu, &ctx->bt, &ctx->rt, &ctx->small,
+                    &ctx->part, &ctx->gram_ws, &ctx->border, &ctx->rowtmp, &ctx->solver_ws, &ctx->solver_mat};
+  for (DevBuf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  for (auto& s : ctx->spans) {
+    cudaEventDestroy(s.a);
+    cudaEventDestroy(s.b);
+  }
+  if (ctx->solver) cusolverDnDestroy(ctx->solver);
+  delete ctx;
+  return NLS_OK;
+}
+
+extern "C" int nls_ctx_set_chunk_rows(nls_ctx* ctx, int64_t rows) {
+  if (!ctx || rows < 128) return fail(NLS_ERR_INVALID, "chunk rows must be >= 128");
+  ctx->chunk_rows = round_up(rows, 128);
+  return NLS_OK;
+}
+
+extern "C" int64_t nls_ctx_launch_count(const nls_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int nls_ctx_profile(nls_ctx* ctx, int enable) {
+  if (!ctx) return fail(NLS_ERR_INVALID, "ctx is null");
+  ctx->prof = enable != 0;
+  for (auto& s : ctx->spans) {
+    cudaEventDestroy(s.a);
+    cudaEventDestroy(s.b);
+  }
+  ctx->spans.clear();
+  for (int k = 0; k < NLS_PROF_N; ++k) {
+    ctx->prof_ms[k] = 0;
+    ctx->prof_n[k] = 0;
+  }
+  return NLS_OK;
+}
+
+extern "C" int nls_ctx_profile_read(nls_ctx* ctx, double* ms_out, int64_t* launches_out) {
+  if (!ctx) return fail(NLS_ERR_INVALID, "ctx is null");
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  for (auto& s : ctx->spans) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, s.a, s.b);
+    ctx->prof_ms[s.kind] += ms;
+    ctx->prof_n[s.kind] += 1;
+    cudaEventDestroy(s.a);
+    cudaEventDestroy(s.b);
+  }
+  ctx->spans.clear();
+  for (int k = 0; k < NLS_PROF_N; ++k) {
+    if (ms_out) ms_out[k] = ctx->prof_ms[k];
+    if (launches_out) launches_out[k] = ctx->prof_n[k];
+  }
+  return NLS_OK;
+}
+
+static int check_map_args(nls_ctx* ctx, const void* X, int64_t n, int d, const void* shift, const void* W, int D) {
+  if (!ctx) return fail(NLS_ERR_INVALID, "ctx is null");
+  if (!X || !shift || !W) return fail(NLS_ERR_INVALID, "null input pointer");
+  if (n < 1 || d < 1 || D < 1) return fail(NLS_ERR_INVALID, "n, d and D must be positive (n=%lld d=%d D=%d)", (long long)n, d, D);
+  if (n > (1LL << 40)) return fail(NLS_ERR_INVALID, "n too large");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  return NLS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage 1
+// ---------------------------------------------------------------------------------------------
+extern "C" int nls_feature_map(nls_ctx* ctx, const double* X, int64_t n, int d, const double* shift, const double* W,
+                               int D, double* phi_out) {
+  NLS_TRY(check_map_args(ctx, X, n, d, shift, W, D));
+  if (!phi_out) return fail(NLS_ERR_INVALID, "phi_out is null");
+  const MapGeom g = geom(d, D);
+  NLS_TRY(prep_weights(ctx, g, W));
+  for (int64_t i0 = 0; i0 < n; i0 += ctx->chunk_rows) {
+    const int rows = (int)std::min<int64_t>(ctx->chunk_rows, n - i0);
+    NLS_TRY(feature_chunk(ctx, g, X + i0 * d, shift, rows, FM_COMPLEX, phi_out + i0 * (D + 1) * 2, 0, 0, nullptr));
+  }
+  return NLS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage 2
+// ---------------------------------------------------------------------------------------------
+extern "C" int nls_primal_gram(nls_ctx* ctx, const double* X, const double* y, const double* s, int64_t n, int d,
+                               const double* shift, const double* W, int D, double* A_out, double* b_out) {
+  NLS_TRY(check_map_args(ctx, X, n, d, shift, W, D));
+  if (!y || !s || !A_out || !b_out) return fail(NLS_ERR_INVALID, "null pointer");
+  const MapGeom g = geom(d, D);
+  NLS_TRY(prep_weights(ctx, g, W));
+  const long long ldT = ctx->chunk_rows;
+  NLS_TRY(ensure(ctx, ctx->psiT, (size_t)2 * g.DpT * ldT * 8));
+  const int tiles_m = (D + BM - 1) / BM, tiles_n = (D + BN - 1) / BN;
+  int n_tiles = 0;
+  for (int kb = 0; kb < tiles_m; ++kb) n_tiles += std::max(0, tiles_n - 2 * kb);
+  const int splits = std::max(1, ctx->sm_count / n_tiles);
+  const size_t ws_bytes = (size_t)splits * 2 * D * D * 8;
+  NLS_TRY(ensure(ctx, ctx->gram_ws, ws_bytes));
+  NLS_TRY(ensure(ctx, ctx->border, (size_t)(4 * D + 2) * 8));
+  CUDA_TRY(cudaMemsetAsync(ctx->gram_ws.p, 0, ws_bytes, ctx->stream));
+  CUDA_TRY(cudaMemsetAsync(ctx->border.p, 0, (size_t)(4 * D + 2) * 8, ctx->stream));
+  double* border = (double*)ctx->border.p;
+  double* scal = border + 4 * D;
+  for (int64_t i0 = 0; i0 < n; i0 += ctx->chunk_rows) {
+    const int rows = (int)std::min<int64_t>(ctx->chunk_rows, n - i0);
+    NLS_TRY(feature_chunk(ctx, g, X + i0 * d, shift, rows, FM_TRANSPOSED, (double*)ctx->psiT.p, ldT, g.DpT, s + i0));
+    OpGram::Params p;
+    p.A = Operand{(const double*)ctx->psiT.p, ldT, 2 * g.DpT, rows, g.DpT, 0};
+    p.B = p.A;
+    p.D = D;
+    p.n_tiles_m = tiles_m;
+    p.n_tiles_n = tiles_n;
+    p.rows = rows;
+    p.k_per_split = (int)round_up((rows + splits - 1) / splits, BK);
+    p.ws = (double*)ctx->gram_ws.p;
+    NLS_TRY((launch_gemm<MODE_COMPLEX, OpGram>(ctx, p, dim3(n_tiles, splits), 2 * g.DpT, 2 * g.DpT, NLS_PROF_GRAM,
+                                                "gram")));
+    gram_border_kernel<<<2 * D + 1, 256, 0, ctx->stream>>>((const double*)ctx->psiT.p, ldT, D, g.DpT, rows, s + i0,
+                                                           y + i0, border, scal);
+    NLS_TRY(check_launch(ctx, "gram_border_kernel"));
+  }
+  gram_assemble_kernel<<<grid_for((long long)g.m * g.m), 256, 0, ctx->stream>>>((const double*)ctx->gram_ws.p, splits,
+                                                                               D, border, scal, A_out, b_out);
+  return check_launch(ctx, "gram_assemble_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage 3 (round 1: cuSOLVER divide & conquer as the library baseline; the hand-written blocked
+// Jacobi solver replaces it behind the same entry point — see DESIGN.md)
+// ---------------------------------------------------------------------------------------------
+extern "C" int nls_heev(nls_ctx* ctx, const double* A, int m, double scale, double* lam_out, double* Q_out) {
+  if (!ctx || !A || !lam_out || !Q_out || m < 1) return fail(NLS_ERR_INVALID, "bad argument to nls_heev");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const long long mm = (long long)m * m;
+  NLS_TRY(ensure(ctx, ctx->solver_mat, (size_t)mm * 16 + 64));
+  double* work_mat = (double*)ctx->solver_mat.p;
+  int* info = (int*)(work_mat + 2 * mm);
+  scale_conj_kernel<<<grid_for(mm), 256, 0, ctx->stream>>>(A, mm, scale, work_mat);
+  NLS_TRY(check_launch(ctx, "scale_conj_kernel"));
+  int lwork = 0;
+  SOLVER_TRY(cusolverDnZheevd_bufferSize(ctx->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m,
+                                         (cuDoubleComplex*)work_mat, m, lam_out, &lwork));
+  NLS_TRY(ensure(ctx, ctx->solver_ws, (size_t)lwork * 16));
+  ProfScope scope(ctx, NLS_PROF_OTHER);
+  SOLVER_TRY(cusolverDnZheevd(ctx->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, m,
+                              (cuDoubleComplex*)work_mat, m, lam_out, (cuDoubleComplex*)ctx->solver_ws.p, lwork,
+                              info));
+  // Column-major eigenvectors V[l, k] at work_mat[k*m + l]  ->  row-major Q[l, k].
+  dim3 grid((m + 31) / 32, (m + 31) / 32), block(32, 8);
+  transpose_square_kernel<2><<<grid, block, 0, ctx->stream>>>(work_mat, m, Q_out);
+  NLS_TRY(check_launch(ctx, "transpose_square_kernel"));
+  int h_info = 0;
+  CUDA_TRY(cudaMemcpyAsync(&h_info, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (h_info != 0) return fail(NLS_ERR_SOLVER, "Hermitian eigensolver failed: info = %d", h_info);
+  return NLS_OK;
+}
+
+// v = Q^H b inv_c  and (optionally, gamma >= 0) beta_eig = Q (v / (lam + gamma)).
+extern "C" int nls_primal_coeffs(nls_ctx* ctx, const double* Q, const double* lam, const double* b, int m,
+                                 double inv_c, double gamma, double* v_out, double* beta_eig_out) {
+  if (!ctx || !Q || !lam || !v_out || m < 1) return fail(NLS_ERR_INVALID, "bad argument to nls_primal_coeffs");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  if (b) {
+    project_rhs_kernel<<<m, 256, 0, ctx->stream>>>(Q, b, m, inv_c, v_out);
+    NLS_TRY(check_launch(ctx, "project_rhs_kernel"));
+  }
+  if (beta_eig_out) {
+    eigen_beta_kernel<<<m, 256, 0, ctx->stream>>>(Q, v_out, lam, m, gamma, beta_eig_out);
+    NLS_TRY(check_launch(ctx, "eigen_beta_kernel"));
+  }
+  return NLS_OK;
+}
+
+// U (upper, row-major, M = U^H U like scipy.linalg.cho_factor) of M = A + diag_shift * I, and
+// beta = M^-1 b.   _neo_ls_svm.py:177-178.
+extern "C" int nls_cholesky_solve(nls_ctx* ctx, const double* A, int m, double diag_shift, const double* b,
+                                  double* U_out, double* beta_out) {
+  if (!ctx || !A || !U_out || m < 1) return fail(NLS_ERR_INVALID, "bad argument to nls_cholesky_solve");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const long long mm = (long long)m * m;
+  CUDA_TRY(cudaMemcpyAsync(U_out, A, (size_t)mm * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+  add_diag_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(U_out, m, diag_shift);
+  NLS_TRY(check_launch(ctx, "add_diag_kernel"));
+  // Row-major M read column-major is conj(M); its LOWER Cholesky factor stored column-major is
+  // exactly U row-major with M = U^H U.
+  int lwork = 0;
+  SOLVER_TRY(cusolverDnZpotrf_bufferSize(ctx->solver, CUBLAS_FILL_MODE_LOWER, m, (cuDoubleComplex*)U_out, m, &lwork));
+  NLS_TRY(ensure(ctx, ctx->solver_ws, (size_t)lwork * 16 + 64));
+  int* info = (int*)((char*)ctx->solver_ws.p + (size_t)lwork * 16);
+  SOLVER_TRY(cusolverDnZpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, m, (cuDoubleComplex*)U_out, m,
+                              (cuDoubleComplex*)ctx->solver_ws.p, lwork, info));
+  int h_info = 0;
+  CUDA_TRY(cudaMemcpyAsync(&h_info, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (h_info != 0) return fail(NLS_ERR_SOLVER, "Cholesky factorisation failed: info = %d", h_info);
+  if (b && beta_out) {
+    // conj(M) conj(beta) = conj(b)
+    CUDA_TRY(cudaMemcpyAsync(beta_out, b, (size_t)m * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+    conj_vec_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(beta_out, m);
+    NLS_TRY(check_launch(ctx, "conj_vec_kernel"));
+    SOLVER_TRY(cusolverDnZpotrs(ctx->solver, CUBLAS_FILL_MODE_LOWER, m, 1, (cuDoubleComplex*)U_out, m,
+                                (cuDoubleComplex*)beta_out, m, info));
+    conj_vec_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(beta_out, m);
+    NLS_TRY(check_launch(ctx, "conj_vec_kernel"));
+  }
+  return NLS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage 4a + 4b
+// ---------------------------------------------------------------------------------------------
+extern "C" int nls_primal_loo_sweep(nls_ctx* ctx, const double* X, const double* y, const double* s, int64_t n, int d,
+                                    const double* shift, const double* W, int D, const double* Q, const double* lam,
+                                    const double* v, double inv_c, const double* gammas, int G, int is_classifier,
+                                    double* sums_out) {
+  NLS_TRY(check_map_args(ctx, X, n, d, shift, W, D));
+  if (!y || !s || !Q || !lam || !v || !gammas || !sums_out || G < 1) return fail(NLS_ERR_INVALID, "null pointer");
+  const MapGeom g = geom(d, D);
+  NLS_TRY(prep_weights(ctx, g, W));
+  BasisScratch bs;
+  NLS_TRY(prep_basis(ctx, g, Q, &bs));
+  split_complex_kernel<<<(g.m + 255) / 256, 256, 0, ctx->stream>>>(v, g.m, bs.v_r, bs.v_i);
+  NLS_TRY(check_launch(ctx, "split_complex_kernel"));
+  const long long cap = ctx->chunk_rows;
+  NLS_TRY(ensure(ctx, ctx->psi, (size_t)cap * 2 * g.Dp * 8));
+  NLS_TRY(ensure(ctx, ctx->pu, (size_t)2 * cap * g.ldp * 8));
+  NLS_TRY(ensure(ctx, ctx->rt, (size_t)round_up(G, BN) * g.ldp * 8));
+  const int max_mtiles = (int)((cap + BM - 1) / BM);
+  NLS_TRY(ensure(ctx, ctx->part, (size_t)max_mtiles * 3 * G * 8));
+  build_rt_kernel<<<grid_for((long long)G * g.ldp), 256, 0, ctx->stream>>>(gammas, lam, G, g.m, g.ldp,
+                                                                          (double*)ctx->rt.p);
+  NLS_TRY(check_launch(ctx, "build_rt_kernel"));
+  CUDA_TRY(cudaMemsetAsync(sums_out, 0, (size_t)3 * G * 8, ctx->stream));
+  double* P = (double*)ctx->pu.p;
+  double* U = P + cap * g.ldp;
+  for (int64_t i0 = 0; i0 < n; i0 += cap) {
+    const int rows = (int)std::min<int64_t>(cap, n - i0);
+    const int mtiles = (rows + BM - 1) / BM;
+    NLS_TRY(feature_chunk(ctx, g, X + i0 * d, shift, rows, FM_PLANAR, (double*)ctx->psi.p, 2LL * g.Dp, g.Dp, nullptr));
+    OpProject::Params pp;
+    pp.A = psi_operand(ctx, g, rows);
+    pp.B = basis_operand(g, bs.bt);
+    pp.n_rows = rows;
+    pp.m = g.m;
+    pp.bias_r = bs.bias_r;
+    pp.bias_i = bs.bias_i;
+    pp.v_r = bs.v_r;
+    pp.v_i = bs.v_i;
+    pp.inv_c = inv_c;
+    pp.P = P;
+    pp.U = U;
+    pp.ld = g.ldp;
+    NLS_TRY((launch_gemm<MODE_COMPLEX, OpProject>(ctx, pp, dim3((g.m + BN - 1) / BN, mtiles), rows, 2 * g.Np,
+                                                   NLS_PROF_PROJECT, "project")));
+    OpSweep::Params sp;
+    sp.A = Operand{P, g.ldp, (int)(cap + rows), g.m, (int)cap, 0};
+    sp.B = Operand{(const double*)ctx->rt.p, g.ldp, G, g.m, 0, 0};
+    sp.n_rows = rows;
+    sp.G = G;
+    sp.y = y + i0;
+    sp.s = s + i0;
+    sp.is_classifier = is_classifier;
+    sp.part = (double*)ctx->part.p;
+    NLS_TRY((launch_gemm<MODE_DUAL_A, OpSweep>(ctx, sp, dim3((G + BN - 1) / BN, mtiles), cap + rows, G,
+                                                NLS_PROF_SWEEP, "sweep")));
+    sweep_reduce_kernel<<<(3 * G + 255) / 256, 256, 0, ctx->stream>>>((const double*)ctx->part.p, mtiles, G, sums_out);
+    NLS_TRY(check_launch(ctx, "sweep_reduce_kernel"));
+  }
+  return NLS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shared by stage 4c and stage 5: per-row yhat (two coefficient vectors) and sigma2 for a chunk.
+// ---------------------------------------------------------------------------------------------
+static int variance_chunk(nls_ctx* ctx, const MapGeom& g, const BasisScratch& bs, int rows, double* sigma2_out) {
+  const int ntiles = (g.m + BN - 1) / BN;
+  const long long cap = ctx->chunk_rows;
+  NLS_TRY(ensure(ctx, ctx->part, (size_t)ntiles * cap * 8));
+  OpVariance::Params vp;
+  vp.A = psi_operand(ctx, g, rows);
+  vp.B = basis_operand(g, bs.bt);
+  vp.n_rows = rows;
+  vp.m = g.m;
+  vp.bias_r = bs.bias_r;
+  vp.bias_i = bs.bias_i;
+  vp.w = bs.w;
+  vp.part = (double*)ctx->part.p;
+  vp.part_ld = cap;
+  NLS_TRY((launch_gemm<MODE_COMPLEX, OpVariance>(ctx, vp, dim3(ntiles, (rows + BM - 1) / BM), rows, 2 * g.Np,
+                                                  NLS_PROF_VARIANCE, "variance")));
+  rowsum_reduce_kernel<<<(rows + 255) / 256, 256, 0, ctx->stream>>>((const double*)ctx->part.p, ntiles, cap, rows,
+                                                                   sigma2_out);
+  return check_launch(ctx, "rowsum_reduce_kernel");
+}
+
+extern "C" int nls_primal_finalize(nls_ctx* ctx, const double* X, const double* y, const double* s, int64_t n, int d,
+                                   const double* shift, const double* W, int D, const double* Q, const double* lam,
+                                   double inv_c, double gamma, const double* beta_eig, const double* beta,
+                                   int is_classifier, double* loo_res_out, double* yhat_loo_out, double* leverage_out,
+                                   double* resid_out, double* loo_std_out) {
+  NLS_TRY(check_map_args(ctx, X, n, d, shift, W, D));
+  if (!y || !s || !Q || !lam || !beta_eig || !beta || !loo_res_out || !yhat_loo_out || !leverage_out || !resid_out ||
+      !loo_std_out)
+    return fail(NLS_ERR_INVALID, "null pointer");
+  const MapGeom g = geom(d, D);
+  NLS_TRY(prep_weights(ctx, g, W));
+  BasisScratch bs;
+  NLS_TRY(prep_basis(ctx, g, Q, &bs));
+  variance_weights_kernel<<<(g.m + 255) / 256, 256, 0, ctx->stream>>>(lam, g.m, inv_c, gamma, bs.w);
+  NLS_TRY(check_launch(ctx, "variance_weights_kernel"));
+  const long long cap = ctx->chunk_rows;
+  NLS_TRY(ensure(ctx, ctx->psi, (size_t)cap * 2 * g.Dp * 8));
+  NLS_TRY(ensure(ctx, ctx->rowtmp, (size_t)3 * cap * 8));
+  double* sigma2 = (double*)ctx->rowtmp.p;
+  double* num = sigma2 + cap;
+  double* fit = num + cap;
+  for (int64_t i0 = 0; i0 < n; i0 += cap) {
+    const int rows = (int)std::min<int64_t>(cap, n - i0);
+    NLS_TRY(feature_chunk(ctx, g, X + i0 * d, shift, rows, FM_PLANAR, (double*)ctx->psi.p, 2LL * g.Dp, g.Dp, nullptr));
+    NLS_TRY(variance_chunk(ctx, g, bs, rows, sigma2));
+    gemv_pair_kernel<<<(rows * 32 + 255) / 256, 256, 0, ctx->stream>>>((const double*)ctx->psi.p, 2LL * g.Dp, g.Dp,
+                                                                      rows, D, beta_eig, beta, num, fit);
+    NLS_TRY(check_launch(ctx, "gemv_pair_kernel"));
+    finalize_rows_kernel<<<(rows + 255) / 256, 256, 0, ctx->stream>>>(rows, y + i0, s + i0, sigma2, num, fit,
+                                                                     is_classifier, loo_res_out + i0,
+                                                                     yhat_loo_out + i0, leverage_out + i0,
+                                                                     resid_out + i0, loo_std_out + i0);
+    NLS_TRY(check_launch(ctx, "finalize_rows_kernel"));
+  }
+  return NLS_OK;
+}
+
+extern "C" int nls_primal_predict(nls_ctx* ctx, const double* X, int64_t n, int d, const double* shift,
+                                  const double* W, int D, const double* beta, const double* B, const double* w,
+                                  double* yhat_out, double* sigma_out) {
+  NLS_TRY(check_map_args(ctx, X, n, d, shift, W, D));
+  if (yhat_out && !beta) return fail(NLS_ERR_INVALID, "beta is required for yhat_out");
+  if (sigma_out && (!B || !w)) return fail(NLS_ERR_INVALID, "B and w are required for sigma_out");
+  const MapGeom g = geom(d, D);
+  NLS_TRY(prep_weights(ctx, g, W));
+  BasisScratch bs;
+  if (sigma_out) {
+    NLS_TRY(prep_basis(ctx, g, B, &bs));
+    CUDA_TRY(cudaMemcpyAsync(bs.w, w, (size_t)g.m * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  const long long cap = ctx->chunk_rows;
+  NLS_TRY(ensure(ctx, ctx->psi, (size_t)cap * 2 * g.Dp * 8));
+  NLS_TRY(ensure(ctx, ctx->rowtmp, (size_t)3 * cap * 8));
+  double* sigma2 = (double*)ctx->rowtmp.p;
+  for (int64_t i0 = 0; i0 < n; i0 += cap) {
+    const int rows = (int)std::min<int64_t>(cap, n - i0);
+    NLS_TRY(feature_chunk(ctx, g, X + i0 * d, shift, rows, FM_PLANAR, (double*)ctx->psi.p, 2LL * g.Dp, g.Dp, nullptr));
+    if (yhat_out) {
+      gemv_pair_kernel<<<(rows * 32 + 255) / 256, 256, 0, ctx->stream>>>((const double*)ctx->psi.p, 2LL * g.Dp, g.Dp,
+                                                                        rows, D, beta, nullptr, yhat_out + i0,
+                                                                        nullptr);
+      NLS_TRY(check_launch(ctx, "gemv_pair_kernel"));
+    }
+    if (sigma_out) {
+      NLS_TRY(variance_chunk(ctx, g, bs, rows, sigma2));
+      sqrt_kernel<<<(rows + 255) / 256, 256, 0, ctx->stream>>>(sigma2, rows, sigma_out + i0);
+      NLS_TRY(check_launch(ctx, "sqrt_kernel"));
+    }
+  }
+  return NLS_OK;
+}
+
+extern "C" int nls_quantile_epilogue(nls_ctx* ctx, const double* yhat, const double* sigma, int64_t n,
+                                     const double* beta_abs, const double* beta_rel, const double* bias_abs,
+                                     const double* bias_rel, int Q, int is_regressor, const double* iso_x,
+                                     const double* iso_y, int n_iso, double* out) {
+  if (!ctx || !yhat || !sigma || !beta_abs || !beta_rel || !bias_abs || !bias_rel || !out)
+    return fail(NLS_ERR_INVALID, "null pointer");
+  if (Q < 1 || Q > MAX_QUANTILES) return fail(NLS_ERR_INVALID, "Q must be in [1, %d]", MAX_QUANTILES);
+  if (!is_regressor && (!iso_x || !iso_y || n_iso < 1)) return fail(NLS_ERR_INVALID, "classifier needs isotonic thresholds");
+  if (n < 1) return NLS_OK;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  quantile_epilogue_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+      yhat, sigma, n, beta_abs, beta_rel, bias_abs, bias_rel, Q, is_regressor, iso_x, iso_y, n_iso, out);
+  return check_launch(ctx, "quantile_epilogue_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Micro-benchmark: register-resident DMMA loop (FP64 tensor peak of this device).
+// ---------------------------------------------------------------------------------------------
+extern "C" int nls_bench_dmma_peak(nls_ctx* ctx, int iters, double* tflops_out) {
+  if (!ctx || !tflops_out || iters < 1) return fail(NLS_ERR_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  NLS_TRY(ensure(ctx, ctx->small, 4096));
+  const int blocks = ctx->sm_count * 4, threads = 256;
+  cudaEvent_t a, b;
+  CUDA_TRY(cudaEventCreate(&a));
+  CUDA_TRY(cudaEventCreate(&b));
+  dmma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(iters / 8 + 1, (double*)ctx->small.p);  // warm-up
+  CUDA_TRY(cudaEventRecord(a, ctx->stream));
+  dmma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(iters, (double*)ctx->small.p);
+  CUDA_TRY(cudaEventRecord(b, ctx->stream));
+  NLS_TRY(check_launch(ctx, "dmma_peak_kernel"));
+  CUDA_TRY(cudaEventSynchronize(b));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+  const double flops = (double)blocks * (threads / 32) * (double)iters * 16.0 * (2.0 * 8 * 8 * 4);
+  *tflops_out = flops / (ms * 1e-3) / 1e12;
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  return NLS_OK;
+}

@@ -1,0 +1,421 @@
+// ops.cuh — per-stage tile mappings and fused epilogues plugged into gemm_kernel (gemm_core.cuh).
+#pragma once
+#include "gemm_core.cuh"
+
+namespace nls {
+
+// Coordinates of accumulator element (i, j, e) of a warp tile inside the CTA tile.
+__device__ __forceinline__ int acc_row(int warp_m, int i, int lane) { return warp_m * 32 + 8 * i + (lane >> 2); }
+__device__ __forceinline__ int acc_col(int warp_n, int j, int lane) { return warp_n * 32 + 8 * j + 2 * (lane & 3); }
+
+// =============================================================================================
+// Stage 1: z = Xc . W^T-tile, epilogue (cos z, sin z)/sqrt(D) in one of three layouts.
+//   reference: _affine_feature_map.py:81-89 (z) and _feature_maps.py:201-202 (exp(-1j z)/sqrt(D)).
+// =============================================================================================
+enum { FM_PLANAR = 0, FM_TRANSPOSED = 1, FM_COMPLEX = 2 };
+
+struct OpFeatureMap {
+  struct Params {
+    Operand A, B;      // A = centred rows (n_rows x d), B = W^T (D x d)
+    int n_rows, D;
+    int layout;
+    double inv_sqrt_D;
+    const double* row_scale;  // optional per-row factor (sample weight s_i), may be null
+    double* out;
+    long long ld;             // FM_PLANAR: row pitch (>= 2*Dp); FM_TRANSPOSED: pitch of a feature row
+    int plane_stride;         // FM_PLANAR: column offset of the sin plane; FM_TRANSPOSED: row offset
+  };
+  static __device__ __forceinline__ Tile tile(const Params& p) {
+    Tile t;
+    t.n0 = blockIdx.x * BN;
+    t.m0 = blockIdx.y * BM;
+    t.k_begin = 0;
+    t.k_end = p.A.kext;
+    t.valid = true;
+    return t;
+  }
+  static __device__ __forceinline__ void epilogue(const Params& p, const Tile& t, Acc& acc, int warp_m, int warp_n,
+                                                  int lane, uint8_t*) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = t.m0 + acc_row(warp_m, i, lane);
+      if (row >= p.n_rows) continue;
+      const double w = p.row_scale ? p.row_scale[row] * p.inv_sqrt_D : p.inv_sqrt_D;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = t.n0 + acc_col(warp_n, j, lane);
+        double c[2], s[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          sincos(acc.r[i][j][e], &s[e], &c[e]);
+          c[e] *= w;
+          s[e] *= w;
+        }
+        if (p.layout == FM_PLANAR) {
+          double* o = p.out + (long long)row * p.ld + col;
+          if (col + 1 < p.D) {
+            *reinterpret_cast<double2*>(o) = make_double2(c[0], c[1]);
+            *reinterpret_cast<double2*>(o + p.plane_stride) = make_double2(s[0], s[1]);
+          } else if (col < p.D) {
+            o[0] = c[0];
+            o[p.plane_stride] = s[0];
+          }
+        } else if (p.layout == FM_TRANSPOSED) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            if (col + e < p.D) {
+              p.out[(long long)(col + e) * p.ld + row] = c[e];
+              p.out[(long long)(col + e + p.plane_stride) * p.ld + row] = s[e];
+            }
+        } else {  // FM_COMPLEX: phi = (c, -s) interleaved, row pitch (D+1) complex
+          double* o = p.out + ((long long)row * (p.D + 1) + col) * 2;
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            if (col + e < p.D) {
+              o[2 * e] = c[e];
+              o[2 * e + 1] = -s[e];
+            }
+          if (col == 0) {  // constant feature, _feature_maps.py:203
+            double* last = p.out + ((long long)row * (p.D + 1) + p.D) * 2;
+            last[0] = 1.0;
+            last[1] = 0.0;
+          }
+        }
+      }
+    }
+  }
+};
+
+// =============================================================================================
+// Stage 2: Hermitian Gram of the weighted, transposed feature chunk Psi^T (2*Dp x rows):
+//   R = C^T C + S^T S = Re A,   I = S^T C - C^T S = Im A    (upper-triangular tiles only),
+// split over the chunk's rows; each (split, tile) CTA owns its slot of the partial-sum workspace and
+// accumulates into it chunk after chunk (fixed order => bitwise reproducible).
+//   reference: _neo_ls_svm.py:112-114.
+// =============================================================================================
+struct OpGram {
+  struct Params {
+    Operand A, B;   // both = Psi^T; A box 128 rows, B box 64 rows
+    int D;
+    int n_tiles_m;  // ceil(D/128)
+    int n_tiles_n;  // ceil(D/64)
+    int rows;       // valid rows (K extent) in this chunk
+    int k_per_split;
+    double* ws;     // [split][2][D][D]
+  };
+  static __device__ __forceinline__ Tile tile(const Params& p) {
+    Tile t;
+    int idx = blockIdx.x, kb = 0;
+    // Row block kb owns column blocks lb >= 2*kb (tiles touching the upper triangle).
+    while (kb < p.n_tiles_m && idx >= p.n_tiles_n - 2 * kb) {
+      idx -= p.n_tiles_n - 2 * kb;
+      ++kb;
+    }
+    t.valid = kb < p.n_tiles_m;
+    t.m0 = kb * BM;
+    t.n0 = (2 * kb + idx) * BN;
+    t.k_begin = blockIdx.y * p.k_per_split;
+    t.k_end = min(p.rows, t.k_begin + p.k_per_split);
+    if (t.k_begin >= t.k_end) t.valid = false;
+    return t;
+  }
+  static __device__ __forceinline__ void epilogue(const Params& p, const Tile& t, Acc& acc, int warp_m, int warp_n,
+                                                  int lane, uint8_t*) {
+    double* wr = p.ws + (long long)blockIdx.y * 2 * p.D * p.D;
+    double* wi = wr + (long long)p.D * p.D;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = t.m0 + acc_row(warp_m, i, lane);
+      if (row >= p.D) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = t.n0 + acc_col(warp_n, j, lane);
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          if (col + e < p.D && col + e >= row) {
+            const long long o = (long long)row * p.D + col + e;
+            wr[o] += acc.r[i][j][e];
+            wi[o] += acc.i[i][j][e];
+          }
+      }
+    }
+  }
+};
+
+// =============================================================================================
+// Stage 4a: T = phi Q for a chunk (complex GEMM on planar [C|S]), epilogue
+//   P = Re(T v),  U = |T|^2 inv_c      reference: _neo_ls_svm.py:134, :137 (single-T form)
+// With xa = C, xb = S, ya = Re Q^T, yb = Im Q^T:  R = Re T,  I = -Im T  (before the constant-feature
+// bias Q[D, k], which is added here).
+// =============================================================================================
+struct OpProject {
+  struct Params {
+    Operand A, B;         // A = Psi chunk (rows x 2Dp), B = Q^T planes (2Np x Dp)
+    int n_rows, m;
+    const double* bias_r;  // Re Q[D, k]
+    const double* bias_i;  // Im Q[D, k]
+    const double* v_r;
+    const double* v_i;
+    double inv_c;
+    double* P;
+    double* U;
+    long long ld;
+  };
+  static __device__ __forceinline__ Tile tile(const Params& p) {
+    Tile t;
+    t.n0 = blockIdx.x * BN;
+    t.m0 = blockIdx.y * BM;
+    t.k_begin = 0;
+    t.k_end = p.A.kext < p.B.kext ? p.A.kext : p.B.kext;
+    t.valid = true;
+    return t;
+  }
+  static __device__ __forceinline__ void epilogue(const Params& p, const Tile& t, Acc& acc, int warp_m, int warp_n,
+                                                  int lane, uint8_t*) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = t.n0 + acc_col(warp_n, j, lane);
+      double br[2], bi[2], vr[2], vi[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool ok = col + e < p.m;
+        br[e] = ok ? p.bias_r[col + e] : 0.0;
+        bi[e] = ok ? p.bias_i[col + e] : 0.0;
+        vr[e] = ok ? p.v_r[col + e] : 0.0;
+        vi[e] = ok ? p.v_i[col + e] : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = t.m0 + acc_row(warp_m, i, lane);
+        if (row >= p.n_rows) continue;
+        double pv[2], uv[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const double tr = acc.r[i][j][e] + br[e];
+          const double ti = bi[e] - acc.i[i][j][e];
+          pv[e] = tr * vr[e] - ti * vi[e];
+          uv[e] = (tr * tr + ti * ti) * p.inv_c;
+        }
+        const long long o = (long long)row * p.ld + col;
+        if (col + 1 < p.m) {
+          *reinterpret_cast<double2*>(p.P + o) = make_double2(pv[0], pv[1]);
+          *reinterpret_cast<double2*>(p.U + o) = make_double2(uv[0], uv[1]);
+        } else if (col < p.m) {
+          p.P[o] = pv[0];
+          p.U[o] = uv[0];
+        }
+      }
+    }
+  }
+};
+
+// =============================================================================================
+// Stage 4b: num = P r, den = s^2 (U r) with r[k, g] = 1/(gamma_g + lam_k); fused LOO residual,
+// classifier clip, |.|, and the s-weighted reduction over rows.  The n x G matrices never exist.
+//   reference: _neo_ls_svm.py:147-161.
+// Output: part[m_tile][3][G] (fixed-order partial sums, reduced by sweep_reduce_kernel).
+// =============================================================================================
+struct OpSweep {
+  struct Params {
+    Operand A, B;   // A = [P ; U] stacked (plane_drow = chunk capacity), B = r^T (G x ldp)
+    int n_rows, G;
+    const double* y;
+    const double* s;
+    int is_classifier;
+    double* part;   // [gridDim.y][3][G]
+  };
+  static __device__ __forceinline__ Tile tile(const Params& p) {
+    Tile t;
+    t.n0 = blockIdx.x * BN;
+    t.m0 = blockIdx.y * BM;
+    t.k_begin = 0;
+    t.k_end = p.A.kext;
+    t.valid = true;
+    return t;
+  }
+  static __device__ __forceinline__ void epilogue(const Params& p, const Tile& t, Acc& acc, int warp_m, int warp_n,
+                                                  int lane, uint8_t* scratch) {
+    // Per-thread partial sums over its 4 rows for each of its 8 columns.
+    double e_abs[4][2], e_cnt[4][2], e_hng[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) e_abs[j][e] = e_cnt[j][e] = e_hng[j][e] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = t.m0 + acc_row(warp_m, i, lane);
+      if (row >= p.n_rows) continue;
+      const double yi = p.y[row];
+      const double si = p.s[row];
+      const double s2 = si * si;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          double loo = (acc.r[i][j][e] - yi) / (1.0 - s2 * acc.i[i][j][e]);
+          if (p.is_classifier) {
+            if ((yi > 0.0 && loo > 0.0) || (yi < 0.0 && loo < 0.0)) loo = 0.0;
+          }
+          const double a = fabs(loo);
+          e_abs[j][e] += si * a;
+          if (p.is_classifier) {
+            e_cnt[j][e] += (a >= 1.0) ? si : 0.0;
+            e_hng[j][e] += si * fmax(0.0, a - 1.0);
+          }
+        }
+    }
+    // Reduce over the 8 row-lanes of the warp (lanes sharing lane%4), fixed butterfly order.
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+#pragma unroll
+        for (int off = 4; off < 32; off <<= 1) {
+          e_abs[j][e] += __shfl_xor_sync(0xffffffffu, e_abs[j][e], off);
+          e_cnt[j][e] += __shfl_xor_sync(0xffffffffu, e_cnt[j][e], off);
+          e_hng[j][e] += __shfl_xor_sync(0xffffffffu, e_hng[j][e], off);
+        }
+    double* red = reinterpret_cast<double*>(scratch);  // [3][4 warp_m][64 cols]
+    if ((lane >> 2) == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = acc_col(warp_n, j, lane) + e;
+          red[(0 * 4 + warp_m) * BN + c] = e_abs[j][e];
+          red[(1 * 4 + warp_m) * BN + c] = e_cnt[j][e];
+          red[(2 * 4 + warp_m) * BN + c] = e_hng[j][e];
+        }
+    }
+    __syncthreads();
+    const int tid = threadIdx.x;
+    if (tid < 3 * BN) {
+      const int q = tid / BN, c = tid % BN;
+      const int g = t.n0 + c;
+      if (g < p.G) {
+        const double* r = red + (q * 4) * BN + c;
+        const double sum = ((r[0] + r[BN]) + r[2 * BN]) + r[3 * BN];
+        p.part[((long long)blockIdx.y * 3 + q) * p.G + g] = sum;
+      }
+    }
+  }
+};
+
+// =============================================================================================
+// Stage 4c / 5b: sigma2_i = sum_k |(phi B)_ik|^2 w_k — same mainloop as OpProject, epilogue reduces
+// over the tile's columns.   reference: _neo_ls_svm.py:184 and :467-469 (eigenbasis / U^-1 form).
+// Output: part[n_tile][row] (reduced over n_tile in fixed order by rowsum_reduce_kernel).
+// =============================================================================================
+struct OpVariance {
+  struct Params {
+    Operand A, B;
+    int n_rows, m;
+    const double* bias_r;
+    const double* bias_i;
+    const double* w;
+    double* part;     // [gridDim.x][part_ld]
+    long long part_ld;
+  };
+  static __device__ __forceinline__ Tile tile(const Params& p) {
+    Tile t;
+    t.n0 = blockIdx.x * BN;
+    t.m0 = blockIdx.y * BM;
+    t.k_begin = 0;
+    t.k_end = p.A.kext < p.B.kext ? p.A.kext : p.B.kext;
+    t.valid = true;
+    return t;
+  }
+  static __device__ __forceinline__ void epilogue(const Params& p, const Tile& t, Acc& acc, int warp_m, int warp_n,
+                                                  int lane, uint8_t* scratch) {
+    double rs[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = t.n0 + acc_col(warp_n, j, lane);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool ok = col + e < p.m;
+        const double br = ok ? p.bias_r[col + e] : 0.0;
+        const double bi = ok ? p.bias_i[col + e] : 0.0;
+        const double w = ok ? p.w[col + e] : 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const double tr = acc.r[i][j][e] + br;
+          const double ti = bi - acc.i[i][j][e];
+          rs[i] += (tr * tr + ti * ti) * w;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 1);
+      rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 2);
+    }
+    double* red = reinterpret_cast<double*>(scratch);  // [2 warp_n][128 rows]
+    if ((lane & 3) == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) red[warp_n * BM + acc_row(warp_m, i, lane)] = rs[i];
+    }
+    __syncthreads();
+    const int tid = threadIdx.x;
+    if (tid < BM) {
+      const int row = t.m0 + tid;
+      if (row < p.n_rows) p.part[(long long)blockIdx.x * p.part_ld + row] = red[tid] + red[BM + tid];
+    }
+  }
+};
+
+// =============================================================================================
+// Plain tile store (used by the dual path: kernel matrix products) with an optional exp epilogue:
+//   out[row, col] = R                         (EXP = false)
+//   out[row, col] = exp(R - 0.5 (na_row + nb_col)) + add   (EXP = true; R = xa.xb^T)
+//   reference: sklearn rbf_kernel(gamma=0.5) at _neo_ls_svm.py:261, :474, :669.
+// =============================================================================================
+template <bool EXP>
+struct OpStore {
+  struct Params {
+    Operand A, B;
+    int n_rows, n_cols;
+    const double* norm_a;
+    const double* norm_b;
+    double add;
+    int zero_diag_to;  // if >= 0 and row == col: store exp(0) + add exactly (distance forced to 0)
+    double* out;
+    long long ld;
+  };
+  static __device__ __forceinline__ Tile tile(const Params& p) {
+    Tile t;
+    t.n0 = blockIdx.x * BN;
+    t.m0 = blockIdx.y * BM;
+    t.k_begin = 0;
+    t.k_end = p.A.kext;
+    t.valid = true;
+    return t;
+  }
+  static __device__ __forceinline__ void epilogue(const Params& p, const Tile& t, Acc& acc, int warp_m, int warp_n,
+                                                  int lane, uint8_t*) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = t.m0 + acc_row(warp_m, i, lane);
+      if (row >= p.n_rows) continue;
+      const double na = EXP ? p.norm_a[row] : 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = t.n0 + acc_col(warp_n, j, lane);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          if (col + e >= p.n_cols) continue;
+          double v = acc.r[i][j][e];
+          if (EXP) {
+            double d2 = na - 2.0 * v + p.norm_b[col + e];
+            if (d2 < 0.0) d2 = 0.0;
+            if (p.zero_diag_to >= 0 && row == col + e) d2 = 0.0;
+            v = exp(-0.5 * d2) + p.add;
+          }
+          p.out[(long long)row * p.ld + col + e] = v;
+        }
+      }
+    }
+  }
+};
+
+}  // namespace nls
