@@ -1,0 +1,259 @@
+"""Affine feature maps: `AffineFeatureMap`, supervised `AffineNormalizer` and `AffineSeparator`.
+
+Host-side (NumPy) mirrors of the reference's transformers — same constructor arguments, fitted
+attributes (`shift_`, `scale_`, `A_`) and numerical recipe:
+
+* AffineFeatureMap   /root/reference/src/neo_ls_svm/_affine_feature_map.py:17-136
+* AffineNormalizer   /root/reference/src/neo_ls_svm/_affine_normalizer.py:16-117
+* AffineSeparator    /root/reference/src/neo_ls_svm/_affine_separator.py:54-210
+
+Fitting them is the pre-pass *before* the five GPU stages and is out of the hot path's
+scope for this round (§8f "next" #1): it stays on the host so that `shift_/scale_/A_` — and therefore
+the matrix W handed to the kernels — match the reference for identical seeds.  `transform` of the
+fitted map is stage 1 of the hot path and runs on the GPU inside the estimator; the NumPy `transform`
+here exists for API parity on small inputs (e.g. the dual path's n ≤ 1024 rows).
+"""
+
+from __future__ import annotations
+
+from functools import cached_property
+from typing import Any
+
+import numpy as np
+from sklearn.base import BaseEstimator, TransformerMixin
+from sklearn.utils import check_array, check_consistent_length, check_random_state, check_X_y
+from sklearn.utils.validation import _check_feature_names_in
+
+from ._quantizer import sample_bins_quantized_ecdf
+from ._weighted_quantile import weighted_quantile
+
+
+class AffineFeatureMap(BaseEstimator, TransformerMixin):
+    """x -> (x - shift) diag(1/scale) A   (A optional)."""
+
+    def __init__(self, *, scale, shift, A=None, append_features: bool = False):
+        self.scale = scale
+        self.shift = shift
+        self.A = A
+        self.append_features = append_features
+
+    # -- helpers -------------------------------------------------------------------------------
+    def _params(self, n_features: int):
+        scale = np.reshape(getattr(self, "scale_", self.scale), (-1, n_features))
+        shift = np.reshape(getattr(self, "shift_", self.shift), (-1, n_features))
+        return scale, shift, getattr(self, "A_", self.A)
+
+    def device_weights(self, n_features: int, dtype=np.float64):
+        """(shift, W) with z = (x - shift) W, i.e. W = A/scaleᵀ (or diag(1/scale) if A is None)."""
+        scale, shift, A = self._params(n_features)
+        W = (np.eye(n_features, dtype=dtype) if A is None else A) / scale.T
+        return np.ascontiguousarray(shift.ravel(), dtype=dtype), np.ascontiguousarray(W, dtype=dtype)
+
+    # -- sklearn API ---------------------------------------------------------------------------
+    def fit(self, X, y=None, sample_weight=None):
+        X = check_array(X)
+        self.n_features_in_ = X.shape[1]
+        scale, shift, A = self._params(X.shape[1])
+        assert scale.dtype == shift.dtype, "The scale and shift must have the same dtype"
+        assert not np.any(scale == 0), "The scale may not be zero"
+        assert np.all(np.isfinite(scale)), "The scale must be finite"
+        assert np.all(np.isfinite(shift)), "The shift must be finite"
+        assert X.shape[1] == scale.shape[1], "The scale must be compatible with the number of features"
+        assert X.shape[1] == shift.shape[1], "The shift must be compatible with the number of features"
+        if A is not None:
+            assert A.dtype == scale.dtype, "The matrix A must have the same dtype as the scale and shift"
+            assert X.shape[1] == A.shape[0], "The matrix A must have rows equal to the number of features in X"
+            assert np.all(np.isfinite(A)), "The matrix A must be finite"
+        return self
+
+    def transform(self, X):
+        X = check_array(X)
+        scale, shift, A = self._params(X.shape[1])
+        if A is None:
+            Z = (X - shift) / scale
+        else:
+            W = A / scale.T
+            # Same association as the reference (:85-87): project first when A narrows the data.
+            Z = X @ W - shift @ W if A.shape[1] < A.shape[0] else (X - shift) @ W
+        Z = Z.astype(X.dtype)
+        if self.append_features and A is not None:
+            Z = np.hstack((X, Z))
+        return Z
+
+    @cached_property
+    def pseudo_inverse(self):
+        return np.linalg.pinv(self.A) if self.A is not None else None
+
+    def inverse_transform(self, X_transformed):
+        X = check_array(X_transformed)
+        A = getattr(self, "A_", self.A)
+        scale = np.reshape(getattr(self, "scale_", self.scale), (-1, X.shape[1] if A is None else A.shape[0]))
+        shift = np.reshape(getattr(self, "shift_", self.shift), scale.shape)
+        if self.append_features and A is not None:
+            return X[:, : A.shape[0]]
+        if A is not None:
+            X = X @ self.pseudo_inverse
+        return (X * scale + shift).astype(X.dtype)
+
+    def get_feature_names_out(self, input_features=None):
+        A = getattr(self, "A_", self.A)
+        names = np.asarray(_check_feature_names_in(self, input_features), dtype=object)
+        if A is None:
+            out = names + "_shifted_scaled"
+        else:
+            out = np.array([f"{','.join(list(names))}_affine_map"] * A.shape[1], dtype=object)
+        if self.append_features and A is not None:
+            out = np.hstack((names, out))
+        return out
+
+    def _more_tags(self) -> dict[str, Any]:
+        return {"preserves_dtype": [np.float64, np.float32]}
+
+
+def _split_by_target_bin(X, y, sample_weight):
+    """Group rows by the quantised target: (masks, X per bin, total weight per bin, normalised row weights)."""
+    codes = sample_bins_quantized_ecdf(y)
+    masks = [codes == c for c in range(np.min(codes), np.max(codes) + 1)]
+    X_bins = [X[mk, :] for mk in masks]
+    mass = [np.sum(sample_weight[mk]) for mk in masks]
+    s_bins = [sample_weight[np.newaxis, mk] / np.sum(sample_weight[mk]) for mk in masks]
+    return masks, X_bins, mass, s_bins
+
+
+class AffineNormalizer(AffineFeatureMap):
+    """Supervised shift/scale: centre between, and scale by the spread of, the target's class bins."""
+
+    def __init__(self, *, append_features: bool = False) -> None:
+        self.shift = 0.0
+        self.scale = 1.0
+        self.A = None
+        self.append_features = append_features
+
+    def fit(self, X, y=None, sample_weight=None):
+        X, y = check_X_y(X, y, dtype=(np.float64, np.float32))
+        y = np.ravel(np.asarray(y)).astype(X.dtype)
+        sw = (np.ones(y.shape) if sample_weight is None else np.ravel(np.asarray(sample_weight))).astype(y.dtype)
+        check_consistent_length(y, sw)
+        _, X_bins, mass, s_bins = _split_by_target_bin(X, y, sw)
+        d = X.shape[1]
+        if len(X_bins) <= 1:
+            self.shift_ = np.zeros((1, d), dtype=X.dtype)
+            self.scale_ = np.ones((1, d), dtype=X.dtype)
+            AffineFeatureMap.fit(self, X, y, sw)
+            return self
+        # Per-bin robust location (weighted median) and spread (weighted mean absolute deviation).
+        centre = [weighted_quantile(Xb, sb.T, 0.5, axis=0) for Xb, sb in zip(X_bins, s_bins)]
+        spread = [sb @ np.abs(Xb - mu) for Xb, sb, mu in zip(X_bins, s_bins, centre)]
+        eps = np.finfo(X.dtype).eps
+        direction = np.zeros((1, d), dtype=X.dtype)
+        weight_sum = np.zeros((1, d), dtype=X.dtype)
+        shift = np.zeros((1, d), dtype=X.dtype)
+        scale = np.zeros((1, d), dtype=X.dtype)
+        n_bins = len(centre)
+        for i in range(n_bins - 1):
+            for j in range(i + 1, n_bins):
+                gap = centre[j] - centre[i]
+                width = np.maximum(spread[i] + spread[j], eps)
+                separability = np.abs(gap) / width
+                # Pair weight: regularised geometric mean of the pair's mass and separability.
+                w = np.sqrt((mass[i] + mass[j]) * (0.5 + separability))
+                # Optimal threshold between the two bins, placed proportionally to their spreads.
+                alpha = np.clip(spread[i] / width, 1e-6, 1.0 - 1e-6)
+                shift = shift + w * (centre[i] + alpha * gap)
+                scale = scale + w * width
+                direction += w * np.sign(gap)
+                weight_sum += w
+        direction /= weight_sum
+        self.shift_ = shift / weight_sum
+        self.scale_ = scale / weight_sum
+        flip = np.sign(direction) < 0
+        self.scale_[flip] = -self.scale_[flip]
+        AffineFeatureMap.fit(self, X, y, sw)
+        return self
+
+
+def pairwise_distances(X, Y):
+    """Squared Euclidean distances between the rows of X and Y."""
+    return np.sum(X * X, axis=1, keepdims=True) - 2 * X @ Y.T + np.sum(Y * Y, axis=1, keepdims=True).T
+
+
+def nearest_neighbours(X, Y):
+    """For each row of X, the closest row of Y."""
+    pick = np.argmin(pairwise_distances(X, Y), axis=1, keepdims=True)
+    return np.take_along_axis(Y, pick, axis=0)
+
+
+def _right_singular_vectors(X):
+    """Singular values (descending) and right singular vectors of X via the smaller Gram matrix."""
+    if X.shape[0] >= X.shape[1]:
+        e, V = np.linalg.eigh(X.conj().T @ X)
+        return np.sqrt(np.abs(e))[::-1], V[:, ::-1]
+    e, U = np.linalg.eigh(X @ X.conj().T)
+    sv = np.sqrt(np.abs(e))[::-1]
+    U = U[:, ::-1]
+    keep = sv > 0
+    sv, U = sv[keep], U[:, keep]
+    return sv, (X.conj().T @ U) / sv[np.newaxis, :]
+
+
+class AffineSeparator(AffineNormalizer):
+    """Supervised affine map: AffineNormalizer's shift/scale plus a matrix A that pulls the target's
+    class bins apart, scaled for a unit-width Gaussian kernel (λ = sqrt(2 log(f/g)/(f-g)))."""
+
+    def __init__(self, *, append_features: bool = False, rank_threshold: float = 2e-2,
+                 edge_sample_size: int = 384, edge_search_multiplier: int = 4,
+                 random_state: int | np.random.RandomState | None = 42) -> None:
+        self.shift = 0.0
+        self.scale = 1.0
+        self.A = None
+        self.append_features = append_features
+        self.rank_threshold = rank_threshold
+        self.edge_sample_size = edge_sample_size
+        self.edge_search_multiplier = edge_search_multiplier
+        self.random_state = random_state
+
+    def fit(self, X, y=None, sample_weight=None):
+        assert y is not None
+        X, y = check_X_y(X, y, dtype=(np.float64, np.float32))
+        y = np.ravel(np.asarray(y)).astype(X.dtype)
+        AffineNormalizer.fit(self, X, y, sample_weight)
+        X = AffineNormalizer.transform(self, X)  # A is still None here: shift and scale only
+        sw = (np.ones(y.shape) if sample_weight is None else np.ravel(np.asarray(sample_weight))).astype(y.dtype)
+        check_consistent_length(y, sw)
+        masks, X_bins, mass, s_bins = _split_by_target_bin(X, y, sw)
+        n_bins = len(X_bins)
+        if n_bins <= 1:
+            return self
+        if n_bins == 2:  # the reference enlarges (and keeps) the sample size for two bins (:139-141)
+            self.edge_sample_size = int(self.edge_sample_size * 4 / 3)
+        E, wide = self.edge_sample_size, self.edge_sample_size * self.edge_search_multiplier
+        rng = check_random_state(self.random_state)
+        directions, inside_edges, outside_edges = [], [], []
+        for i in range(n_bins):
+            own = X_bins[i]
+            p_own = np.ravel(s_bins[i])
+            seeds = own[rng.choice(len(own), size=E, p=p_own), :]
+            rest = np.vstack([Xb for j, Xb in enumerate(X_bins) if j != i])
+            w_rest = np.hstack([sw[mk] for j, mk in enumerate(masks) if j != i])
+            rest_sample = rest[rng.choice(len(rest), size=wide, p=np.ravel(w_rest) / np.sum(w_rest)), :]
+            # Points of the complement closest to bin i, then points of bin i closest to those.
+            outside = nearest_neighbours(seeds, rest_sample)
+            own_sample = own[rng.choice(len(own), size=wide, p=p_own), :]
+            inside = nearest_neighbours(outside, own_sample)
+            outside_edges.append(outside)
+            inside_edges.append(inside)
+            sv, V = _right_singular_vectors(inside - outside)
+            directions.append(V[:, : np.sum(sv > self.rank_threshold * sv[0])])
+        self.A_ = np.hstack(directions)
+        # Kernel-width scaling from the mean inter-bin (f) and intra-bin (g) squared edge distances.
+        f = g = 0.0
+        pairs_f, pairs_g = E * (E + 1) / 2, E * (E - 1) / 2
+        for inside, outside, n_b in zip(inside_edges, outside_edges, mass, strict=True):
+            pi, po = inside @ self.A_, outside @ self.A_
+            f += n_b * np.sum(np.tril(pairwise_distances(pi, po), k=0)) / pairs_f
+            g += n_b * np.sum(np.tril(pairwise_distances(pi, pi), k=-1)) / pairs_g
+        f /= sum(mass)
+        g /= sum(mass)
+        lam = np.sqrt(2 * np.log(f / g) / (f - g)) if g > 0 else 1
+        self.A_ *= lam
+        return self

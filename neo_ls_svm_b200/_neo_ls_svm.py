@@ -1,0 +1,422 @@
+"""`NeoLSSVM`: the sklearn-compatible estimator, with the numerical core on a B200.
+
+Drop-in mirror of the reference estimator (/root/reference/src/neo_ls_svm/_neo_ls_svm.py:43-821): same
+keyword-only constructor, same public methods (`fit`, `decision_function`, `predict`, `predict_proba`,
+`predict_std`, `predict_quantiles`, `predict_interval`, `score`) and the same fitted attributes
+(`β̂_ γ_ γs_ loo_errors_γs_ loo_residuals_ loo_ŷ_ loo_leverage_ loo_error_ loo_score_ L_ residuals_
+loo_std_ primal_feature_map_ dual_feature_map_ X_ α̂_ dual_ primal_ classes_ y_dtype_ n_features_in_
+predict_proba_calibrator_ *_calib_l1_/_l2_ conformal_l1_/_l2_`), all host NumPy so that `pickle` and
+`sklearn.base.clone` behave as before.
+
+What moved to the GPU: the feature map, the Hermitian Gram, the eigendecomposition,
+the leave-one-out γ sweep, the per-row LOO outputs, `decision_function`, `predict_std` and the
+per-row part of `predict_quantiles` (primal), and the kernel-matrix / eigen / LOO pipeline of the dual
+solve.  What stays on the host: input validation, the supervised affine pre-pass
+(`AffineSeparator.fit`), isotonic calibration, the conformal split and the two small quantile LPs.
+
+Host↔device traffic per primal fit: X, y, s up (once); A (m×m) and five n-vectors down.
+"""
+
+from __future__ import annotations
+
+from typing import Any, Literal
+
+import numpy as np
+from sklearn.base import BaseEstimator, clone
+from sklearn.isotonic import IsotonicRegression
+from sklearn.metrics import accuracy_score, r2_score
+from sklearn.model_selection import train_test_split
+from sklearn.utils.validation import check_array, check_consistent_length, check_is_fitted, check_X_y
+
+from ._affine import AffineSeparator
+from ._clqr import CoherentLinearQuantileRegressor
+from ._feature_maps import KernelApproximatingFeatureMap, OrthogonalRandomFourierFeatures
+
+_DEVICE_STATE = "_device_state"
+
+
+def _is_frame(obj) -> bool:
+    return hasattr(obj, "dtypes") and hasattr(obj, "index")
+
+
+def _clip_correct_side(res: np.ndarray, y: np.ndarray) -> None:
+    res[(y > 0) & (res > 0)] = 0
+    res[(y < 0) & (res < 0)] = 0
+
+
+class NeoLSSVM(BaseEstimator):
+    """Neo LS-SVM (primal random-feature or dual kernel least-squares SVM with closed-form LOO tuning)."""
+
+    def __init__(
+        self,
+        *,
+        primal_feature_map: KernelApproximatingFeatureMap | Literal["auto"] = "auto",
+        dual_feature_map: AffineSeparator | Literal["auto"] = "auto",
+        dual: bool | Literal["auto"] = "auto",
+        estimator_type: Literal["auto", "classifier", "regressor"] = "auto",
+        random_state: int | np.random.RandomState | None = 42,
+    ) -> None:
+        self.primal_feature_map = primal_feature_map
+        self.dual_feature_map = dual_feature_map
+        self.dual = dual
+        self.random_state = random_state
+        self.estimator_type = estimator_type
+
+    # ------------------------------------------------------------------------------------------
+    # pickling: device buffers are a cache, never part of the fitted state
+    # ------------------------------------------------------------------------------------------
+    def __getstate__(self):
+        state = super().__getstate__() if hasattr(super(), "__getstate__") else self.__dict__.copy()
+        state = dict(state)
+        state.pop(_DEVICE_STATE, None)
+        return state
+
+    # ------------------------------------------------------------------------------------------
+    # device helpers
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _gpu():
+        import torch
+
+        from . import _lib
+
+        ctx = _lib.context()
+        return ctx, torch, torch.device("cuda", ctx.device)
+
+    def _primal_device_state(self):
+        """Device copies of what predict needs (rebuilt lazily, e.g. after unpickling)."""
+        st = self.__dict__.get(_DEVICE_STATE)
+        if st is not None and st.get("kind") == "primal":
+            return st
+        ctx, torch, dev = self._gpu()
+        shift, W = self.primal_feature_map_.device_weights(self.n_features_in_)
+        m = W.shape[1] + 1
+        U = torch.from_numpy(np.triu(np.asarray(self.L_[0], dtype=np.complex128))).to(dev)
+        # (γC + A)⁻¹ = U⁻¹ U⁻ᴴ: the variance kernel takes B = U⁻¹ with unit weights.
+        B = torch.linalg.solve_triangular(U, torch.eye(m, dtype=torch.complex128, device=dev), upper=True)
+        st = {
+            "kind": "primal",
+            "shift": torch.from_numpy(shift).to(dev),
+            "W": torch.from_numpy(W).to(dev),
+            "beta": torch.from_numpy(np.asarray(self.β̂_, dtype=np.complex128)).to(dev),
+            "B": B.contiguous(),
+            "w": torch.ones(m, dtype=torch.float64, device=dev),
+        }
+        self.__dict__[_DEVICE_STATE] = st
+        return st
+
+    # ------------------------------------------------------------------------------------------
+    # solvers
+    # ------------------------------------------------------------------------------------------
+    def _optimize_β̂_γ(self, X, y, s):
+        """GPU counterpart of the reference's `_optimize_β̂_γ` (:77-189); takes X, not the materialised φ."""
+        from . import _primal
+
+        ctx, torch, dev = self._gpu()
+        shift, W = self.primal_feature_map_.device_weights(X.shape[1])
+        dt = X.dtype
+        s64 = np.asarray(s, dtype=np.float64)
+        s_norm = s64 / np.sum(s64)  # :110
+        Xd = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).to(dev)
+        yd = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float64)).to(dev)
+        sd = torch.from_numpy(s_norm).to(dev)
+        shd, Wd = torch.from_numpy(shift).to(dev), torch.from_numpy(W).to(dev)
+        fit = _primal.primal_fit(Xd, yd, sd, shd, Wd, self._estimator_type == "classifier", ctx=ctx)
+        cdt = np.complex64 if dt == np.float32 else np.complex128
+        self.γs_ = fit.gammas.astype(dt)
+        self.loo_errors_γs_ = fit.loo_errors.astype(dt)
+        rows = {k: v.cpu().numpy() for k, v in fit.rows.items()}
+        self.loo_residuals_ = rows["loo_residuals"].astype(dt)
+        self.loo_ŷ_ = (np.asarray(y, dtype=np.float64) + rows["loo_residuals"]).astype(dt)
+        self.loo_leverage_ = rows["loo_leverage"].astype(dt)
+        self.loo_error_ = self.loo_errors_γs_[fit.opt]
+        self.loo_score_ = fit.loo_score
+        self.L_ = (fit.U.cpu().numpy().astype(cdt), False)  # scipy.linalg.cho_factor layout (:177)
+        self.residuals_ = rows["residuals"].astype(dt)
+        self.loo_std_ = rows["loo_std"].astype(dt)
+        m = W.shape[1] + 1
+        self.__dict__[_DEVICE_STATE] = {
+            "kind": "primal", "shift": shd, "W": Wd, "beta": fit.beta, "B": fit.Q,
+            "w": _primal.variance_weights(fit.lam, fit.inv_c, fit.gamma), "m": m,
+        }
+        return fit.beta.cpu().numpy().astype(cdt), self.γs_[fit.opt]
+
+    def _optimize_α̂_γ(self, X, y, s, ρ: float = 1.0):
+        """GPU counterpart of the reference's `_optimize_α̂_γ` (:191-325) for ρ = 1."""
+        from . import _dual
+
+        assert ρ == 1.0, "only the default ρ = 1 of the reference is supported"
+        return _dual.fit_into(self, X, y, s)
+
+    # ------------------------------------------------------------------------------------------
+    # fit
+    # ------------------------------------------------------------------------------------------
+    def fit(self, X, y, sample_weight=None) -> "NeoLSSVM":
+        """Fit this predictor."""
+        X, y = check_X_y(X, y, dtype=(np.float64, np.float32), ensure_min_samples=2)
+        y = np.ravel(np.asarray(y))
+        self.n_features_in_ = X.shape[1]
+        self.y_dtype_ = y.dtype
+        sample_weight_ = (
+            np.ones(y.shape, X.dtype) if sample_weight is None else np.ravel(np.asarray(sample_weight)).astype(X.dtype)
+        )
+        check_consistent_length(y, sample_weight_)
+        # Task type from the target (:351-373).
+        distinct = np.unique(y)
+        inferred = None
+        if len(distinct) == 2:  # noqa: PLR2004
+            inferred = "classifier"
+        elif any(np.issubdtype(y.dtype, t) for t in (np.number, np.datetime64, np.timedelta64)):
+            inferred = "regressor"
+        self._estimator_type = inferred if self.estimator_type == "auto" else self.estimator_type
+        if self._estimator_type == "classifier":
+            self.classes_ = distinct
+            y_ = np.ones(y.shape, dtype=X.dtype)
+            y_[y == self.classes_[0]] = -1
+        elif self._estimator_type == "regressor":
+            y_ = y.astype(X.dtype)
+        else:
+            raise ValueError("Target type not supported")
+        self.dual_ = X.shape[0] <= 1024 if self.dual == "auto" else self.dual  # noqa: PLR2004
+        self.primal_ = not self.dual_
+        self.__dict__.pop(_DEVICE_STATE, None)
+        if self.primal_:
+            self.primal_feature_map_ = clone(
+                OrthogonalRandomFourierFeatures() if self.primal_feature_map == "auto" else self.primal_feature_map
+            )
+            self.primal_feature_map_.fit(X, y_, sample_weight_)
+            self.β̂_, self.γ_ = self._optimize_β̂_γ(X, y_, sample_weight_)
+        else:
+            keep = sample_weight_ > 0
+            X, y_, sample_weight_ = X[keep], y_[keep], sample_weight_[keep]
+            self.dual_feature_map_ = clone(AffineSeparator() if self.dual_feature_map == "auto" else self.dual_feature_map)
+            self.dual_feature_map_.fit(X, y_, sample_weight_)
+            self.X_ = self.dual_feature_map_.transform(X)
+            self.α̂_, self.γ_ = self._optimize_α̂_γ(self.X_, y_, sample_weight_)
+        # Isotonic probability calibration on the LOO predictions (:406-412).
+        if self._estimator_type == "classifier":
+            self.predict_proba_calibrator_ = IsotonicRegression(out_of_bounds="clip", y_min=0, y_max=1, increasing=True)
+            target = np.zeros_like(y_)
+            target[y_ == np.max(y_)] = 1.0
+            self.predict_proba_calibrator_.fit(self.loo_ŷ_, target, sample_weight_)
+        # Two-level conformal calibration split of the LOO predictions (:414-430).
+        (
+            self.nonconformity_calib_l1_, self.nonconformity_calib_l2_,
+            self.ŷ_calib_l1_, self.ŷ_calib_l2_,
+            self.residuals_calib_l1_, self.residuals_calib_l2_,
+            self.sample_weight_calib_l1_, self.sample_weight_calib_l2_,
+        ) = train_test_split(
+            self.loo_std_, self.loo_ŷ_, self.loo_residuals_, sample_weight_,
+            train_size=min(1440, max(1024, (X.shape[0] * 2) // 3), X.shape[0] - 1),
+            random_state=self.random_state,
+        )
+        self.conformal_l1_ = {"Δŷ": {}, "Δŷ/ŷ": {}}
+        self.conformal_l2_ = {"Δŷ": {}, "Δŷ/ŷ": {}}
+        return self
+
+    # ------------------------------------------------------------------------------------------
+    # point predictions and predictive standard deviation (one fused device pass over φ(x))
+    # ------------------------------------------------------------------------------------------
+    def _decision_and_std(self, X: np.ndarray, want_decision: bool, want_std: bool):
+        dt = X.dtype
+        ctx, torch, dev = self._gpu()
+        if self.primal_:
+            st = self._primal_device_state()
+            Xd = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).to(dev)
+            yhat, sigma = ctx.primal_predict(
+                Xd, st["shift"], st["W"], beta=st["beta"] if want_decision else None,
+                B=st["B"] if want_std else None, w=st["w"] if want_std else None, want_std=want_std,
+            )
+        else:
+            from . import _dual
+
+            yhat, sigma = _dual.predict(self, X, want_decision, want_std)
+        yhat = yhat.cpu().numpy().astype(dt) if yhat is not None else None
+        sigma = sigma.cpu().numpy().astype(dt) if sigma is not None else None
+        return yhat, sigma
+
+    def decision_function(self, X):
+        """Evaluate the prediction function ŷ(x) (:655-681)."""
+        check_is_fitted(self)
+        X, X_df = check_array(X, dtype=(np.float64, np.float32)), X
+        ŷ, _ = self._decision_and_std(X, True, False)
+        if _is_frame(X_df):
+            try:
+                import pandas as pd
+            except ImportError:
+                pass
+            else:
+                return pd.Series(ŷ, index=X_df.index)
+        return ŷ
+
+    def predict_std(self, X):
+        """Bayesian estimate of the predictive standard deviation (:452-487)."""
+        check_is_fitted(self)
+        X, X_df = check_array(X, dtype=(np.float64, np.float32)), X
+        _, σ = self._decision_and_std(X, False, True)
+        if _is_frame(X_df):
+            try:
+                import pandas as pd
+            except ImportError:
+                pass
+            else:
+                return pd.Series(σ, index=X_df.index)
+        return σ
+
+    # ------------------------------------------------------------------------------------------
+    # conformal quantiles
+    # ------------------------------------------------------------------------------------------
+    def _lazily_fit_conformal_predictor(self, target_type: str, quantiles):
+        """Level-1 coherent quantile regressor + level-2 conformal bias, cached per quantile tuple (:489-532)."""
+        quantiles = np.asarray(quantiles)
+        key = tuple(quantiles)
+        if key in self.conformal_l1_[target_type]:
+            return self.conformal_l1_[target_type][key], self.conformal_l2_[target_type][key]
+        relative = "/ŷ" in target_type
+        regressor = self._estimator_type == "regressor"
+        eps = np.finfo(self.ŷ_calib_l1_.dtype).eps
+
+        def design(nonconformity, ŷ):
+            cols = [nonconformity[:, np.newaxis]]
+            if regressor:
+                cols.append(np.abs(ŷ[:, np.newaxis]))
+            return np.hstack(cols) if len(cols) > 1 else cols[0]
+
+        def target(residuals, ŷ):
+            return -residuals / (np.maximum(np.abs(ŷ), eps) if relative else 1)
+
+        X1, y1 = design(self.nonconformity_calib_l1_, self.ŷ_calib_l1_), target(self.residuals_calib_l1_, self.ŷ_calib_l1_)
+        cqr = CoherentLinearQuantileRegressor(quantiles=quantiles)
+        cqr.fit(X1, y1, sample_weight=self.sample_weight_calib_l1_)
+        self.conformal_l1_[target_type][key] = cqr
+        bias = np.zeros(quantiles.shape, dtype=self.ŷ_calib_l1_.dtype)
+        if len(self.ŷ_calib_l2_) >= 128:  # noqa: PLR2004
+            X2, y2 = design(self.nonconformity_calib_l2_, self.ŷ_calib_l2_), target(self.residuals_calib_l2_, self.ŷ_calib_l2_)
+            pred2 = cqr.predict(X2)
+            clip = cqr.intercept_clip(np.vstack([X1, X2]), np.hstack([y1, y2]))
+            for j, q in enumerate(quantiles):
+                bias[j] = np.clip(np.quantile(y2 - pred2[:, j], q), clip[0, j], clip[1, j])
+        self.conformal_l2_[target_type][key] = bias
+        return cqr, bias
+
+    def predict_quantiles(self, X, *, quantiles=(0.025, 0.5, 0.975), priority: Literal["accuracy", "coverage"] = "accuracy"):
+        """Predict conformally calibrated quantiles (:554-624)."""
+        check_is_fitted(self)
+        X, X_df = check_array(X, dtype=(np.float64, np.float32)), X
+        ŷ, σ = self._decision_and_std(X, True, True)  # φ(x) is generated once for both
+        cqr_abs, bias_abs = self._lazily_fit_conformal_predictor("Δŷ", quantiles)
+        cqr_rel, bias_rel = self._lazily_fit_conformal_predictor("Δŷ/ŷ", quantiles)
+        if priority == "coverage":  # only allow the quantiles to move outwards; mutates the cache as the reference does
+            q = np.asarray(quantiles)
+            for bias in (bias_abs, bias_rel):
+                bias[0.5 <= q] = np.maximum(bias[0.5 <= q], 0)
+                bias[q <= 0.5] = np.minimum(bias[q <= 0.5], 0)
+        regressor = self._estimator_type == "regressor"
+        ctx, torch, dev = self._gpu()
+
+        def up(a):
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+
+        iso = self.predict_proba_calibrator_ if not regressor else None
+        out = ctx.quantile_epilogue(
+            up(ŷ), up(σ), up(cqr_abs.β_), up(cqr_rel.β_), up(bias_abs), up(bias_rel), regressor,
+            up(iso.X_thresholds_) if iso is not None else None, up(iso.y_thresholds_) if iso is not None else None,
+        )
+        ŷ_quantiles = out.cpu().numpy().astype(X.dtype)
+        if regressor and not np.issubdtype(self.y_dtype_, np.integer):
+            ŷ_quantiles = ŷ_quantiles.astype(self.y_dtype_)
+        if _is_frame(X_df):
+            try:
+                import pandas as pd
+            except ImportError:
+                pass
+            else:
+                if regressor:
+                    frame = pd.DataFrame(ŷ_quantiles, index=X_df.index, columns=quantiles)
+                else:
+                    neg = pd.DataFrame(ŷ_quantiles[:, :, 0], index=X_df.index, columns=quantiles)
+                    pos = pd.DataFrame(ŷ_quantiles[:, :, 1], index=X_df.index, columns=quantiles)
+                    frame = pd.concat([neg, pos], axis=0, keys=self.classes_, names=["class", X_df.index.name])
+                frame.columns.name = "quantile"
+                return frame
+        return ŷ_quantiles
+
+    def predict_interval(self, X, *, coverage: float = 0.95):
+        """Predict conformally calibrated intervals (:636-645)."""
+        lb = (1 - coverage) / 2
+        return self.predict_quantiles(X, quantiles=(lb, 1 - lb), priority="coverage")
+
+    # ------------------------------------------------------------------------------------------
+    # predict / predict_proba / score
+    # ------------------------------------------------------------------------------------------
+    def predict(self, X, *, coverage: float | None = None, quantiles=None):
+        """Predict on a given dataset (:719-762)."""
+        assert coverage is None or quantiles is None
+        if coverage is not None:
+            return self.predict_interval(X, coverage=coverage)
+        if quantiles is not None:
+            return self.predict_quantiles(X, quantiles=quantiles)
+        check_is_fitted(self)
+        X, X_df = check_array(X, dtype=(np.float64, np.float32)), X
+        ŷ = self.decision_function(X)
+        if self._estimator_type == "classifier":
+            side = np.sign(ŷ)
+            side[side == 0] = -1  # ties go to the negative class
+            ŷ = self.classes_[((side + 1) // 2).astype(np.intp)]
+        if not np.issubdtype(self.y_dtype_, np.integer):
+            ŷ = ŷ.astype(self.y_dtype_)
+        if _is_frame(X_df):
+            try:
+                import pandas as pd
+            except ImportError:
+                pass
+            else:
+                return pd.Series(ŷ, index=X_df.index)
+        return ŷ
+
+    def predict_proba(self, X):
+        """Isotonically calibrated class probabilities (classifier) or the point prediction (regressor) (:772-799)."""
+        check_is_fitted(self)
+        X, X_df = check_array(X, dtype=(np.float64, np.float32)), X
+        ŷ = self.decision_function(X)
+        if self._estimator_type == "classifier":
+            p = self.predict_proba_calibrator_.transform(ŷ)
+            proba = np.hstack([1 - p[:, np.newaxis], p[:, np.newaxis]])
+        else:
+            proba = ŷ if np.issubdtype(self.y_dtype_, np.integer) else ŷ.astype(self.y_dtype_)
+        if _is_frame(X_df):
+            try:
+                import pandas as pd
+            except ImportError:
+                pass
+            else:
+                if self._estimator_type == "regressor":
+                    return pd.Series(proba, index=X_df.index)
+                return pd.DataFrame(proba, index=X_df.index, columns=self.classes_)
+        return proba
+
+    def score(self, X, y, sample_weight=None) -> float:
+        """Accuracy (classifier) or R² (regressor) (:801-817)."""
+        ŷ = self.predict(X)
+        if self._estimator_type == "classifier":
+            return accuracy_score(y, ŷ, sample_weight=sample_weight)
+        return r2_score(np.asarray(y).astype(np.float64), np.asarray(ŷ).astype(np.float64), sample_weight=sample_weight)
+
+    def _more_tags(self) -> dict[str, Any]:
+        return {"binary_only": True, "requires_y": True}
+
+    def __sklearn_tags__(self):
+        tags = super().__sklearn_tags__()
+        tags.target_tags.required = True
+        est = getattr(self, "_estimator_type", None) or (self.estimator_type if self.estimator_type != "auto" else None)
+        if est in ("classifier", "regressor"):
+            tags.estimator_type = est
+        if est == "classifier":
+            from sklearn.utils import ClassifierTags
+
+            tags.classifier_tags = ClassifierTags(multi_class=False)
+        elif est == "regressor":
+            from sklearn.utils import RegressorTags
+
+            tags.regressor_tags = RegressorTags()
+        return tags

@@ -1,0 +1,168 @@
+"""ECDF quantisation of a numeric vector into variable-width bins (host pre-pass utility).
+
+Behavioural mirror of /root/reference/src/neo_ls_svm/_quantizer.py: bins are grown greedily from both
+ends of the empirical CDF; a bin is closed as soon as a straight line through it would deviate from the
+ECDF by more than `max_bin_error` samples, or it holds more than `max_bin_size` samples
+(`_next_knot` :18-44, `_prev_knot` :47-73, `hist_quantized_ecdf` :104-177).  The target's bin index
+drives the supervised normaliser / separator.  Out of the GPU hot path's scope.
+"""
+
+from __future__ import annotations
+
+from typing import Any
+
+import numpy as np
+from sklearn.base import BaseEstimator, TransformerMixin
+from sklearn.utils.validation import check_array
+
+
+def _grow_bin_py(x, y, knot, max_err, max_size, forward):
+    """Grow one bin from `knot` (forward: to the right; else to the left).
+
+    Returns (stop_knot, samples_in_bin).  x: knot positions with -inf/+inf sentinels; y: cumulative
+    counts with 0 / int-max sentinels.
+    """
+    lo_slope, hi_slope = 0.0, np.inf
+    stop, count = knot, 0
+    if forward:
+        for stop in range(knot + 1, len(x)):
+            count = int(y[stop - 1] - y[knot - 1] if knot > 0 else y[stop - 1])
+            if count > max_size:
+                break
+            if stop == knot + 1:
+                continue
+            dx, dy = x[stop - 1] - x[knot], y[stop - 1] - y[knot]
+            hi_slope = min(hi_slope, (dy + max_err) / dx)
+            lo_slope = max(lo_slope, (dy - max_err) / dx)
+            slope = dy / dx
+            if not (lo_slope <= slope <= hi_slope):
+                break
+    else:
+        for stop in range(knot - 1, -1, -1):
+            count = int(y[knot - 1] - y[stop - 1] if stop > 0 else y[knot - 1])
+            if count > max_size:
+                break
+            if knot == stop + 1:
+                continue
+            dx, dy = x[knot - 1] - x[stop], y[knot - 1] - y[stop]
+            hi_slope = min(hi_slope, (dy + max_err) / dx)
+            lo_slope = max(lo_slope, (dy - max_err) / dx)
+            slope = dy / dx
+            if not (lo_slope <= slope <= hi_slope):
+                break
+    return stop, count
+
+
+try:
+    import numba
+
+    _grow_bin = numba.jit(nopython=True, nogil=True, fastmath=True, cache=False)(_grow_bin_py)
+except Exception:  # noqa: BLE001
+    _grow_bin = _grow_bin_py
+
+
+def hist_quantized_ecdf(
+    x: np.ndarray,
+    *,
+    density: bool = False,
+    max_bin_error: float = 0.0125,
+    max_bin_size: float = 0.125,
+    merge_bin_size: float = 0.025,
+):
+    """Variable-width histogram of `x` obtained by quantising its ECDF.  Returns (hist, bin_edges)."""
+    n = len(x)
+    err_abs, size_abs, merge_abs = int(max_bin_error * n), int(max_bin_size * n), int(merge_bin_size * n)
+    values, counts = np.unique(x, return_counts=True)
+    cum = np.cumsum(counts)
+    xs = np.insert(np.append(values, np.inf), 0, -np.inf)
+    ys = np.insert(np.append(cum, np.iinfo(cum.dtype).max), 0, 0)
+    lo, hi = 1, len(xs) - 1
+    edges_lo, edges_hi = [values[0]], [values[-1]]
+    hist_lo: list = []
+    hist_hi: list = []
+    hist, edges = [], []
+    while lo < hi:
+        lo_before, hi_before = lo, hi
+        lo, n_lo = _grow_bin(xs, ys, lo, err_abs, size_abs, True)
+        hi, n_hi = _grow_bin(xs, ys, hi, err_abs, size_abs, False)
+        hist_lo.append(n_lo)
+        hist_hi.insert(0, n_hi)
+        edges_lo.append((xs[lo] + xs[lo - 1]) / 2 if lo > 0 else xs[lo])
+        edges_hi.insert(0, (xs[hi] + xs[hi - 1]) / 2 if hi > 0 else xs[hi])
+        if lo == hi:  # the two fronts met exactly
+            edges = edges_lo + edges_hi[1:]
+            hist = hist_lo + hist_hi
+            break
+        if lo > hi:  # the fronts crossed: the last two bins overlap, fuse them
+            middle = cum[-1] - np.sum(hist_lo[:-1]) - np.sum(hist_hi[1:])
+            hist = hist_lo[:-1] + [middle] + hist_hi[1:]
+            edges = edges_lo[:-1] + edges_hi[1:]
+            break
+        if ys[hi - 1] - ys[lo - 1] <= merge_abs:  # small remainder: split it between the neighbours
+            mid_lo = int(np.floor((lo + hi) / 2))
+            mid_hi = int(np.ceil((lo + hi) / 2))
+            centre = (xs[mid_lo] + xs[mid_hi]) / 2
+            hist = (
+                hist_lo[:-1]
+                + [ys[mid_lo] - ys[lo_before - 1]]
+                + [ys[hi_before - 1] - ys[mid_hi - 1]]
+                + hist_hi[1:]
+            )
+            edges = edges_lo[:-1] + [centre] + edges_hi[1:]
+            break
+    fdtype = values.dtype if np.issubdtype(values.dtype, np.floating) else np.float64
+    hist_arr = (np.array(hist) / cum[-1]).astype(fdtype) if density else np.array(hist)
+    return hist_arr, np.array(edges).astype(fdtype)
+
+
+class Quantizer(BaseEstimator, TransformerMixin):
+    """Maps each numeric column to the index of its ECDF-quantised bin (reference :180-243)."""
+
+    def __init__(self, *, max_bin_error: float = 0.0125, max_bin_size: float = 0.125,
+                 append_invfreq: bool = False, dtype: Any = np.intp):
+        self.max_bin_error = max_bin_error
+        self.max_bin_size = max_bin_size
+        self.append_invfreq = append_invfreq
+        self.dtype = dtype
+        if append_invfreq and not np.issubdtype(dtype, np.floating):
+            self.dtype = np.float32
+
+    def fit(self, X, y=None):
+        X = check_array(X)
+        self.n_features_in_ = X.shape[1]
+        self.X_hist_, self.X_bin_edges_ = [], []
+        for j in range(X.shape[1]):
+            hist, edges = hist_quantized_ecdf(
+                X[:, j], density=False, max_bin_error=self.max_bin_error, max_bin_size=self.max_bin_size
+            )
+            self.X_hist_.append(hist)
+            self.X_bin_edges_.append(edges)
+        return self
+
+    def transform(self, X):
+        ncol = X.shape[1]
+        out = np.empty((X.shape[0], (1 + self.append_invfreq) * ncol), dtype=self.dtype)
+        for j in range(ncol):
+            edges = self.X_bin_edges_[j]
+            code = np.clip(np.searchsorted(edges, X[:, j], side="right") - 1, 0, len(edges) - 2)
+            out[:, j] = code
+            if self.append_invfreq:
+                out[:, ncol + j] = 1 / len(self.X_hist_[j]) / self.X_hist_[j][code]
+        return out
+
+
+def sample_bins_quantized_ecdf(x: np.ndarray, **kwargs: Any) -> np.ndarray:
+    """Bin index per sample: the class code if there are few distinct values, else ECDF bins (:246-253)."""
+    distinct, codes = np.unique(x, return_inverse=True)
+    if len(distinct) <= np.ceil(np.sqrt(len(codes))):
+        return codes
+    return Quantizer(dtype=np.intp, **kwargs).fit_transform(codes[:, np.newaxis]).ravel()
+
+
+def sample_weights_quantized_ecdf(x: np.ndarray, **kwargs: Any) -> np.ndarray:
+    """Inverse-frequency sample weights from the same quantisation (:256-264)."""
+    fdtype = x.dtype if np.issubdtype(x.dtype, np.floating) else np.float64
+    distinct, codes, counts = np.unique(x, return_inverse=True, return_counts=True)
+    if len(distinct) <= np.ceil(np.sqrt(len(codes))):
+        return counts[codes] / np.sum(counts)
+    return Quantizer(append_invfreq=True, dtype=fdtype, **kwargs).fit_transform(codes[:, np.newaxis])[:, 1]

@@ -38,23 +38,31 @@ def make_churn_rows(n: int, d: int = 70, n_informative: int = 20, flip_y: float 
     return np.ascontiguousarray(X), np.ascontiguousarray(y)
 
 
-def fast_regression_rows(n: int, d: int, n_informative: int, noise: float = 1.0, seed: int = 0):
+BLOCK_ROWS = 1 << 18
+
+
+def fast_regression_rows(n: int, d: int, n_informative: int, noise: float = 1.0, seed: int = 0,
+                         row_begin: int = 0, row_end: int | None = None):
     """Streaming equivalent of `make_regression` for multi-million-row benchmark inputs.
 
-    Same distribution (standard-normal X, sparse linear ground truth with coefficients
-    100*U(0,1), Gaussian noise) but generated with `numpy.random.Generator` in row blocks so that a
-    4M x 64 matrix takes seconds and no more than its own size in RAM.
+    Same distribution (standard-normal X, sparse linear ground truth with coefficients 100*U(0,1),
+    Gaussian noise).  Rows are generated in blocks of 2^18, each block from its own
+    `numpy.random.Generator` seeded by (seed, block), so any rank can materialise exactly its own row
+    range [row_begin, row_end) of the same global dataset without generating the rest.
     """
-    rng = np.random.default_rng(seed)
+    row_end = n if row_end is None else row_end
     coef = np.zeros(d)
-    coef[:n_informative] = 100.0 * rng.random(n_informative)
-    X = np.empty((n, d), dtype=np.float64)
-    y = np.empty(n, dtype=np.float64)
-    step = 1 << 18
-    for i0 in range(0, n, step):
-        i1 = min(n, i0 + step)
-        rng.standard_normal(out=X[i0:i1])
-        y[i0:i1] = X[i0:i1] @ coef + noise * rng.standard_normal(i1 - i0)
+    coef[:n_informative] = 100.0 * np.random.default_rng([seed, 1 << 30]).random(n_informative)
+    X = np.empty((row_end - row_begin, d), dtype=np.float64)
+    y = np.empty(row_end - row_begin, dtype=np.float64)
+    for blk in range(row_begin // BLOCK_ROWS, (row_end + BLOCK_ROWS - 1) // BLOCK_ROWS):
+        b0, b1 = blk * BLOCK_ROWS, min(n, (blk + 1) * BLOCK_ROWS)
+        rng = np.random.default_rng([seed, blk])
+        Xb = rng.standard_normal((b1 - b0, d))
+        yb = Xb @ coef + noise * rng.standard_normal(b1 - b0)
+        lo, hi = max(b0, row_begin), min(b1, row_end)
+        X[lo - row_begin : hi - row_begin] = Xb[lo - b0 : hi - b0]
+        y[lo - row_begin : hi - row_begin] = yb[lo - b0 : hi - b0]
     return X, y
 
 

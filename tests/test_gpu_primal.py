@@ -1,0 +1,213 @@
+"""Parity of the CUDA primal hot path (through the C ABI) against the reference's golden outputs and
+the CPU oracle.  Tolerances are the north star's: 1e-9 relative on β̂ / LOO residuals / γ (same index
+required), 1e-7 on predictions and quantiles."""
+
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rel_err  # noqa: E402
+from neo_ls_svm_b200.datasets import load_case, make_regression_rows
+
+pytestmark = pytest.mark.gpu
+
+TOL_FIT = 1e-9  # β̂, LOO residuals, LOO error curve
+TOL_PRED = 1e-7  # predictions, std, quantiles
+
+PRIMAL = ["reg_small", "clf_small", "c1", "c2_small", "c3_small"]
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+
+    from neo_ls_svm_b200 import _lib, _primal
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    ctx = _lib.Context(0)
+
+    def dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64 if not np.iscomplexobj(a) else np.complex128)).cuda()
+
+    return ctx, dev, _primal, torch
+
+
+def _case(name, g):
+    X, y, sw, Xt, _ = load_case(name)
+    classifier = bool(g["classifier"])
+    y_ = np.where(y == np.unique(y)[0], -1.0, 1.0) if classifier else y.astype(np.float64)
+    s = np.ones(len(y)) if sw is None else sw.astype(np.float64)
+    shift = g["shift"].ravel()
+    W = g["A_map"] / g["scale"].reshape(-1, 1)
+    return X, y_, s / s.sum(), Xt, classifier, shift, W
+
+
+@pytest.mark.parametrize("name", PRIMAL)
+@pytest.mark.parametrize("chunk", [640, 32768])
+def test_primal_fit_matches_reference(name, chunk, golden, gpu):
+    ctx, dev, _primal, torch = gpu
+    g = golden(name)
+    X, y_, s, Xt, classifier, shift, W = _case(name, g)
+    ctx.set_chunk_rows(chunk)
+    fit = _primal.primal_fit(dev(X), dev(y_), dev(s), dev(shift), dev(W), classifier, ctx=ctx)
+    assert fit.opt == int(g["opt"]), "selected γ index must equal the reference's"
+    assert fit.gamma == float(g["gamma"])
+    assert rel_err(fit.loo_errors, g["loo_errors"]) < TOL_FIT
+    assert rel_err(fit.beta.cpu().numpy(), g["beta"]) < TOL_FIT
+    assert rel_err(fit.beta_eig.cpu().numpy(), g["beta"]) < TOL_FIT
+    assert rel_err(fit.rows["loo_residuals"].cpu().numpy(), g["loo_residuals"]) < TOL_FIT
+    assert rel_err(fit.rows["loo_leverage"].cpu().numpy(), g["loo_leverage"]) < TOL_FIT
+    assert rel_err(fit.rows["residuals"].cpu().numpy(), g["residuals"]) < TOL_FIT
+    assert rel_err(fit.rows["loo_std"].cpu().numpy(), g["loo_std"]) < TOL_FIT
+    assert abs(fit.loo_score - float(g["loo_score"])) < TOL_FIT
+    U = fit.U.cpu().numpy()
+    probe = np.cos(np.arange(U.shape[0]) * 0.7) + 0.25
+    assert rel_err(np.diag(U), g["L_diag"]) < TOL_FIT
+    assert rel_err(np.triu(U) @ probe, g["L_probe"]) < TOL_FIT
+    # predict / predict_std via the eigenbasis and via the inverse Cholesky factor
+    w = _primal.variance_weights(fit.lam, fit.inv_c, fit.gamma)
+    yhat, sigma = ctx.primal_predict(dev(Xt), dev(shift), dev(W), beta=fit.beta, B=fit.Q, w=w, want_std=True)
+    assert rel_err(yhat.cpu().numpy(), g["decision"]) < TOL_PRED
+    assert rel_err(sigma.cpu().numpy(), g["std"]) < TOL_PRED
+    m = U.shape[0]
+    Uinv = torch.linalg.solve_triangular(torch.triu(fit.U), torch.eye(m, dtype=torch.complex128, device="cuda"), upper=True)
+    _, sigma2 = ctx.primal_predict(dev(Xt), dev(shift), dev(W), B=Uinv.contiguous(),
+                                   w=torch.ones(m, dtype=torch.float64, device="cuda"), want_std=True)
+    assert rel_err(sigma2.cpu().numpy(), g["std"]) < TOL_PRED
+
+
+@pytest.mark.parametrize("name", ["reg_small", "c3_small"])
+def test_feature_map_matches_oracle(name, golden, gpu):
+    from oracle import neo_oracle as orc
+
+    ctx, dev, _, _ = gpu
+    g = golden(name)
+    X, *_ , shift, W = _case(name, g)
+    ctx.set_chunk_rows(512)
+    phi = ctx.feature_map(dev(X[:1300]), dev(shift), dev(W)).cpu().numpy()
+    ref = orc.feature_map(X[:1300], g["shift"], g["scale"], g["A_map"])
+    assert rel_err(phi, ref) < 1e-13
+    assert rel_err(phi[:16], g["phi_head"]) < 1e-13
+    assert np.all(phi[:, -1] == 1.0)
+
+
+@pytest.mark.parametrize("n,d,D", [(130, 3, 40), (1000, 7, 100), (2049, 5, 129), (777, 9, 64)])
+def test_ragged_shapes_match_oracle(n, d, D, gpu):
+    """Rows/features/inputs that are not multiples of any tile size, odd d, tail chunks, zero weights."""
+    from oracle import neo_oracle as orc
+
+    ctx, dev, _primal, torch = gpu
+    rng = np.random.default_rng(n + d + D)
+    X = rng.standard_normal((n, d))
+    y = np.sin(X[:, 0]) + 0.3 * rng.standard_normal(n)
+    s = rng.uniform(0.5, 1.5, n)
+    s[:: 17] = 0.0  # zero-weight rows stay in the primal solve (only the dual path drops them)
+    shift = rng.standard_normal(d) * 0.1
+    scale = rng.uniform(0.5, 2.0, (1, d))
+    A_map = rng.standard_normal((d, D)) * 0.7
+    ref = orc.primal_fit_chunked(X, y, s, shift, scale, A_map, classifier=False, chunk=500)
+    ctx.set_chunk_rows(256)
+    W = A_map / scale.T
+    fit = _primal.primal_fit(dev(X), dev(y), dev(s / s.sum()), dev(shift), dev(W), False, ctx=ctx)
+    assert rel_err(fit.A.cpu().numpy(), ref["A"]) < 1e-12
+    assert rel_err(fit.b.cpu().numpy(), ref["b"]) < 1e-12
+    assert rel_err(fit.lam.cpu().numpy(), ref["lam"]) < 1e-11
+    assert fit.opt == ref["opt"]
+    assert rel_err(fit.loo_errors, ref["loo_errors"]) < TOL_FIT
+    assert rel_err(fit.beta.cpu().numpy(), ref["beta"]) < TOL_FIT
+    assert rel_err(fit.rows["loo_residuals"].cpu().numpy(), ref["loo_residuals"]) < TOL_FIT
+    assert rel_err(fit.rows["loo_std"].cpu().numpy(), ref["loo_std"]) < TOL_FIT
+
+
+def test_tma_pipeline_equals_plain_loader(golden, gpu):
+    """The TMA/mbarrier pipeline and the bounds-checked reference loader must agree bitwise."""
+    from neo_ls_svm_b200 import _lib
+
+    ctx, dev, _primal, _ = gpu
+    g = golden("clf_small")
+    X, y_, s, Xt, classifier, shift, W = _case("clf_small", g)
+    os.environ["NLS_NO_TMA"] = "1"
+    try:
+        plain = _lib.Context(0)
+    finally:
+        os.environ["NLS_NO_TMA"] = "0"
+    ctx.set_chunk_rows(512)
+    plain.set_chunk_rows(512)
+    A1, b1 = ctx.primal_gram(dev(X), dev(y_), dev(s), dev(shift), dev(W))
+    A2, b2 = plain.primal_gram(dev(X), dev(y_), dev(s), dev(shift), dev(W))
+    assert np.array_equal(A1.cpu().numpy(), A2.cpu().numpy())
+    assert np.array_equal(b1.cpu().numpy(), b2.cpu().numpy())
+
+
+def test_determinism(golden, gpu):
+    """Fixed-order reductions: two runs are bitwise identical (the reference is)."""
+    ctx, dev, _primal, _ = gpu
+    g = golden("reg_small")
+    X, y_, s, Xt, classifier, shift, W = _case("reg_small", g)
+    ctx.set_chunk_rows(512)
+    f1 = _primal.primal_fit(dev(X), dev(y_), dev(s), dev(shift), dev(W), classifier, ctx=ctx)
+    f2 = _primal.primal_fit(dev(X), dev(y_), dev(s), dev(shift), dev(W), classifier, ctx=ctx)
+    assert np.array_equal(f1.loo_errors, f2.loo_errors)
+    assert np.array_equal(f1.beta.cpu().numpy(), f2.beta.cpu().numpy())
+    assert np.array_equal(f1.rows["loo_residuals"].cpu().numpy(), f2.rows["loo_residuals"].cpu().numpy())
+
+
+def test_large_n_properties(gpu):
+    """At a size the reference cannot hold (n = 300k, m = 1025): invariants that do not need an oracle."""
+    ctx, dev, _primal, torch = gpu
+    n, d, D = 300_000, 16, 1024
+    X, y = make_regression_rows(n, d, n_informative=8, noise=5.0)
+    rng = np.random.default_rng(0)
+    W = rng.standard_normal((d, D)) * 0.5
+    shift = np.zeros(d)
+    s = np.full(n, 1.0 / n)
+    ctx.set_chunk_rows(32768)
+    Xd, yd, sd, shd, Wd = dev(X), dev(y), dev(s), dev(shift), dev(W)
+    fit = _primal.primal_fit(Xd, yd, sd, shd, Wd, False, ctx=ctx)
+    A = fit.A
+    assert torch.allclose(A, A.conj().T, rtol=0, atol=0), "A must be exactly Hermitian"
+    # trace(A) = Σ s_i² ||φ_i||² = Σ s_i² (1 + 1) since ||exp(-iz)/√D||² = 1 and the constant feature is 1
+    assert abs(float(A.diagonal().real.sum()) - 2.0 * float((sd * sd).sum())) < 1e-12 * 2.0 / n
+    # eigen-expansion β̂ equals the Cholesky re-solve, and both solve the normal equations
+    assert rel_err(fit.beta_eig.cpu().numpy(), fit.beta.cpu().numpy()) < 1e-8
+    M = A + (fit.gamma / fit.inv_c) * torch.eye(D + 1, dtype=A.dtype, device=A.device)
+    assert rel_err((M @ fit.beta).cpu().numpy(), fit.b.cpu().numpy()) < 1e-9
+    # Σ s_i |loo_i| recomputed from the per-row output equals the swept error at the optimum
+    err = float((sd * fit.rows["loo_residuals"].abs()).sum())
+    assert abs(err - fit.loo_error) < 1e-9 * abs(fit.loo_error)
+    # linearity in y: scaling y scales β̂ and the residuals, and keeps γ
+    fit2 = _primal.primal_fit(Xd, 3.0 * yd, sd, shd, Wd, False, ctx=ctx)
+    assert fit2.opt == fit.opt
+    assert rel_err(fit2.beta.cpu().numpy(), 3.0 * fit.beta.cpu().numpy()) < 1e-9
+    # sharding invariance: two half-shards summed == one shard (what the NCCL all-reduce does)
+    h = n // 2
+    A1, b1 = ctx.primal_gram(Xd[:h].contiguous(), yd[:h].contiguous(), sd[:h].contiguous(), shd, Wd)
+    A2, b2 = ctx.primal_gram(Xd[h:].contiguous(), yd[h:].contiguous(), sd[h:].contiguous(), shd, Wd)
+    assert rel_err((A1 + A2).cpu().numpy(), A.cpu().numpy()) < 1e-12
+
+
+def test_quantile_epilogue_matches_reference(golden, gpu):
+    ctx, dev, _, _ = gpu
+    for name in ("reg_small", "clf_small", "c1"):
+        g = golden(name)
+        classifier = bool(g["classifier"])
+        q = ctx.quantile_epilogue(
+            dev(g["decision"]), dev(g["std"]), dev(g["cqr_abs_beta"]), dev(g["cqr_rel_beta"]), dev(g["cqr_abs_bias"]),
+            dev(g["cqr_rel_bias"]), not classifier,
+            dev(g["iso_x"]) if classifier else None, dev(g["iso_y"]) if classifier else None)
+        assert q.shape == g["quantiles_accuracy"].shape
+        assert rel_err(q.cpu().numpy(), g["quantiles_accuracy"]) < TOL_PRED
+
+
+def test_error_paths(gpu):
+    from neo_ls_svm_b200 import _lib
+
+    ctx, dev, _, torch = gpu
+    X = dev(np.zeros((4, 2)))
+    with pytest.raises(_lib.NlsError):
+        ctx.lib.nls_ctx_set_chunk_rows(ctx.handle, 5) and _lib.check(-1)
+    with pytest.raises(_lib.NlsError):
+        _lib.check(ctx.lib.nls_feature_map(ctx.handle, None, 4, 2, None, None, 8, None))
+    assert b"null" in ctx.lib.nls_last_error()
+    del X
