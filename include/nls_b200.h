@@ -64,6 +64,10 @@ enum { NLS_PROF_FEATURE_MAP = 0, NLS_PROF_GRAM = 1, NLS_PROF_PROJECT = 2, NLS_PR
  * ------------------------------------------------------------------------------------------- */
 int nls_feature_map(nls_ctx* ctx, const double* X, int64_t n, int d, const double* shift,
                     const double* W, int D, double* phi_out);
+/* The affine part alone, z = (x - shift) W as a real n x D matrix: AffineFeatureMap.transform
+ * (_affine_feature_map.py:72-92), used by the dual path (_neo_ls_svm.py:394, :473, :668). */
+int nls_affine_map(nls_ctx* ctx, const double* X, int64_t n, int d, const double* shift,
+                   const double* W, int D, double* Z_out);
 
 /* ---------------------------------------------------------------------------------------------
  * Stage 2 — primal Gram.  Replaces _neo_ls_svm.py:112-114 and :127:
@@ -104,11 +108,15 @@ int nls_cholesky_solve(nls_ctx* ctx, const double* A, int m, double diag_shift, 
  *     sums_out[2, g] = sum_i s_i max(0, |loo_ig| - 1)             (classifier only, :161)
  * v = Q^H b inv_c (:121, :129), inv_c = n_global * m (:117-118).  sums_out: 3 x G, partial over
  * rows: all-reduce(sum); the caller takes the argmin (:159-165).
+ * sigma2_stash (optional, n x G, may be NULL): receives sigma2_i(gamma_g) = sum_k |T_ik|^2 inv_c r[k,g]
+ * for every row and gamma, so that nls_primal_finalize needs no second projection pass (8 KB per
+ * row of HBM instead of 8 m^2 flops per row).
  * ------------------------------------------------------------------------------------------- */
 int nls_primal_loo_sweep(nls_ctx* ctx, const double* X, const double* y, const double* s,
                          int64_t n, int d, const double* shift, const double* W, int D,
                          const double* Q, const double* lam, const double* v, double inv_c,
-                         const double* gammas, int G, int is_classifier, double* sums_out);
+                         const double* gammas, int G, int is_classifier, double* sums_out,
+                         double* sigma2_stash);
 
 /* ---------------------------------------------------------------------------------------------
  * Stage 4c — per-row outputs at the selected gamma.  Replaces _neo_ls_svm.py:167-187:
@@ -119,11 +127,14 @@ int nls_primal_loo_sweep(nls_ctx* ctx, const double* X, const double* y, const d
  *     resid_i    = Re(phi_i beta) - y_i, classifier-clipped    (:179-182)
  *     loo_std_i  = sqrt(sigma2_i + (s_i sigma2_i)^2 / (1 - leverage_i))   (:186-187)
  * beta_eig = Q (v / (lam + gamma)) (:175); beta = Cholesky re-solve (:177-178).  All outputs: n.
+ * sigma2_in (optional, n, may be NULL): column `opt` of the stash written by nls_primal_loo_sweep;
+ * when given, Q and lam are not read and the projection GEMM is skipped.
  * ------------------------------------------------------------------------------------------- */
 int nls_primal_finalize(nls_ctx* ctx, const double* X, const double* y, const double* s, int64_t n,
                         int d, const double* shift, const double* W, int D, const double* Q,
                         const double* lam, double inv_c, double gamma, const double* beta_eig,
-                        const double* beta, int is_classifier, double* loo_res_out,
+                        const double* beta, int is_classifier, const double* sigma2_in,
+                        double* loo_res_out,
                         double* yhat_loo_out, double* leverage_out, double* resid_out,
                         double* loo_std_out);
 
@@ -150,6 +161,34 @@ int nls_quantile_epilogue(nls_ctx* ctx, const double* yhat, const double* sigma,
                           const double* beta_abs, const double* beta_rel, const double* bias_abs,
                           const double* bias_rel, int Q, int is_regressor, const double* iso_x,
                           const double* iso_y, int n_iso, double* out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dual path (single GPU; "replicas only").  Replaces _optimize_alpha_gamma
+ * (_neo_ls_svm.py:252-323) for rho = 1 and the dual branches of decision_function (:668-671) and
+ * predict_std (:473-475).  The n x G x n tensor of :272-282 is never formed.
+ * ------------------------------------------------------------------------------------------- */
+/* Kernel matrix F = exp(-0.5 ||x_i - x_j||^2) + 1 (:261), lam, Q = eigh(sn F sn) (:265), and the LOO
+ * sweep over `gammas` (:268-302).  Xt: n x p transformed training rows; s: weights / sum (:252);
+ * sn = s / median|s| (:253).  Outputs: sums_out 3 x G (as nls_primal_loo_sweep), yhat_loo_out n x G
+ * (the LOO predictions at every gamma, :286), lam_out n.  F, Q and F0.SQ stay in the context for
+ * nls_dual_finalize. */
+int nls_dual_sweep(nls_ctx* ctx, const double* Xt, int n, int p, const double* y, const double* s,
+                   const double* sn, const double* gammas, int G, int is_classifier,
+                   double* sums_out, double* yhat_loo_out, double* lam_out);
+/* Per-row outputs at the selected gamma (:311-323); must follow nls_dual_sweep with the same n.
+ * alpha_out: Cholesky re-solve (:313-314) when U_out != NULL (U_out: n x n, cho_factor layout of
+ * gamma diag(sn^-2) + F), otherwise the eigen-expansion; alpha_eig_out (optional): eigen-expansion
+ * (:311); Falpha_out (optional): F alpha (:315); sigma2_out (optional): 1 - k_i^T (.)^-1 k_i (:322);
+ * Bt_out (optional, n x n) and w_out (optional, n): (gamma S^-2 + F)^-1 = Bt^T diag(w) Bt for
+ * nls_dual_predict. */
+int nls_dual_finalize(nls_ctx* ctx, int n, const double* y, const double* sn, double gamma,
+                      double* alpha_out, double* alpha_eig_out, double* U_out, double* Falpha_out,
+                      double* sigma2_out, double* Bt_out, double* w_out);
+/* yhat = K(xq, Xt) alpha + alpha_sum (:669-671); sigma = sqrt(1 - sum_k ((K Bt^T)_ik)^2 w_k) (:474-477).
+ * Either output may be NULL. */
+int nls_dual_predict(nls_ctx* ctx, const double* Xq, int64_t nq, const double* Xt, int n, int p,
+                     const double* alpha, double alpha_sum, const double* Bt, const double* w,
+                     double* yhat_out, double* sigma_out);
 
 /* Micro-benchmarks used for the roofline denominators (bench.py / profiles/). */
 int nls_bench_dmma_peak(nls_ctx* ctx, int iters, double* tflops_out);

@@ -37,14 +37,18 @@ def _signatures(lib: C.CDLL) -> None:
         "nls_ctx_profile": ([p, i], i),
         "nls_ctx_profile_read": ([p, C.POINTER(d), C.POINTER(i64)], i),
         "nls_feature_map": ([p, p, i64, i, p, p, i, p], i),
+        "nls_affine_map": ([p, p, i64, i, p, p, i, p], i),
         "nls_primal_gram": ([p, p, p, p, i64, i, p, p, i, p, p], i),
         "nls_heev": ([p, p, i, d, p, p], i),
         "nls_primal_coeffs": ([p, p, p, p, i, d, d, p, p], i),
         "nls_cholesky_solve": ([p, p, i, d, p, p, p], i),
-        "nls_primal_loo_sweep": ([p, p, p, p, i64, i, p, p, i, p, p, p, d, p, i, i, p], i),
-        "nls_primal_finalize": ([p, p, p, p, i64, i, p, p, i, p, p, d, d, p, p, i, p, p, p, p, p], i),
+        "nls_primal_loo_sweep": ([p, p, p, p, i64, i, p, p, i, p, p, p, d, p, i, i, p, p], i),
+        "nls_primal_finalize": ([p, p, p, p, i64, i, p, p, i, p, p, d, d, p, p, i, p, p, p, p, p, p], i),
         "nls_primal_predict": ([p, p, i64, i, p, p, i, p, p, p, p, p], i),
         "nls_quantile_epilogue": ([p, p, p, i64, p, p, p, p, i, i, p, p, i, p], i),
+        "nls_dual_sweep": ([p, p, i, i, p, p, p, p, i, i, p, p, p], i),
+        "nls_dual_finalize": ([p, i, p, p, d, p, p, p, p, p, p, p], i),
+        "nls_dual_predict": ([p, p, i64, p, i, i, p, d, p, p, p, p], i),
         "nls_bench_dmma_peak": ([p, i, C.POINTER(d)], i),
     }
     for name, (argtypes, restype) in sig.items():
@@ -151,6 +155,15 @@ class Context:
         check(self.lib.nls_feature_map(self.handle, ptr(X), n, d, ptr(shift), ptr(W), D, ptr(phi)))
         return phi
 
+    def affine_map(self, X, shift, W):
+        import torch
+
+        n, d = X.shape
+        D = W.shape[1]
+        Z = torch.empty((n, D), dtype=torch.float64, device=X.device)
+        check(self.lib.nls_affine_map(self.handle, ptr(X), n, d, ptr(shift), ptr(W), D, ptr(Z)))
+        return Z
+
     def primal_gram(self, X, y, s, shift, W):
         import torch
 
@@ -193,19 +206,23 @@ class Context:
         check(self.lib.nls_cholesky_solve(self.handle, ptr(A), m, float(diag_shift), ptr(b), ptr(U), ptr(beta)))
         return U, beta
 
-    def primal_loo_sweep(self, X, y, s, shift, W, Q, lam, v, inv_c: float, gammas, classifier: bool):
+    def primal_loo_sweep(self, X, y, s, shift, W, Q, lam, v, inv_c: float, gammas, classifier: bool, stash=None):
+        """Per-γ error sums (3×G); `stash` (n×G float64, optional) receives σ²ᵢ(γ_g) for every row."""
         import torch
 
         n, d = X.shape
         D = W.shape[1]
         G = gammas.shape[0]
         sums = torch.empty((3, G), dtype=torch.float64, device=X.device)
+        if stash is not None:
+            assert stash.shape == (n, G)
         check(self.lib.nls_primal_loo_sweep(
             self.handle, ptr(X), ptr(y), ptr(s), n, d, ptr(shift), ptr(W), D, ptr(Q), ptr(lam), ptr(v),
-            float(inv_c), ptr(gammas), G, int(classifier), ptr(sums)))
+            float(inv_c), ptr(gammas), G, int(classifier), ptr(sums), ptr(stash)))
         return sums
 
-    def primal_finalize(self, X, y, s, shift, W, Q, lam, inv_c: float, gamma: float, beta_eig, beta, classifier: bool):
+    def primal_finalize(self, X, y, s, shift, W, Q, lam, inv_c: float, gamma: float, beta_eig, beta, classifier: bool,
+                        sigma2=None):
         import torch
 
         n, d = X.shape
@@ -213,7 +230,7 @@ class Context:
         out = torch.empty((5, n), dtype=torch.float64, device=X.device)
         check(self.lib.nls_primal_finalize(
             self.handle, ptr(X), ptr(y), ptr(s), n, d, ptr(shift), ptr(W), D, ptr(Q), ptr(lam), float(inv_c),
-            float(gamma), ptr(beta_eig), ptr(beta), int(classifier),
+            float(gamma), ptr(beta_eig), ptr(beta), int(classifier), ptr(sigma2),
             ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(out[3]), ptr(out[4])))
         return {"loo_residuals": out[0], "yhat_loo": out[1], "loo_leverage": out[2], "residuals": out[3],
                 "loo_std": out[4]}
@@ -242,6 +259,51 @@ class Context:
             self.handle, ptr(yhat), ptr(sigma), n, ptr(beta_abs), ptr(beta_rel), ptr(bias_abs), ptr(bias_rel),
             Q, int(regressor), ptr(iso_x), ptr(iso_y), n_iso, ptr(out)))
         return out
+
+
+    # -- dual path -----------------------------------------------------------------------------
+    def dual_sweep(self, Xt, y, s, sn, gammas, classifier: bool):
+        import torch
+
+        n, p_ = Xt.shape
+        G = gammas.shape[0]
+        sums = torch.empty((3, G), dtype=torch.float64, device=Xt.device)
+        yhat_loo = torch.empty((n, G), dtype=torch.float64, device=Xt.device)
+        lam = torch.empty((n,), dtype=torch.float64, device=Xt.device)
+        check(self.lib.nls_dual_sweep(
+            self.handle, ptr(Xt), n, p_, ptr(y), ptr(s), ptr(sn), ptr(gammas), G, int(classifier),
+            ptr(sums), ptr(yhat_loo), ptr(lam)))
+        return sums, yhat_loo, lam
+
+    def dual_finalize(self, n: int, y, sn, gamma: float, cholesky: bool = True):
+        import torch
+
+        dev = y.device
+        f64 = torch.float64
+        out = {
+            "alpha": torch.empty((n,), dtype=f64, device=dev),
+            "alpha_eig": torch.empty((n,), dtype=f64, device=dev),
+            "U": torch.empty((n, n), dtype=f64, device=dev) if cholesky else None,
+            "Falpha": torch.empty((n,), dtype=f64, device=dev),
+            "sigma2": torch.empty((n,), dtype=f64, device=dev),
+            "Bt": torch.empty((n, n), dtype=f64, device=dev),
+            "w": torch.empty((n,), dtype=f64, device=dev),
+        }
+        check(self.lib.nls_dual_finalize(
+            self.handle, n, ptr(y), ptr(sn), float(gamma), ptr(out["alpha"]), ptr(out["alpha_eig"]), ptr(out["U"]),
+            ptr(out["Falpha"]), ptr(out["sigma2"]), ptr(out["Bt"]), ptr(out["w"])))
+        return out
+
+    def dual_predict(self, Xq, Xt, alpha=None, alpha_sum: float = 0.0, Bt=None, w=None, want_std: bool = False):
+        import torch
+
+        nq, p_ = Xq.shape
+        n = Xt.shape[0]
+        yhat = torch.empty((nq,), dtype=torch.float64, device=Xq.device) if alpha is not None else None
+        sigma = torch.empty((nq,), dtype=torch.float64, device=Xq.device) if want_std else None
+        check(self.lib.nls_dual_predict(
+            self.handle, ptr(Xq), nq, ptr(Xt), n, p_, ptr(alpha), float(alpha_sum), ptr(Bt), ptr(w), ptr(yhat), ptr(sigma)))
+        return yhat, sigma
 
 
 _contexts: dict = {}

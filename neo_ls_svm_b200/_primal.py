@@ -76,11 +76,16 @@ def primal_fit(
     n_global: int | None = None,
     ctx: _lib.Context | None = None,
     time_stages: bool = False,
+    stash: bool | str = "auto",
 ) -> PrimalFit:
     """Run stages 1–4 for the local row shard.
 
     X (n×d), y (n), s (n, ALREADY divided by the global weight sum, :110), shift (d), W (d×D) are
     contiguous float64 CUDA tensors.  `n_global` is the total number of rows over all ranks.
+
+    `stash`: keep σ²ᵢ(γ_g) for every local row and γ (n×G doubles, 8 KB/row) while sweeping, so that the
+    per-row outputs at the selected γ are a column gather instead of a second n·m² projection pass.
+    "auto" enables it when the buffer fits in 60% of the free HBM.
     """
     ctx = ctx or _lib.context(X.device.index)
     n, d = X.shape
@@ -106,7 +111,13 @@ def primal_fit(
     mark("eigh")
     gammas_np = gamma_grid(N_GAMMAS_PRIMAL)
     gammas = torch.from_numpy(gammas_np).to(X.device)
-    sums = ctx.primal_loo_sweep(X, y, s, shift, W, Q, lam, v, inv_c, gammas, classifier)  # stage 4a+4b
+    stash_buf = None
+    if stash == "auto":
+        free_bytes, _ = torch.cuda.mem_get_info(X.device)
+        stash = n * N_GAMMAS_PRIMAL * 8 < 0.6 * free_bytes
+    if stash:
+        stash_buf = torch.empty((n, N_GAMMAS_PRIMAL), dtype=torch.float64, device=X.device)
+    sums = ctx.primal_loo_sweep(X, y, s, shift, W, Q, lam, v, inv_c, gammas, classifier, stash=stash_buf)  # stage 4a+4b
     _all_reduce(sums)
     sums_np = sums.cpu().numpy()
     opt, obj = select_gamma(sums_np, classifier)
@@ -115,7 +126,9 @@ def primal_fit(
     _, beta_eig = ctx.primal_coeffs(Q, lam, None, inv_c, gamma, v=v)
     U, beta = ctx.cholesky_solve(A, gamma / inv_c, b)  # :177-178
     mark("solve")
-    rows = ctx.primal_finalize(X, y, s, shift, W, Q, lam, inv_c, gamma, beta_eig, beta, classifier)  # stage 4c
+    sigma2 = stash_buf[:, opt].contiguous() if stash_buf is not None else None
+    del stash_buf
+    rows = ctx.primal_finalize(X, y, s, shift, W, Q, lam, inv_c, gamma, beta_eig, beta, classifier, sigma2=sigma2)  # stage 4c
     mark("finalize")
     # LOO score (:171-174) from weighted sums over all ranks.
     yhat_loo = rows["yhat_loo"]

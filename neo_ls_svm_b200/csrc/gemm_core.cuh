@@ -17,6 +17,7 @@
 //   MODE_REAL     R += xa.ya                                   (1 A plane, 1 B plane)
 //   MODE_DUAL_A   R += xa.ya ;  I += xb.ya                     (2 A planes, 1 B plane)
 //   MODE_COMPLEX  R += xa.ya + xb.yb ;  I += xb.ya - xa.yb     (2 A planes, 2 B planes)
+//   MODE_PAIR     R += xa.ya ;  I += xb.yb                     (2 A planes, 2 B planes; two GEMMs at once)
 // MODE_COMPLEX is conj(xa + i xb) * (ya + i yb) up to the sign of I, i.e. one complex GEMM on a real
 // MMA with each operand tile loaded once.
 #pragma once
@@ -35,12 +36,12 @@ constexpr int GEMM_THREADS = CONSUMER_THREADS;
 constexpr int A_PLANE_BYTES = BM * BK * 8;  // 16 KiB
 constexpr int B_PLANE_BYTES = BN * BK * 8;  //  8 KiB
 
-enum { MODE_REAL = 0, MODE_DUAL_A = 1, MODE_COMPLEX = 2 };
+enum { MODE_REAL = 0, MODE_DUAL_A = 1, MODE_COMPLEX = 2, MODE_PAIR = 3 };
 
 template <int MODE>
 struct ModeTraits {
   static constexpr int A_PLANES = (MODE == MODE_REAL) ? 1 : 2;
-  static constexpr int B_PLANES = (MODE == MODE_COMPLEX) ? 2 : 1;
+  static constexpr int B_PLANES = (MODE == MODE_COMPLEX || MODE == MODE_PAIR) ? 2 : 1;
   static constexpr int STAGE_BYTES = A_PLANES * A_PLANE_BYTES + B_PLANES * B_PLANE_BYTES;
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
   // 1 KiB alignment slack + pipeline + barriers.
@@ -106,6 +107,12 @@ __device__ __forceinline__ void mma_stage(Acc& acc, uint32_t stage_base, int war
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) dmma(acc.i[i][j][0], acc.i[i][j][1], xb[i], ya[j]);
+    }
+    if (MODE == MODE_PAIR) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma(acc.i[i][j][0], acc.i[i][j][1], xb[i], yb[j]);
     }
     if (MODE == MODE_COMPLEX) {
 #pragma unroll

@@ -81,6 +81,9 @@ struct nls_ctx {
   cusolverDnHandle_t solver = nullptr;
   // scratch (grow-only, zero-filled when (re)allocated)
   DevBuf xc, wt, psi, psiT, pu, bt, rt, small, part, gram_ws, border, rowtmp, solver_ws, solver_mat;
+  // dual path (state kept between nls_dual_sweep and nls_dual_finalize)
+  DevBuf d_xpad, d_xq, d_norm, d_fm, d_sq, d_sqt, d_g1, d_ab, d_ra, d_vec, d_ng, d_kq, d_btp;
+  int dual_n = 0;
   // profiling
   bool prof = false;
   std::vector<ProfSpan> spans;
@@ -318,7 +321,9 @@ extern "C" int nls_ctx_destroy(nls_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->xc, &ctx->wt, &ctx->psi, &ctx->psiT, &ctx->pu, &ctx->bt, &ctx->rt, &ctx->small,
-                    &ctx->part, &ctx->gram_ws, &ctx->border, &ctx->rowtmp, &ctx->solver_ws, &ctx->solver_mat};
+                    &ctx->part, &ctx->gram_ws, &ctx->border, &ctx->rowtmp, &ctx->solver_ws, &ctx->solver_mat,
+                    &ctx->d_xpad, &ctx->d_xq, &ctx->d_norm, &ctx->d_fm, &ctx->d_sq, &ctx->d_sqt, &ctx->d_g1,
+                    &ctx->d_ab, &ctx->d_ra, &ctx->d_vec, &ctx->d_ng, &ctx->d_kq, &ctx->d_btp};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   for (auto& s : ctx->spans) {
@@ -393,6 +398,35 @@ extern "C" int nls_feature_map(nls_ctx* ctx, const double* X, int64_t n, int d, 
   for (int64_t i0 = 0; i0 < n; i0 += ctx->chunk_rows) {
     const int rows = (int)std::min<int64_t>(ctx->chunk_rows, n - i0);
     NLS_TRY(feature_chunk(ctx, g, X + i0 * d, shift, rows, FM_COMPLEX, phi_out + i0 * (D + 1) * 2, 0, 0, nullptr));
+  }
+  return NLS_OK;
+}
+
+// z = (x - shift) W as a plain real matrix (the dual path's feature map and AffineFeatureMap.transform).
+extern "C" int nls_affine_map(nls_ctx* ctx, const double* X, int64_t n, int d, const double* shift, const double* W,
+                              int D, double* Z_out) {
+  NLS_TRY(check_map_args(ctx, X, n, d, shift, W, D));
+  if (!Z_out) return fail(NLS_ERR_INVALID, "Z_out is null");
+  const MapGeom g = geom(d, D);
+  NLS_TRY(prep_weights(ctx, g, W));
+  for (int64_t i0 = 0; i0 < n; i0 += ctx->chunk_rows) {
+    const int rows = (int)std::min<int64_t>(ctx->chunk_rows, n - i0);
+    center_rows_kernel<<<grid_for((long long)rows * g.dpad), 256, 0, ctx->stream>>>(X + i0 * d, shift, rows, g.d, g.dpad,
+                                                                                   (double*)ctx->xc.p);
+    NLS_TRY(check_launch(ctx, "center_rows_kernel"));
+    OpStore<false>::Params p;
+    p.A = Operand{(const double*)ctx->xc.p, g.dpad, rows, g.d, 0, 0};
+    p.B = Operand{(const double*)ctx->wt.p, g.dpad, g.D, g.d, 0, 0};
+    p.n_rows = rows;
+    p.n_cols = D;
+    p.norm_a = nullptr;
+    p.norm_b = nullptr;
+    p.add = 0.0;
+    p.zero_diag_to = -1;
+    p.out = Z_out + i0 * D;
+    p.ld = D;
+    NLS_TRY((launch_gemm<MODE_REAL, OpStore<false>>(ctx, p, dim3((D + BN - 1) / BN, (rows + BM - 1) / BM), rows, D,
+                                                     NLS_PROF_FEATURE_MAP, "affine_map")));
   }
   return NLS_OK;
 }
@@ -531,7 +565,7 @@ extern "C" int nls_cholesky_solve(nls_ctx* ctx, const double* A, int m, double d
 extern "C" int nls_primal_loo_sweep(nls_ctx* ctx, const double* X, const double* y, const double* s, int64_t n, int d,
                                     const double* shift, const double* W, int D, const double* Q, const double* lam,
                                     const double* v, double inv_c, const double* gammas, int G, int is_classifier,
-                                    double* sums_out) {
+                                    double* sums_out, double* sigma2_stash) {
   NLS_TRY(check_map_args(ctx, X, n, d, shift, W, D));
   if (!y || !s || !Q || !lam || !v || !gammas || !sums_out || G < 1) return fail(NLS_ERR_INVALID, "null pointer");
   const MapGeom g = geom(d, D);
@@ -580,6 +614,8 @@ extern "C" int nls_primal_loo_sweep(nls_ctx* ctx, const double* X, const double*
     sp.s = s + i0;
     sp.is_classifier = is_classifier;
     sp.part = (double*)ctx->part.p;
+    sp.den_out = sigma2_stash ? sigma2_stash + i0 * G : nullptr;
+    sp.den_ld = G;
     NLS_TRY((launch_gemm<MODE_DUAL_A, OpSweep>(ctx, sp, dim3((G + BN - 1) / BN, mtiles), cap + rows, G,
                                                 NLS_PROF_SWEEP, "sweep")));
     sweep_reduce_kernel<<<(3 * G + 255) / 256, 256, 0, ctx->stream>>>((const double*)ctx->part.p, mtiles, G, sums_out);
@@ -615,28 +651,32 @@ static int variance_chunk(nls_ctx* ctx, const MapGeom& g, const BasisScratch& bs
 extern "C" int nls_primal_finalize(nls_ctx* ctx, const double* X, const double* y, const double* s, int64_t n, int d,
                                    const double* shift, const double* W, int D, const double* Q, const double* lam,
                                    double inv_c, double gamma, const double* beta_eig, const double* beta,
-                                   int is_classifier, double* loo_res_out, double* yhat_loo_out, double* leverage_out,
-                                   double* resid_out, double* loo_std_out) {
+                                   int is_classifier, const double* sigma2_in, double* loo_res_out,
+                                   double* yhat_loo_out, double* leverage_out, double* resid_out,
+                                   double* loo_std_out) {
   NLS_TRY(check_map_args(ctx, X, n, d, shift, W, D));
-  if (!y || !s || !Q || !lam || !beta_eig || !beta || !loo_res_out || !yhat_loo_out || !leverage_out || !resid_out ||
-      !loo_std_out)
+  if (!y || !s || !beta_eig || !beta || !loo_res_out || !yhat_loo_out || !leverage_out || !resid_out || !loo_std_out)
     return fail(NLS_ERR_INVALID, "null pointer");
+  if (!sigma2_in && (!Q || !lam)) return fail(NLS_ERR_INVALID, "Q and lam are required when sigma2_in is null");
   const MapGeom g = geom(d, D);
   NLS_TRY(prep_weights(ctx, g, W));
   BasisScratch bs;
-  NLS_TRY(prep_basis(ctx, g, Q, &bs));
-  variance_weights_kernel<<<(g.m + 255) / 256, 256, 0, ctx->stream>>>(lam, g.m, inv_c, gamma, bs.w);
-  NLS_TRY(check_launch(ctx, "variance_weights_kernel"));
+  if (!sigma2_in) {
+    NLS_TRY(prep_basis(ctx, g, Q, &bs));
+    variance_weights_kernel<<<(g.m + 255) / 256, 256, 0, ctx->stream>>>(lam, g.m, inv_c, gamma, bs.w);
+    NLS_TRY(check_launch(ctx, "variance_weights_kernel"));
+  }
   const long long cap = ctx->chunk_rows;
   NLS_TRY(ensure(ctx, ctx->psi, (size_t)cap * 2 * g.Dp * 8));
   NLS_TRY(ensure(ctx, ctx->rowtmp, (size_t)3 * cap * 8));
-  double* sigma2 = (double*)ctx->rowtmp.p;
-  double* num = sigma2 + cap;
+  double* sigma2_tmp = (double*)ctx->rowtmp.p;
+  double* num = sigma2_tmp + cap;
   double* fit = num + cap;
   for (int64_t i0 = 0; i0 < n; i0 += cap) {
     const int rows = (int)std::min<int64_t>(cap, n - i0);
     NLS_TRY(feature_chunk(ctx, g, X + i0 * d, shift, rows, FM_PLANAR, (double*)ctx->psi.p, 2LL * g.Dp, g.Dp, nullptr));
-    NLS_TRY(variance_chunk(ctx, g, bs, rows, sigma2));
+    const double* sigma2 = sigma2_in ? sigma2_in + i0 : sigma2_tmp;
+    if (!sigma2_in) NLS_TRY(variance_chunk(ctx, g, bs, rows, sigma2_tmp));
     gemv_pair_kernel<<<(rows * 32 + 255) / 256, 256, 0, ctx->stream>>>((const double*)ctx->psi.p, 2LL * g.Dp, g.Dp,
                                                                       rows, D, beta_eig, beta, num, fit);
     NLS_TRY(check_launch(ctx, "gemv_pair_kernel"));
@@ -700,6 +740,288 @@ extern "C" int nls_quantile_epilogue(nls_ctx* ctx, const double* yhat, const dou
 }
 
 // ---------------------------------------------------------------------------------------------
+// Dual path
+// ---------------------------------------------------------------------------------------------
+static int rbf_block(nls_ctx* ctx, const double* xa, const double* na, int rows_a, const double* xb, const double* nb,
+                     int rows_b, int p, int pp, double add, int force_diag, double* out, long long ld) {
+  OpStore<true>::Params rp;
+  rp.A = Operand{xa, pp, rows_a, p, 0, 0};
+  rp.B = Operand{xb, pp, rows_b, p, 0, 0};
+  rp.n_rows = rows_a;
+  rp.n_cols = rows_b;
+  rp.norm_a = na;
+  rp.norm_b = nb;
+  rp.add = add;
+  rp.zero_diag_to = force_diag ? 0 : -1;
+  rp.out = out;
+  rp.ld = ld;
+  return launch_gemm<MODE_REAL, OpStore<true>>(ctx, rp, dim3((rows_b + BN - 1) / BN, (rows_a + BM - 1) / BM), rows_a,
+                                               rows_b, NLS_PROF_OTHER, "rbf");
+}
+
+static int pad_and_norm(nls_ctx* ctx, const double* X, long long rows, int p, int pp, double* xpad, double* norms) {
+  pad_rows_kernel<<<grid_for(rows * pp), 256, 0, ctx->stream>>>(X, p, rows, p, pp, xpad);
+  NLS_TRY(check_launch(ctx, "pad_rows_kernel"));
+  row_sqnorm_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, ctx->stream>>>(xpad, pp, rows, p, norms);
+  return check_launch(ctx, "row_sqnorm_kernel");
+}
+
+extern "C" int nls_dual_sweep(nls_ctx* ctx, const double* Xt, int n, int p, const double* y, const double* s,
+                              const double* sn, const double* gammas, int G, int is_classifier, double* sums_out,
+                              double* yhat_loo_out, double* lam_out) {
+  if (!ctx || !Xt || !y || !s || !sn || !gammas || !sums_out || !yhat_loo_out || !lam_out)
+    return fail(NLS_ERR_INVALID, "null pointer");
+  if (n < 2 || p < 1 || G < 1) return fail(NLS_ERR_INVALID, "bad shape (n=%d p=%d G=%d)", n, p, G);
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  ctx->dual_n = 0;
+  const long long ldn = round_up(n, 16);
+  const int pp = (int)round_up(p, 16);
+  const int Gp = (int)round_up(G, BN);
+  const size_t nn = (size_t)n * ldn * 8;
+  NLS_TRY(ensure(ctx, ctx->d_xpad, (size_t)n * pp * 8));
+  NLS_TRY(ensure(ctx, ctx->d_norm, (size_t)2 * ldn * 8 + (size_t)65536 * 8));
+  NLS_TRY(ensure(ctx, ctx->d_fm, 2 * nn));
+  NLS_TRY(ensure(ctx, ctx->d_sq, nn));
+  NLS_TRY(ensure(ctx, ctx->d_sqt, nn));
+  NLS_TRY(ensure(ctx, ctx->d_g1, nn));
+  NLS_TRY(ensure(ctx, ctx->d_ab, 2 * nn));
+  NLS_TRY(ensure(ctx, ctx->d_ra, (size_t)(Gp + G) * ldn * 8));
+  NLS_TRY(ensure(ctx, ctx->d_vec, (size_t)4 * ldn * 8));
+  NLS_TRY(ensure(ctx, ctx->d_ng, (size_t)2 * n * G * 8));
+  NLS_TRY(ensure(ctx, ctx->solver_mat, (size_t)n * n * 8 + 64));
+  const int mtiles = (n + BM - 1) / BM;
+  NLS_TRY(ensure(ctx, ctx->part, (size_t)mtiles * 3 * G * 8));
+  double* xpad = (double*)ctx->d_xpad.p;
+  double* norms = (double*)ctx->d_norm.p;
+  double* F = (double*)ctx->d_fm.p;
+  double* M = F + (size_t)n * ldn;
+  double* SQ = (double*)ctx->d_sq.p;
+  double* SQt = (double*)ctx->d_sqt.p;
+  double* G1 = (double*)ctx->d_g1.p;
+  double* AB = (double*)ctx->d_ab.p;
+  double* alooT = (double*)ctx->d_ra.p;
+  double* Rt = alooT + (size_t)Gp * ldn;
+  double* qsy = (double*)ctx->d_vec.p;
+  double* colsum = qsy + ldn;
+  double* lam = colsum + ldn;
+  double* aloo = (double*)ctx->d_ng.p;
+  double* hd = aloo + (size_t)n * G;
+  double* S = (double*)ctx->solver_mat.p;
+  int* info = (int*)(S + (size_t)n * n);
+  // F = rbf(Xt) + 1   (:261)
+  NLS_TRY(pad_and_norm(ctx, Xt, n, p, pp, xpad, norms));
+  NLS_TRY(rbf_block(ctx, xpad, norms, n, xpad, norms, n, p, pp, 1.0, 1, F, ldn));
+  // lam, Q = eigh(sn F sn)   (:265)  (round 1: cuSOLVER dsyevd)
+  scale_sym_kernel<<<grid_for((long long)n * n), 256, 0, ctx->stream>>>(F, ldn, n, sn, S);
+  NLS_TRY(check_launch(ctx, "scale_sym_kernel"));
+  int lwork = 0;
+  SOLVER_TRY(cusolverDnDsyevd_bufferSize(ctx->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, S, n, lam,
+                                         &lwork));
+  NLS_TRY(ensure(ctx, ctx->solver_ws, (size_t)lwork * 8));
+  SOLVER_TRY(cusolverDnDsyevd(ctx->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, S, n, lam,
+                              (double*)ctx->solver_ws.p, lwork, info));
+  int h_info = 0;
+  CUDA_TRY(cudaMemcpyAsync(&h_info, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (h_info != 0) return fail(NLS_ERR_SOLVER, "symmetric eigensolver failed: info = %d", h_info);
+  CUDA_TRY(cudaMemcpyAsync(lam_out, lam, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  // Column-major eigenvectors = row-major Q^T; SQ^T[k, j] = Q[j, k] sn_j, SQ = its transpose.
+  scale_cols_kernel<<<grid_for((long long)n * n), 256, 0, ctx->stream>>>(S, n, n, n, sn, ldn, SQt);
+  NLS_TRY(check_launch(ctx, "scale_cols_kernel"));
+  {
+    dim3 grid((n + 31) / 32, (n + 31) / 32), block(32, 8);
+    transpose_kernel<<<grid, block, 0, ctx->stream>>>(SQt, ldn, n, n, SQ, ldn);
+    NLS_TRY(check_launch(ctx, "transpose_kernel"));
+  }
+  const unsigned warp_grid = (unsigned)(((long long)n * 32 + 255) / 256);
+  gemv_rows_kernel<<<warp_grid, 256, 0, ctx->stream>>>(SQt, ldn, n, n, y, 0.0, qsy);   // Q^T (sn*y), :268
+  NLS_TRY(check_launch(ctx, "gemv_rows_kernel"));
+  gemv_rows_kernel<<<warp_grid, 256, 0, ctx->stream>>>(SQt, ldn, n, n, nullptr, 0.0, colsum);
+  NLS_TRY(check_launch(ctx, "gemv_rows_kernel"));
+  dual_ab_kernel<<<grid_for((long long)n * n), 256, 0, ctx->stream>>>(SQ, ldn, n, qsy, AB);
+  NLS_TRY(check_launch(ctx, "dual_ab_kernel"));
+  build_rt_kernel<<<grid_for((long long)G * ldn), 256, 0, ctx->stream>>>(gammas, lam, G, n, ldn, Rt);
+  NLS_TRY(check_launch(ctx, "build_rt_kernel"));
+  // alpha_loo = alpha_mat r (:285), hdiag = (SQ*SQ) r (:272-281)
+  {
+    OpDualCoef::Params cp;
+    cp.A = Operand{AB, ldn, 2 * n, n, n, 0};
+    cp.B = Operand{Rt, ldn, G, n, 0, 0};
+    cp.n = n;
+    cp.G = G;
+    cp.aloo = aloo;
+    cp.alooT = alooT;
+    cp.ldT = ldn;
+    cp.hd = hd;
+    cp.eps = 2.220446049250313e-16;
+    NLS_TRY((launch_gemm<MODE_DUAL_A, OpDualCoef>(ctx, cp, dim3((G + BN - 1) / BN, mtiles), 2 * n, G, NLS_PROF_SWEEP,
+                                                   "dual_coef")));
+  }
+  // G1 = F0 SQ, M = G1 * SQ
+  {
+    OpDualCross::Params xp;
+    xp.A = Operand{F, ldn, n, n, 0, 0};
+    xp.B = Operand{SQt, ldn, n, n, 0, 0};
+    xp.n = n;
+    xp.SQ = SQ;
+    xp.ld = ldn;
+    xp.fdiag = 2.0;  // F_ii = exp(0) + 1
+    xp.G1 = G1;
+    xp.M = M;
+    NLS_TRY((launch_gemm<MODE_REAL, OpDualCross>(ctx, xp, dim3((n + BN - 1) / BN, mtiles), n, n, NLS_PROF_PROJECT,
+                                                  "dual_cross")));
+  }
+  // yhat_loo = -(M r)/hdiag * alpha_loo + F0 alpha_loo (:286) and the error sums (:287-302)
+  {
+    OpDualSweep::Params sp;
+    sp.A = Operand{F, ldn, 2 * n, n, n, 0};
+    sp.B = Operand{alooT, ldn, Gp + G, n, Gp, 0};
+    sp.n_rows = n;
+    sp.G = G;
+    sp.y = y;
+    sp.s = s;
+    sp.is_classifier = is_classifier;
+    sp.part = (double*)ctx->part.p;
+    sp.aloo = aloo;
+    sp.hd = hd;
+    sp.fdiag = 2.0;
+    sp.yhat_loo = yhat_loo_out;
+    NLS_TRY((launch_gemm<MODE_PAIR, OpDualSweep>(ctx, sp, dim3((G + BN - 1) / BN, mtiles), 2 * n, Gp + G,
+                                                  NLS_PROF_SWEEP, "dual_sweep")));
+  }
+  CUDA_TRY(cudaMemsetAsync(sums_out, 0, (size_t)3 * G * 8, ctx->stream));
+  sweep_reduce_kernel<<<(3 * G + 255) / 256, 256, 0, ctx->stream>>>((const double*)ctx->part.p, mtiles, G, sums_out);
+  NLS_TRY(check_launch(ctx, "sweep_reduce_kernel"));
+  ctx->dual_n = n;
+  return NLS_OK;
+}
+
+extern "C" int nls_dual_finalize(nls_ctx* ctx, int n, const double* y, const double* sn, double gamma,
+                                 double* alpha_out, double* alpha_eig_out, double* U_out, double* Falpha_out,
+                                 double* sigma2_out, double* Bt_out, double* w_out) {
+  if (!ctx || !y || !sn || !alpha_out) return fail(NLS_ERR_INVALID, "null pointer");
+  if (ctx->dual_n != n || n < 2) return fail(NLS_ERR_INVALID, "nls_dual_finalize must follow nls_dual_sweep with the same n");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const long long ldn = round_up(n, 16);
+  double* F = (double*)ctx->d_fm.p;
+  double* SQ = (double*)ctx->d_sq.p;
+  double* SQt = (double*)ctx->d_sqt.p;
+  double* G1 = (double*)ctx->d_g1.p;
+  double* qsy = (double*)ctx->d_vec.p;
+  double* colsum = qsy + ldn;
+  double* lam = colsum + ldn;
+  double* xk = lam + ldn;
+  const unsigned warp_grid = (unsigned)(((long long)n * 32 + 255) / 256);
+  // alpha from the eigen-expansion (:311): alpha = SQ (qsy / (gamma + lam))
+  dual_coef_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(qsy, lam, n, gamma, xk);
+  NLS_TRY(check_launch(ctx, "dual_coef_kernel"));
+  double* aeig = alpha_eig_out ? alpha_eig_out : alpha_out;
+  gemv_rows_kernel<<<warp_grid, 256, 0, ctx->stream>>>(SQ, ldn, n, n, xk, 0.0, aeig);
+  NLS_TRY(check_launch(ctx, "gemv_rows_kernel"));
+  if (U_out) {
+    // Re-solve with a Cholesky factorisation of gamma S^-2 + F (:313-314); U_out is cho_factor's layout.
+    pad_rows_kernel<<<grid_for((long long)n * n), 256, 0, ctx->stream>>>(F, ldn, n, n, n, U_out);
+    NLS_TRY(check_launch(ctx, "pad_rows_kernel"));
+    dual_add_diag_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(U_out, n, sn, gamma);
+    NLS_TRY(check_launch(ctx, "dual_add_diag_kernel"));
+    int lwork = 0;
+    SOLVER_TRY(cusolverDnDpotrf_bufferSize(ctx->solver, CUBLAS_FILL_MODE_LOWER, n, U_out, n, &lwork));
+    NLS_TRY(ensure(ctx, ctx->solver_ws, (size_t)lwork * 8 + 64));
+    int* info = (int*)((char*)ctx->solver_ws.p + (size_t)lwork * 8);
+    SOLVER_TRY(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, n, U_out, n, (double*)ctx->solver_ws.p, lwork, info));
+    int h_info = 0;
+    CUDA_TRY(cudaMemcpyAsync(&h_info, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (h_info != 0) return fail(NLS_ERR_SOLVER, "dual Cholesky factorisation failed: info = %d", h_info);
+    CUDA_TRY(cudaMemcpyAsync(alpha_out, y, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    SOLVER_TRY(cusolverDnDpotrs(ctx->solver, CUBLAS_FILL_MODE_LOWER, n, 1, U_out, n, alpha_out, n, info));
+  } else if (alpha_eig_out) {
+    CUDA_TRY(cudaMemcpyAsync(alpha_out, alpha_eig_out, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  if (Falpha_out) {  // F alpha (:315)
+    gemv_rows_kernel<<<warp_grid, 256, 0, ctx->stream>>>(F, ldn, n, n, alpha_out, 0.0, Falpha_out);
+    NLS_TRY(check_launch(ctx, "gemv_rows_kernel"));
+  }
+  if (sigma2_out) {  // :321-322 in the eigenbasis
+    dual_sigma2_kernel<<<warp_grid, 256, 0, ctx->stream>>>(G1, SQ, ldn, n, colsum, lam, 2.0, gamma, sigma2_out);
+    NLS_TRY(check_launch(ctx, "dual_sigma2_kernel"));
+  }
+  if (Bt_out) {
+    pad_rows_kernel<<<grid_for((long long)n * n), 256, 0, ctx->stream>>>(SQt, ldn, n, n, n, Bt_out);
+    NLS_TRY(check_launch(ctx, "pad_rows_kernel"));
+  }
+  if (w_out) {
+    variance_weights_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(lam, n, 1.0, gamma, w_out);
+    NLS_TRY(check_launch(ctx, "variance_weights_kernel"));
+  }
+  return NLS_OK;
+}
+
+extern "C" int nls_dual_predict(nls_ctx* ctx, const double* Xq, int64_t nq, const double* Xt, int n, int p,
+                                const double* alpha, double alpha_sum, const double* Bt, const double* w,
+                                double* yhat_out, double* sigma_out) {
+  if (!ctx || !Xq || !Xt) return fail(NLS_ERR_INVALID, "null pointer");
+  if (yhat_out && !alpha) return fail(NLS_ERR_INVALID, "alpha is required for yhat_out");
+  if (sigma_out && (!Bt || !w)) return fail(NLS_ERR_INVALID, "Bt and w are required for sigma_out");
+  if (nq < 1 || n < 1 || p < 1) return fail(NLS_ERR_INVALID, "bad shape");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const long long ldn = round_up(n, 16);
+  const int pp = (int)round_up(p, 16);
+  const int cq = (int)std::min<int64_t>(std::min<int64_t>(ctx->chunk_rows, 8192), round_up(nq, 128));
+  const int ntiles = (n + BN - 1) / BN;
+  NLS_TRY(ensure(ctx, ctx->d_xpad, (size_t)n * pp * 8));
+  NLS_TRY(ensure(ctx, ctx->d_xq, (size_t)cq * pp * 8));
+  NLS_TRY(ensure(ctx, ctx->d_norm, (size_t)2 * ldn * 8 + (size_t)65536 * 8));
+  NLS_TRY(ensure(ctx, ctx->d_kq, (size_t)cq * ldn * 8));
+  NLS_TRY(ensure(ctx, ctx->rowtmp, (size_t)3 * std::max<long long>(cq, ctx->chunk_rows) * 8));
+  ctx->dual_n = 0;  // d_xpad / d_norm are shared with the fit state
+  double* xt = (double*)ctx->d_xpad.p;
+  double* nt = (double*)ctx->d_norm.p;
+  double* nqv = nt + 2 * ldn;
+  double* xq = (double*)ctx->d_xq.p;
+  double* Kq = (double*)ctx->d_kq.p;
+  double* q = (double*)ctx->rowtmp.p;
+  NLS_TRY(pad_and_norm(ctx, Xt, n, p, pp, xt, nt));
+  double* btp = nullptr;
+  if (sigma_out) {
+    NLS_TRY(ensure(ctx, ctx->d_btp, (size_t)n * ldn * 8));
+    NLS_TRY(ensure(ctx, ctx->part, (size_t)ntiles * cq * 8));
+    btp = (double*)ctx->d_btp.p;
+    pad_rows_kernel<<<grid_for((long long)n * ldn), 256, 0, ctx->stream>>>(Bt, n, n, n, (int)ldn, btp);
+    NLS_TRY(check_launch(ctx, "pad_rows_kernel"));
+  }
+  for (int64_t i0 = 0; i0 < nq; i0 += cq) {
+    const int rows = (int)std::min<int64_t>(cq, nq - i0);
+    NLS_TRY(pad_and_norm(ctx, Xq + i0 * p, rows, p, pp, xq, nqv));
+    NLS_TRY(rbf_block(ctx, xq, nqv, rows, xt, nt, n, p, pp, 0.0, 0, Kq, ldn));  // :474 / :669
+    const unsigned warp_grid = (unsigned)(((long long)rows * 32 + 255) / 256);
+    if (yhat_out) {  // K alpha + sum(alpha), :670-671
+      gemv_rows_kernel<<<warp_grid, 256, 0, ctx->stream>>>(Kq, ldn, rows, n, alpha, alpha_sum, yhat_out + i0);
+      NLS_TRY(check_launch(ctx, "gemv_rows_kernel"));
+    }
+    if (sigma_out) {  // sqrt(1 - sum_k (K B^T)_ik^2 w_k), :475-477
+      OpRowQuad::Params vp;
+      vp.A = Operand{Kq, ldn, rows, n, 0, 0};
+      vp.B = Operand{btp, ldn, n, n, 0, 0};
+      vp.n_rows = rows;
+      vp.m = n;
+      vp.bias_r = nullptr;
+      vp.bias_i = nullptr;
+      vp.w = w;
+      vp.part = (double*)ctx->part.p;
+      vp.part_ld = cq;
+      NLS_TRY((launch_gemm<MODE_REAL, OpRowQuad>(ctx, vp, dim3(ntiles, (rows + BM - 1) / BM), rows, n, NLS_PROF_VARIANCE,
+                                                  "dual_variance")));
+      rowsum_reduce_kernel<<<(rows + 255) / 256, 256, 0, ctx->stream>>>((const double*)ctx->part.p, ntiles, cq, rows, q);
+      NLS_TRY(check_launch(ctx, "rowsum_reduce_kernel"));
+      one_minus_sqrt_kernel<<<(rows + 255) / 256, 256, 0, ctx->stream>>>(q, rows, sigma_out + i0);
+      NLS_TRY(check_launch(ctx, "one_minus_sqrt_kernel"));
+    }
+  }
+  return NLS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Micro-benchmark: register-resident DMMA loop (FP64 tensor peak of this device).
 // ---------------------------------------------------------------------------------------------
 extern "C" int nls_bench_dmma_peak(nls_ctx* ctx, int iters, double* tflops_out) {
@@ -710,14 +1032,19 @@ extern "C" int nls_bench_dmma_peak(nls_ctx* ctx, int iters, double* tflops_out) 
   cudaEvent_t a, b;
   CUDA_TRY(cudaEventCreate(&a));
   CUDA_TRY(cudaEventCreate(&b));
-  dmma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(iters / 8 + 1, (double*)ctx->small.p);  // warm-up
-  CUDA_TRY(cudaEventRecord(a, ctx->stream));
-  dmma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(iters, (double*)ctx->small.p);
-  CUDA_TRY(cudaEventRecord(b, ctx->stream));
-  NLS_TRY(check_launch(ctx, "dmma_peak_kernel"));
-  CUDA_TRY(cudaEventSynchronize(b));
-  float ms = 0.f;
-  CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+  // Two untimed launches ramp the clocks from idle; the burst peak is the best of three timed ones.
+  for (int w = 0; w < 2; ++w) dmma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(iters, (double*)ctx->small.p);
+  float ms = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    CUDA_TRY(cudaEventRecord(a, ctx->stream));
+    dmma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(iters, (double*)ctx->small.p);
+    CUDA_TRY(cudaEventRecord(b, ctx->stream));
+    NLS_TRY(check_launch(ctx, "dmma_peak_kernel"));
+    CUDA_TRY(cudaEventSynchronize(b));
+    float t = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&t, a, b));
+    ms = t < ms ? t : ms;
+  }
   const double flops = (double)blocks * (threads / 32) * (double)iters * 16.0 * (2.0 * 8 * 8 * 4);
   *tflops_out = flops / (ms * 1e-3) / 1e12;
   cudaEventDestroy(a);

@@ -8,6 +8,76 @@ namespace nls {
 __device__ __forceinline__ int acc_row(int warp_m, int i, int lane) { return warp_m * 32 + 8 * i + (lane >> 2); }
 __device__ __forceinline__ int acc_col(int warp_n, int j, int lane) { return warp_n * 32 + 8 * j + 2 * (lane & 3); }
 
+// Shared tail of the two LOO sweeps (primal and dual): acc.r holds the unclipped LOO residuals of the
+// CTA tile (rows x gammas).  Applies the classifier clip (_neo_ls_svm.py:153-155 / :290-292), takes
+// |.| and reduces s-weighted over rows in a fixed order:
+//   part[m_tile][0][g] = sum_i s_i |e_ig|,  [1] = sum_i s_i (|e_ig| >= 1),  [2] = sum_i s_i max(0, |e_ig| - 1).
+__device__ __forceinline__ void loo_reduce(Acc& acc, const Tile& t, int n_rows, int G, const double* __restrict__ y,
+                                           const double* __restrict__ s, int is_classifier, double* __restrict__ part,
+                                           int warp_m, int warp_n, int lane, uint8_t* scratch) {
+  double e_abs[4][2], e_cnt[4][2], e_hng[4][2];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) e_abs[j][e] = e_cnt[j][e] = e_hng[j][e] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = t.m0 + acc_row(warp_m, i, lane);
+    if (row >= n_rows) continue;
+    const double yi = y[row];
+    const double si = s[row];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        double loo = acc.r[i][j][e];
+        if (is_classifier) {
+          if ((yi > 0.0 && loo > 0.0) || (yi < 0.0 && loo < 0.0)) loo = 0.0;
+        }
+        const double a = fabs(loo);
+        e_abs[j][e] += si * a;
+        if (is_classifier) {
+          e_cnt[j][e] += (a >= 1.0) ? si : 0.0;
+          e_hng[j][e] += si * fmax(0.0, a - 1.0);
+        }
+      }
+  }
+  // Reduce over the 8 row-lanes of the warp (lanes sharing lane%4), fixed butterfly order.
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+#pragma unroll
+      for (int off = 4; off < 32; off <<= 1) {
+        e_abs[j][e] += __shfl_xor_sync(0xffffffffu, e_abs[j][e], off);
+        e_cnt[j][e] += __shfl_xor_sync(0xffffffffu, e_cnt[j][e], off);
+        e_hng[j][e] += __shfl_xor_sync(0xffffffffu, e_hng[j][e], off);
+      }
+  double* red = reinterpret_cast<double*>(scratch);  // [3][4 warp_m][64 cols]
+  if ((lane >> 2) == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = acc_col(warp_n, j, lane) + e;
+        red[(0 * 4 + warp_m) * BN + c] = e_abs[j][e];
+        red[(1 * 4 + warp_m) * BN + c] = e_cnt[j][e];
+        red[(2 * 4 + warp_m) * BN + c] = e_hng[j][e];
+      }
+  }
+  __syncthreads();
+  const int tid = threadIdx.x;
+  if (tid < 3 * BN) {
+    const int q = tid / BN, c = tid % BN;
+    const int g = t.n0 + c;
+    if (g < G) {
+      const double* r = red + (q * 4) * BN + c;
+      const double sum = ((r[0] + r[BN]) + r[2 * BN]) + r[3 * BN];
+      part[((long long)blockIdx.y * 3 + q) * G + g] = sum;
+    }
+  }
+}
+
 // =============================================================================================
 // Stage 1: z = Xc . W^T-tile, epilogue (cos z, sin z)/sqrt(D) in one of three layouts.
 //   reference: _affine_feature_map.py:81-89 (z) and _feature_maps.py:201-202 (exp(-1j z)/sqrt(D)).
@@ -223,6 +293,8 @@ struct OpSweep {
     const double* s;
     int is_classifier;
     double* part;   // [gridDim.y][3][G]
+    double* den_out;  // optional stash of U r (= sigma2_i at every gamma), row pitch den_ld; may be null
+    long long den_ld;
   };
   static __device__ __forceinline__ Tile tile(const Params& p) {
     Tile t;
@@ -235,69 +307,39 @@ struct OpSweep {
   }
   static __device__ __forceinline__ void epilogue(const Params& p, const Tile& t, Acc& acc, int warp_m, int warp_n,
                                                   int lane, uint8_t* scratch) {
-    // Per-thread partial sums over its 4 rows for each of its 8 columns.
-    double e_abs[4][2], e_cnt[4][2], e_hng[4][2];
+    if (p.den_out) {
+      // Stash sigma2_i(gamma_g) = (U r)_ig so that the per-row outputs at the selected gamma need no
+      // second projection pass (the n x G matrix costs HBM capacity, not time: 8 B per MMA'd 2m flops).
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+      for (int i = 0; i < 4; ++i) {
+        const int row = t.m0 + acc_row(warp_m, i, lane);
+        if (row >= p.n_rows) continue;
 #pragma unroll
-      for (int e = 0; e < 2; ++e) e_abs[j][e] = e_cnt[j][e] = e_hng[j][e] = 0.0;
+        for (int j = 0; j < 4; ++j) {
+          const int col = t.n0 + acc_col(warp_n, j, lane);
+          double* o = p.den_out + (long long)row * p.den_ld + col;
+          if (col + 1 < p.G && (p.den_ld & 1) == 0) {
+            *reinterpret_cast<double2*>(o) = make_double2(acc.i[i][j][0], acc.i[i][j][1]);
+          } else {
+            if (col < p.G) o[0] = acc.i[i][j][0];
+            if (col + 1 < p.G) o[1] = acc.i[i][j][1];
+          }
+        }
+      }
+    }
+    // Leave-one-out residuals in place of the numerators, then the shared weighted reduction.
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int row = t.m0 + acc_row(warp_m, i, lane);
-      if (row >= p.n_rows) continue;
-      const double yi = p.y[row];
-      const double si = p.s[row];
+      const double yi = row < p.n_rows ? p.y[row] : 0.0;
+      const double si = row < p.n_rows ? p.s[row] : 0.0;
       const double s2 = si * si;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          double loo = (acc.r[i][j][e] - yi) / (1.0 - s2 * acc.i[i][j][e]);
-          if (p.is_classifier) {
-            if ((yi > 0.0 && loo > 0.0) || (yi < 0.0 && loo < 0.0)) loo = 0.0;
-          }
-          const double a = fabs(loo);
-          e_abs[j][e] += si * a;
-          if (p.is_classifier) {
-            e_cnt[j][e] += (a >= 1.0) ? si : 0.0;
-            e_hng[j][e] += si * fmax(0.0, a - 1.0);
-          }
-        }
+        for (int e = 0; e < 2; ++e) acc.r[i][j][e] = (acc.r[i][j][e] - yi) / (1.0 - s2 * acc.i[i][j][e]);
     }
-    // Reduce over the 8 row-lanes of the warp (lanes sharing lane%4), fixed butterfly order.
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int e = 0; e < 2; ++e)
-#pragma unroll
-        for (int off = 4; off < 32; off <<= 1) {
-          e_abs[j][e] += __shfl_xor_sync(0xffffffffu, e_abs[j][e], off);
-          e_cnt[j][e] += __shfl_xor_sync(0xffffffffu, e_cnt[j][e], off);
-          e_hng[j][e] += __shfl_xor_sync(0xffffffffu, e_hng[j][e], off);
-        }
-    double* red = reinterpret_cast<double*>(scratch);  // [3][4 warp_m][64 cols]
-    if ((lane >> 2) == 0) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int c = acc_col(warp_n, j, lane) + e;
-          red[(0 * 4 + warp_m) * BN + c] = e_abs[j][e];
-          red[(1 * 4 + warp_m) * BN + c] = e_cnt[j][e];
-          red[(2 * 4 + warp_m) * BN + c] = e_hng[j][e];
-        }
-    }
-    __syncthreads();
-    const int tid = threadIdx.x;
-    if (tid < 3 * BN) {
-      const int q = tid / BN, c = tid % BN;
-      const int g = t.n0 + c;
-      if (g < p.G) {
-        const double* r = red + (q * 4) * BN + c;
-        const double sum = ((r[0] + r[BN]) + r[2 * BN]) + r[3 * BN];
-        p.part[((long long)blockIdx.y * 3 + q) * p.G + g] = sum;
-      }
-    }
+    loo_reduce(acc, t, p.n_rows, p.G, p.y, p.s, p.is_classifier, p.part, warp_m, warp_n, lane, scratch);
   }
 };
 
@@ -306,7 +348,8 @@ struct OpSweep {
 // over the tile's columns.   reference: _neo_ls_svm.py:184 and :467-469 (eigenbasis / U^-1 form).
 // Output: part[n_tile][row] (reduced over n_tile in fixed order by rowsum_reduce_kernel).
 // =============================================================================================
-struct OpVariance {
+template <bool COMPLEX>
+struct OpVarianceT {
   struct Params {
     Operand A, B;
     int n_rows, m;
@@ -334,13 +377,13 @@ struct OpVariance {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const bool ok = col + e < p.m;
-        const double br = ok ? p.bias_r[col + e] : 0.0;
-        const double bi = ok ? p.bias_i[col + e] : 0.0;
+        const double br = (ok && COMPLEX) ? p.bias_r[col + e] : 0.0;
+        const double bi = (ok && COMPLEX) ? p.bias_i[col + e] : 0.0;
         const double w = ok ? p.w[col + e] : 0.0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const double tr = acc.r[i][j][e] + br;
-          const double ti = bi - acc.i[i][j][e];
+          const double ti = COMPLEX ? bi - acc.i[i][j][e] : 0.0;
           rs[i] += (tr * tr + ti * ti) * w;
         }
       }
@@ -361,6 +404,146 @@ struct OpVariance {
       const int row = t.m0 + tid;
       if (row < p.n_rows) p.part[(long long)blockIdx.x * p.part_ld + row] = red[tid] + red[BM + tid];
     }
+  }
+};
+
+using OpVariance = OpVarianceT<true>;   // primal: |phi B|^2 w
+using OpRowQuad = OpVarianceT<false>;  // dual:   (K B^T)^2 w
+
+// =============================================================================================
+// Dual path (reference _optimize_alpha_gamma, _neo_ls_svm.py:252-323, einsum-free restatement of
+// SURVEY.md §8c).  With SQ = sn*Q, r[k,g] = 1/(gamma_g + lam_k):
+//   OpDualCoef  : [alpha_mat ; SQ*SQ] r  ->  alpha_loo (n x G, and transposed), hdiag (0 -> eps, :281)
+//   OpDualCross : F SQ                    ->  G1 = F0 SQ (F0 = F with zero diagonal), M = G1 * SQ
+//   OpDualSweep : F alpha_loo (plane a) and M r (plane b)  ->  yhat_loo (:286) and the error sums
+// =============================================================================================
+struct OpDualCoef {
+  struct Params {
+    Operand A, B;
+    int n, G;
+    double* aloo;   // n x G
+    double* alooT;  // G x ldT
+    long long ldT;
+    double* hd;     // n x G
+    double eps;
+  };
+  static __device__ __forceinline__ Tile tile(const Params& p) {
+    Tile t;
+    t.n0 = blockIdx.x * BN;
+    t.m0 = blockIdx.y * BM;
+    t.k_begin = 0;
+    t.k_end = p.A.kext;
+    t.valid = true;
+    return t;
+  }
+  static __device__ __forceinline__ void epilogue(const Params& p, const Tile& t, Acc& acc, int warp_m, int warp_n,
+                                                  int lane, uint8_t*) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = t.m0 + acc_row(warp_m, i, lane);
+      if (row >= p.n) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = t.n0 + acc_col(warp_n, j, lane) + e;
+          if (col >= p.G) continue;
+          const double a = acc.r[i][j][e];
+          const double h = acc.i[i][j][e];
+          p.aloo[(long long)row * p.G + col] = a;
+          p.alooT[(long long)col * p.ldT + row] = a;
+          p.hd[(long long)row * p.G + col] = (h == 0.0) ? p.eps : h;
+        }
+    }
+  }
+};
+
+struct OpDualCross {
+  struct Params {
+    Operand A, B;
+    int n;
+    const double* SQ;
+    long long ld;
+    double fdiag;
+    double* G1;
+    double* M;
+  };
+  static __device__ __forceinline__ Tile tile(const Params& p) {
+    Tile t;
+    t.n0 = blockIdx.x * BN;
+    t.m0 = blockIdx.y * BM;
+    t.k_begin = 0;
+    t.k_end = p.A.kext;
+    t.valid = true;
+    return t;
+  }
+  static __device__ __forceinline__ void epilogue(const Params& p, const Tile& t, Acc& acc, int warp_m, int warp_n,
+                                                  int lane, uint8_t*) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = t.m0 + acc_row(warp_m, i, lane);
+      if (row >= p.n) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = t.n0 + acc_col(warp_n, j, lane) + e;
+          if (col >= p.n) continue;
+          const long long o = (long long)row * p.ld + col;
+          const double sq = p.SQ[o];
+          const double g1 = acc.r[i][j][e] - p.fdiag * sq;
+          p.G1[o] = g1;
+          p.M[o] = g1 * sq;
+        }
+    }
+  }
+};
+
+struct OpDualSweep {
+  struct Params {
+    Operand A, B;  // A = [F ; M] stacked, B = [alpha_loo^T ; r^T] stacked
+    int n_rows, G;
+    const double* y;
+    const double* s;
+    int is_classifier;
+    double* part;
+    const double* aloo;
+    const double* hd;
+    double fdiag;
+    double* yhat_loo;  // n x G
+  };
+  static __device__ __forceinline__ Tile tile(const Params& p) {
+    Tile t;
+    t.n0 = blockIdx.x * BN;
+    t.m0 = blockIdx.y * BM;
+    t.k_begin = 0;
+    t.k_end = p.A.kext;
+    t.valid = true;
+    return t;
+  }
+  static __device__ __forceinline__ void epilogue(const Params& p, const Tile& t, Acc& acc, int warp_m, int warp_n,
+                                                  int lane, uint8_t* scratch) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = t.m0 + acc_row(warp_m, i, lane);
+      const bool rok = row < p.n_rows;
+      const double yi = rok ? p.y[row] : 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = t.n0 + acc_col(warp_n, j, lane) + e;
+          double yh = 0.0;
+          if (rok && col < p.G) {
+            const long long o = (long long)row * p.G + col;
+            const double a = p.aloo[o];
+            yh = (-acc.i[i][j][e] / p.hd[o]) * a + (acc.r[i][j][e] - p.fdiag * a);
+            p.yhat_loo[o] = yh;
+          }
+          acc.r[i][j][e] = yh - yi;
+        }
+    }
+    loo_reduce(acc, t, p.n_rows, p.G, p.y, p.s, p.is_classifier, p.part, warp_m, warp_n, lane, scratch);
   }
 };
 

@@ -410,6 +410,140 @@ __global__ void quantile_epilogue_kernel(const double* __restrict__ yhat, const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Dual-path helpers
+// ---------------------------------------------------------------------------------------------
+// out[row, 0:cols] = in[row, 0:cols], zero in the pad columns (pitch conversion for TMA operands).
+__global__ void pad_rows_kernel(const double* __restrict__ in, long long ld_in, long long rows, int cols, int ld_out,
+                                double* __restrict__ out) {
+  const long long total = rows * ld_out;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(e % ld_out);
+    const long long row = e / ld_out;
+    out[e] = (j < cols) ? in[row * ld_in + j] : 0.0;
+  }
+}
+
+// y[i] = sum_j A[i, j] x[j]  (x == nullptr: row sums), one warp per row, fixed order.
+__global__ void gemv_rows_kernel(const double* __restrict__ A, long long ld, long long rows, int cols,
+                                 const double* __restrict__ x, double add, double* __restrict__ y) {
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const double* a = A + warp * ld;
+  double acc = 0.0;
+  for (int j = lane; j < cols; j += 32) acc += x ? a[j] * x[j] : a[j];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) y[warp] = acc + add;
+}
+
+__global__ void row_sqnorm_kernel(const double* __restrict__ A, long long ld, long long rows, int cols,
+                                  double* __restrict__ out) {
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const double* a = A + warp * ld;
+  double acc = 0.0;
+  for (int j = lane; j < cols; j += 32) acc += a[j] * a[j];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) out[warp] = acc;
+}
+
+// S[i, j] = sn_i F[i, j] sn_j  (dense n x n for the eigensolver).   _neo_ls_svm.py:265.
+__global__ void scale_sym_kernel(const double* __restrict__ F, long long ld, int n, const double* __restrict__ sn,
+                                 double* __restrict__ S) {
+  const long long total = (long long)n * n;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(e % n);
+    const int i = (int)(e / n);
+    S[e] = sn[i] * F[(long long)i * ld + j] * sn[j];
+  }
+}
+
+// out[k, j] = in[k, j] * col_scale[j]   (SQ^T from the eigensolver's column-major eigenvectors).
+__global__ void scale_cols_kernel(const double* __restrict__ in, long long ld_in, int rows, int cols,
+                                  const double* __restrict__ col_scale, long long ld_out, double* __restrict__ out) {
+  const long long total = (long long)rows * cols;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(e % cols);
+    const long long k = e / cols;
+    out[k * ld_out + j] = in[k * ld_in + j] * col_scale[j];
+  }
+}
+
+// out[c, r] = in[r, c] with independent pitches.
+__global__ void transpose_kernel(const double* __restrict__ in, long long ld_in, int rows, int cols,
+                                 double* __restrict__ out, long long ld_out) {
+  __shared__ double tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+    const int r = r0 + dy, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[dy][threadIdx.x] = in[(long long)r * ld_in + c];
+  }
+  __syncthreads();
+  for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+    const int c = c0 + dy, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) out[(long long)c * ld_out + r] = tile[threadIdx.x][dy];
+  }
+}
+
+// AB[i, k] = SQ[i, k] qsy[k]  (alpha_mat, :268);  AB[n + i, k] = SQ[i, k]^2.
+__global__ void dual_ab_kernel(const double* __restrict__ SQ, long long ld, int n, const double* __restrict__ qsy,
+                               double* __restrict__ AB) {
+  const long long total = (long long)n * n;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(e % n);
+    const long long i = e / n;
+    const double v = SQ[i * ld + k];
+    AB[i * ld + k] = v * qsy[k];
+    AB[(n + i) * ld + k] = v * v;
+  }
+}
+
+// x[k] = qsy[k] / (gamma + lam[k]).
+__global__ void dual_coef_kernel(const double* __restrict__ qsy, const double* __restrict__ lam, int n, double gamma,
+                                 double* __restrict__ x) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) x[k] = qsy[k] / (gamma + lam[k]);
+}
+
+// sigma2_i = 1 - sum_k (G1[i,k] + fdiag SQ[i,k] - colsum[k])^2 / (gamma + lam_k)   (K_rbf SQ in the
+// eigenbasis; equals 1 - k_i^T (gamma S^-2 + F)^-1 k_i of _neo_ls_svm.py:321-322).  One warp per row.
+__global__ void dual_sigma2_kernel(const double* __restrict__ G1, const double* __restrict__ SQ, long long ld, int n,
+                                   const double* __restrict__ colsum, const double* __restrict__ lam, double fdiag,
+                                   double gamma, double* __restrict__ sigma2) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const double* g = G1 + (long long)warp * ld;
+  const double* q = SQ + (long long)warp * ld;
+  double acc = 0.0;
+  for (int k = lane; k < n; k += 32) {
+    const double v = g[k] + fdiag * q[k] - colsum[k];
+    acc += v * v / (gamma + lam[k]);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) sigma2[warp] = 1.0 - acc;
+}
+
+// M[i, i] += gamma / sn_i^2   (:313).
+__global__ void dual_add_diag_kernel(double* __restrict__ M, int n, const double* __restrict__ sn, double gamma) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) M[(long long)i * n + i] += gamma / (sn[i] * sn[i]);
+}
+
+__global__ void one_minus_sqrt_kernel(const double* __restrict__ in, int n, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = sqrt(1.0 - in[i]);
+}
+
 // Register-resident DMMA loop for measuring the FP64 tensor peak (roofline denominator).
 __global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* __restrict__ sink) {
   double c[16][2];

@@ -44,13 +44,13 @@ def _case(name, g):
 
 
 @pytest.mark.parametrize("name", PRIMAL)
-@pytest.mark.parametrize("chunk", [640, 32768])
-def test_primal_fit_matches_reference(name, chunk, golden, gpu):
+@pytest.mark.parametrize("chunk,stash", [(640, True), (32768, False)])
+def test_primal_fit_matches_reference(name, chunk, stash, golden, gpu):
     ctx, dev, _primal, torch = gpu
     g = golden(name)
     X, y_, s, Xt, classifier, shift, W = _case(name, g)
     ctx.set_chunk_rows(chunk)
-    fit = _primal.primal_fit(dev(X), dev(y_), dev(s), dev(shift), dev(W), classifier, ctx=ctx)
+    fit = _primal.primal_fit(dev(X), dev(y_), dev(s), dev(shift), dev(W), classifier, ctx=ctx, stash=stash)
     assert fit.opt == int(g["opt"]), "selected γ index must equal the reference's"
     assert fit.gamma == float(g["gamma"])
     assert rel_err(fit.loo_errors, g["loo_errors"]) < TOL_FIT
