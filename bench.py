@@ -179,6 +179,8 @@ def run_ours(args) -> None:
     sh = torch.from_numpy(s).pin_memory()
     shd, Wd = torch.from_numpy(shift).to(dev), torch.from_numpy(W).to(dev)
     ctx = _lib.context(local_rank)
+    # FP64 tensor peak of this device, measured before any sustained load ("burst" figure).
+    peak_burst = ctx.dmma_peak_tflops(20000) if rank == 0 else 0.0
 
     def barrier():
         if world > 1:
@@ -205,7 +207,8 @@ def run_ours(args) -> None:
     Xd, yd, sd = Xh.to(dev), yh.to(dev), sh.to(dev)
     for _ in range(args.warmup):
         fit = solve(Xd, yd, sd)
-    peak_tflops = ctx.dmma_peak_tflops(20000) if rank == 0 else 0.0
+    peak_sustained = ctx.dmma_peak_tflops(20000) if rank == 0 else 0.0  # same loop right after the warm-up fits
+    peak_tflops = max(peak_burst, peak_sustained)
     sampler = ClockSampler(local_rank)
     launches0 = ctx.launch_count()
     ctx.profile(True)
@@ -271,8 +274,10 @@ def run_ours(args) -> None:
                 "bound": "tensor", "kernel": "gemm_kernel<MODE_COMPLEX, OpProject> (T = φQ, 8m² flop/row)",
                 "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
                 "frac": achieved / peak_tflops if peak_tflops else None,
-                "peak_source": "FP64 DMMA register-loop peak measured in this run (nls_bench_dmma_peak); "
-                               "MEASURED_PEAKS.json has no FP64 figure",
+                "peak_source": "FP64 DMMA register-resident loop measured in this run (nls_bench_dmma_peak), the larger "
+                               "of a cold-start burst and a post-warm-up reading; MEASURED_PEAKS.json has no FP64 "
+                               "figure. 148 SMs x 64 FMA/clk x 1.965 GHz = 37.2 TFLOP/s nominal",
+                "peak_burst": peak_burst, "peak_sustained": peak_sustained,
                 "traffic": None,
                 "fit_tflops": fit_tflops, "fit_frac": fit_tflops / (peak_tflops * world) if peak_tflops else None,
                 "kernel_ms": kernel_share,
