@@ -10,8 +10,9 @@
 //    tcgen05/TMEM has no FP64 kind, so DMMA + register accumulators is the sm_100a FP64 tensor path.
 //  * One elected thread streams operand tiles with TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) into
 //    a 4-stage ring guarded by full/empty mbarriers, two k-tiles ahead of the math.
-//  * Fragment loads are conflict-free: with the 128B swizzle, the 32 lanes of an 8x4 (or 4x8)
-//    fragment hit each of the 16 eight-byte bank pairs exactly twice (the 2-wavefront minimum).
+//  * Fragment loads are conflict-free: with the 128B swizzle and the k assignment
+//    {2c, 2c+1, 2c+8, 2c+9} per MMA step, each half-warp of an 8x4 (or 4x8) fragment load hits 16
+//    distinct eight-byte bank pairs (the 2-wavefront minimum for a 256-byte warp load).
 //
 // Three arithmetic modes (operand "planes" are separate TMA boxes):
 //   MODE_REAL     R += xa.ya                                   (1 A plane, 1 B plane)
@@ -89,7 +90,11 @@ __device__ __forceinline__ void mma_stage(Acc& acc, uint32_t stage_base, int war
   const int q = lane & 3;
 #pragma unroll
   for (int kk = 0; kk < BK / 4; ++kk) {
-    const uint32_t lo = r8 * 128 + ((((2 * kk + (q >> 1)) ^ r8) & 7) << 4) + ((q & 1) << 3);
+    // MMA step kk contracts k = {2kk, 2kk+1, 2kk+8, 2kk+9} of the stage (any order of the reduction
+    // index is valid as long as A and B agree).  The two k-pairs of a lane quad then sit in 16-byte
+    // chunks kk and kk+4, so the 16 lanes of each half-warp (rows r8..r8+3, XOR-swizzled) hit 16
+    // distinct 8-byte bank pairs: one conflict-free wavefront per half-warp.
+    const uint32_t lo = r8 * 128 + ((((kk + 4 * (q >> 1)) ^ r8) & 7) << 4) + ((q & 1) << 3);
     double xa[4], xb[4], ya[4], yb[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
