@@ -179,6 +179,7 @@ def run_ours(args) -> None:
     sh = torch.from_numpy(s).pin_memory()
     shd, Wd = torch.from_numpy(shift).to(dev), torch.from_numpy(W).to(dev)
     ctx = _lib.context(local_rank)
+    ctx.set_eigensolver(args.eig)
     # FP64 tensor peak of this device, measured before any sustained load ("burst" figure).
     peak_burst = ctx.dmma_peak_tflops(20000) if rank == 0 else 0.0
 
@@ -265,6 +266,7 @@ def run_ours(args) -> None:
                          "stream through HBM)" % (Xh.numel() * 8 / 1e6),
                 "feature_map": f"OrthogonalRandomFourierFeatures({D}) fitted on the first {min(PREPASS_ROWS, n)} rows (host pre-pass, untimed)",
                 "selected_gamma_index": fit.opt,
+                "eigensolver": args.eig, "jacobi_sweeps": ctx.last_eig_sweeps(),
             },
             "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
@@ -278,7 +280,9 @@ def run_ours(args) -> None:
                                "of a cold-start burst and a post-warm-up reading; MEASURED_PEAKS.json has no FP64 "
                                "figure. 148 SMs x 64 FMA/clk x 1.965 GHz = 37.2 TFLOP/s nominal",
                 "peak_burst": peak_burst, "peak_sustained": peak_sustained,
-                "traffic": None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one projection launch (32768 rows) from
+                # profiles/r1_ncu_full_gemm_kernels.md; algorithmic bytes: 571 MB in + 537 MB out.
+                "traffic": 1.0895e9 if rows_local >= 32768 else None,
                 "fit_tflops": fit_tflops, "fit_frac": fit_tflops / (peak_tflops * world) if peak_tflops else None,
                 "kernel_ms": kernel_share,
             },
@@ -296,6 +300,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--rows", type=int, default=N_ROWS, help="total training rows (default: config C3)")
+    ap.add_argument("--eig", choices=["auto", "jacobi", "cusolver"], default="auto",
+                    help="stage-3 eigensolver: hand-written block Jacobi (auto for m<=1100) or the cuSOLVER comparator")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

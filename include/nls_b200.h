@@ -85,6 +85,12 @@ int nls_primal_gram(nls_ctx* ctx, const double* X, const double* y, const double
  * A: m x m complex128 (only needs to be Hermitian), lam_out: m, Q_out: m x m complex128.
  * ------------------------------------------------------------------------------------------- */
 int nls_heev(nls_ctx* ctx, const double* A, int m, double scale, double* lam_out, double* Q_out);
+/* Which solver nls_heev runs: 0 = the hand-written parallel two-sided block Jacobi kernels
+ * (csrc/jacobi.cuh), 1 = cuSOLVER Zheevd (library comparator), 2 = auto (default: Jacobi for
+ * m <= 1100, cuSOLVER above).  Also selectable with NLS_EIG=jacobi|cusolver. */
+int nls_ctx_set_eigensolver(nls_ctx* ctx, int kind);
+/* Number of Jacobi sweeps the last nls_heev call needed (0 for cuSOLVER). */
+int nls_ctx_last_eig_sweeps(const nls_ctx* ctx);
 
 /* ---------------------------------------------------------------------------------------------
  * Small replicated solves between the stages (O(m^2) / O(m^3), every rank computes the same).

@@ -40,6 +40,8 @@ def _signatures(lib: C.CDLL) -> None:
         "nls_affine_map": ([p, p, i64, i, p, p, i, p], i),
         "nls_primal_gram": ([p, p, p, p, i64, i, p, p, i, p, p], i),
         "nls_heev": ([p, p, i, d, p, p], i),
+        "nls_ctx_set_eigensolver": ([p, i], i),
+        "nls_ctx_last_eig_sweeps": ([p], i),
         "nls_primal_coeffs": ([p, p, p, p, i, d, d, p, p], i),
         "nls_cholesky_solve": ([p, p, i, d, p, p, p], i),
         "nls_primal_loo_sweep": ([p, p, p, p, i64, i, p, p, i, p, p, p, d, p, i, i, p, p], i),
@@ -126,6 +128,13 @@ class Context:
     # -- bookkeeping ---------------------------------------------------------------------------
     def set_chunk_rows(self, rows: int) -> None:
         check(self.lib.nls_ctx_set_chunk_rows(self.handle, rows))
+
+    def set_eigensolver(self, kind: str) -> None:
+        """'jacobi' (hand-written block Jacobi kernels), 'cusolver' (library comparator) or 'auto' (default)."""
+        check(self.lib.nls_ctx_set_eigensolver(self.handle, {"jacobi": 0, "cusolver": 1, "auto": 2}[kind]))
+
+    def last_eig_sweeps(self) -> int:
+        return int(self.lib.nls_ctx_last_eig_sweeps(self.handle))
 
     def launch_count(self) -> int:
         return int(self.lib.nls_ctx_launch_count(self.handle))

@@ -1,0 +1,264 @@
+// jacobi.cuh — hand-written Hermitian eigensolver for stage 3: parallel two-sided block Jacobi.
+//
+// Replaces scipy.linalg.eigh at _neo_ls_svm.py:120 for the m x m complex Hermitian matrix A/c.
+// (One-sided / Hestenes Jacobi on A was prototyped first and rejected: it implicitly works on A^2,
+// and the Gram matrices of this path have spectra graded over >14 decades, on which it stalls.)
+//
+// The index range [0, mp) (mp = m padded to an even number of 4-wide blocks) is cut into 4-wide blocks;
+// a round-robin tournament pairs the blocks so that every round holds nb/2 disjoint pivot pairs of 8
+// indices.  One round is two kernels:
+//   jacobi_pivot_kernel  : one warp per pair diagonalises its 8 x 8 Hermitian pivot block with cyclic
+//                          Jacobi rotations in shared memory (32 lanes = 8 rows x 4 disjoint rotations),
+//                          accumulating the 8 x 8 unitary J_i.
+//   jacobi_update_kernel : G <- J^H G J tile by tile (tile (i,j) = J_i^H G[I_i, I_j] J_j, read and written
+//                          by one warp only, so the update is in place) and V <- V J, as complex 8x8x8
+//                          products on DMMA.8x8x4.
+// A rotation is skipped when |g_pq| <= eps ||G||_F (absolute threshold: the decomposition is backward
+// stable w.r.t. ||A||, like LAPACK's zheevr); the sweep loop ends when no pair rotated.  Pad
+// rows/columns are exactly zero, never rotate, and are dropped at the end.  One sweep (nb-1 rounds x 2
+// kernels) is captured once into a CUDA graph and replayed, so the ~500 launches per sweep cost no
+// host time.
+#pragma once
+#include "ptx.cuh"
+
+namespace nls {
+
+constexpr int JB = 4;       // block width
+constexpr int JP = 2 * JB;  // indices per pivot pair
+
+// Pair `slot` of round `round` in a round-robin tournament over n (even) players.
+__device__ __forceinline__ void rr_pair(int n, int round, int slot, int& p, int& q) {
+  const int r = n - 1;
+  if (slot == 0) {
+    p = r;
+    q = round;
+  } else {
+    p = (round + slot) % r;
+    q = (round - slot + r) % r;
+  }
+}
+
+// Global index of local index a (0..7) of the pair (bp, bq) of 4-wide blocks.
+__device__ __forceinline__ int pair_index(int bp, int bq, int a) { return a < JB ? bp * JB + a : bq * JB + a - JB; }
+
+// G (planar, row-major, pitch ld) = scale * A (interleaved complex, m x m) zero-padded to mp; V = I.
+__global__ void jacobi_init_kernel(const double* __restrict__ A, int m, int mp, double scale, double* __restrict__ Gr,
+                                   double* __restrict__ Gi, double* __restrict__ Vr, double* __restrict__ Vi) {
+  const long long total = (long long)mp * mp;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % mp), r = (int)(e / mp);
+    double re = 0.0, im = 0.0;
+    if (r < m && c < m) {
+      re = scale * A[((long long)r * m + c) * 2];
+      im = scale * A[((long long)r * m + c) * 2 + 1];
+    }
+    Gr[e] = re;
+    Gi[e] = (r == c) ? 0.0 : im;
+    Vr[e] = (r == c) ? 1.0 : 0.0;
+    Vi[e] = 0.0;
+  }
+}
+
+// sum of squares of a vector (single block, fixed order).
+__global__ void sumsq_kernel(const double* __restrict__ a, const double* __restrict__ b, long long n,
+                             double* __restrict__ out) {
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (long long e = threadIdx.x; e < n; e += blockDim.x) acc += a[e] * a[e] + b[e] * b[e];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+    out[0] = t;
+  }
+}
+
+// One warp per pivot pair: J_i = eigenvectors of G[I_i, I_i] by cyclic two-sided Jacobi.
+// Jbuf: [pair][2][8][8] (Re, Im), flags[pair] = 1 if any rotation was applied, *active += #rotating pairs.
+__global__ void __launch_bounds__(128) jacobi_pivot_kernel(const double* __restrict__ Gr, const double* __restrict__ Gi,
+                                                           int ld, int nb, int round,
+                                                           const double* __restrict__ thr /* [abs^2, rel^2] */,
+                                                           int max_inner, double* __restrict__ Jbuf, int* __restrict__ flags,
+                                                           int* __restrict__ active) {
+  __shared__ double sm[4][4][8][9];  // per warp: Sr, Si, Jr, Ji
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.x * 4 + warp;
+  if (pair >= nb / 2) return;
+  double(*Sr)[9] = sm[warp][0];
+  double(*Si)[9] = sm[warp][1];
+  double(*Jr)[9] = sm[warp][2];
+  double(*Ji)[9] = sm[warp][3];
+  int bp, bq;
+  rr_pair(nb, round, pair, bp, bq);
+  for (int e = lane; e < 64; e += 32) {
+    const int a = e >> 3, b = e & 7;
+    const long long o = (long long)pair_index(bp, bq, a) * ld + pair_index(bp, bq, b);
+    Sr[a][b] = Gr[o];
+    Si[a][b] = Gi[o];
+    Jr[a][b] = (a == b) ? 1.0 : 0.0;
+    Ji[a][b] = 0.0;
+  }
+  __syncwarp();
+  const int i = lane >> 2, slot = lane & 3;
+  const double thr_abs2 = thr[0], thr_rel2 = thr[1];
+  bool any_total = false;
+  for (int sweep = 0; sweep < max_inner; ++sweep) {
+    bool any = false;
+    for (int r = 0; r < 7; ++r) {
+      int p, q;
+      rr_pair(8, r, slot, p, q);
+      const double a = Sr[p][p], b = Sr[q][q], zr = Sr[p][q], zi = Si[p][q];
+      const double az2 = zr * zr + zi * zi;
+      // Rotate unless |g_pq| is below the absolute noise floor eps ||G||_F (and, optionally, negligible
+      // relative to its diagonal pair).  A purely relative test never terminates on the numerically
+      // rank-deficient Gram matrices of this path: their null-space block is rounding noise.
+      const bool rot = az2 > thr_abs2 && az2 > thr_rel2 * fabs(a * b);
+      double c = 1.0, s = 0.0, er = 1.0, ei = 0.0;
+      if (rot) {
+        const double inv_az = rsqrt(az2);
+        const double tau = 0.5 * (b - a) * inv_az;
+        const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+        c = rsqrt(1.0 + t * t);
+        s = t * c;
+        er = zr * inv_az;
+        ei = zi * inv_az;
+      }
+      any |= rot;
+      const double wr = s * er, wi = s * ei;  // w = s e
+      __syncwarp();
+      {  // columns p, q of S and J, row i:  x_p' = c x_p - conj(w) x_q ;  x_q' = w x_p + c x_q
+        const double pr = Sr[i][p], pi = Si[i][p], qr = Sr[i][q], qi = Si[i][q];
+        Sr[i][p] = c * pr - (wr * qr + wi * qi);
+        Si[i][p] = c * pi - (wr * qi - wi * qr);
+        Sr[i][q] = (wr * pr - wi * pi) + c * qr;
+        Si[i][q] = (wr * pi + wi * pr) + c * qi;
+        const double jpr = Jr[i][p], jpi = Ji[i][p], jqr = Jr[i][q], jqi = Ji[i][q];
+        Jr[i][p] = c * jpr - (wr * jqr + wi * jqi);
+        Ji[i][p] = c * jpi - (wr * jqi - wi * jqr);
+        Jr[i][q] = (wr * jpr - wi * jpi) + c * jqr;
+        Ji[i][q] = (wr * jpi + wi * jpr) + c * jqi;
+      }
+      __syncwarp();
+      {  // rows p, q of S, column i:  x_p' = c x_p - w x_q ;  x_q' = conj(w) x_p + c x_q
+        const double pr = Sr[p][i], pi = Si[p][i], qr = Sr[q][i], qi = Si[q][i];
+        Sr[p][i] = c * pr - (wr * qr - wi * qi);
+        Si[p][i] = c * pi - (wr * qi + wi * qr);
+        Sr[q][i] = (wr * pr + wi * pi) + c * qr;
+        Si[q][i] = (wr * pi - wi * pr) + c * qi;
+      }
+      __syncwarp();
+      if (rot && i == 0) {  // the rotated pivot is diagonal by construction: remove the rounding residue
+        Sr[p][q] = Sr[q][p] = 0.0;
+        Si[p][q] = Si[q][p] = 0.0;
+        Si[p][p] = Si[q][q] = 0.0;
+      }
+      __syncwarp();
+    }
+    if (!__any_sync(0xffffffffu, any)) break;
+    any_total = true;
+  }
+  double* out = Jbuf + (long long)pair * 128;
+  for (int e = lane; e < 64; e += 32) {
+    out[e] = Jr[e >> 3][e & 7];
+    out[64 + e] = Ji[e >> 3][e & 7];
+  }
+  if (lane == 0) {
+    flags[pair] = any_total ? 1 : 0;
+    if (any_total) atomicAdd(active, 1);
+  }
+}
+
+// G <- J^H G J and V <- V J for one round, one warp per 8 x 8 tile.
+__global__ void __launch_bounds__(256) jacobi_update_kernel(double* __restrict__ Gr, double* __restrict__ Gi,
+                                                            double* __restrict__ Vr, double* __restrict__ Vi, int ld,
+                                                            int nb, int round, const double* __restrict__ Jbuf,
+                                                            const int* __restrict__ flags) {
+  __shared__ double ts[8][2][8][9];  // per warp: T (Re, Im) for the accumulator -> operand relayout
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int np = nb / 2;
+  const int rb = nb * JB / 8;  // 8-row blocks of V
+  const long long n_g = (long long)np * np;
+  const long long total = n_g + (long long)rb * np;
+  const int fr = lane >> 2, fk = lane & 3;
+  for (long long task = (long long)blockIdx.x * 8 + warp; task < total; task += (long long)gridDim.x * 8) {
+    const bool is_g = task < n_g;
+    const int i = is_g ? (int)(task / np) : (int)((task - n_g) / np);  // pair index (G) or row block (V)
+    const int j = is_g ? (int)(task % np) : (int)((task - n_g) % np);
+    const bool fj = flags[j] != 0;
+    const bool fi = is_g && flags[i] != 0;
+    if (!fi && !fj) continue;  // warp-uniform
+    int jp, jq;
+    rr_pair(nb, round, j, jp, jq);
+    int ip = 0, iq = 0;
+    if (is_g) rr_pair(nb, round, i, ip, iq);
+    double* Mr = is_g ? Gr : Vr;
+    double* Mi = is_g ? Gi : Vi;
+    const int row = is_g ? pair_index(ip, iq, fr) : i * 8 + fr;
+    // ---- T = M_tile * J_j  (identity if pair j did not rotate) ----
+    double tr[2] = {0.0, 0.0}, ti[2] = {0.0, 0.0};
+    const double* Jj = Jbuf + (long long)j * 128;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const long long o = (long long)row * ld + pair_index(jp, jq, 4 * ks + fk);
+      const double ar = Mr[o], ai = Mi[o];
+      const double br = Jj[(4 * ks + fk) * 8 + fr], bi = Jj[64 + (4 * ks + fk) * 8 + fr];
+      dmma(tr[0], tr[1], ar, br);
+      dmma(tr[0], tr[1], -ai, bi);
+      dmma(ti[0], ti[1], ar, bi);
+      dmma(ti[0], ti[1], ai, br);
+    }
+    double outr[2] = {tr[0], tr[1]}, outi[2] = {ti[0], ti[1]};
+    if (is_g) {
+      // ---- out = J_i^H * T ----
+      double(*Tr)[9] = ts[warp][0];
+      double(*Ti)[9] = ts[warp][1];
+      __syncwarp();
+      Tr[fr][2 * fk] = tr[0];
+      Tr[fr][2 * fk + 1] = tr[1];
+      Ti[fr][2 * fk] = ti[0];
+      Ti[fr][2 * fk + 1] = ti[1];
+      __syncwarp();
+      const double* Ji_ = Jbuf + (long long)i * 128;
+      outr[0] = outr[1] = outi[0] = outi[1] = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        // A operand: (J_i^H)[m = fr][k] = conj(J_i[k][fr]);  B operand: T[k][n = fr]
+        const double ar = Ji_[(4 * ks + fk) * 8 + fr], ai = Ji_[64 + (4 * ks + fk) * 8 + fr];
+        const double br = Tr[4 * ks + fk][fr], bi = Ti[4 * ks + fk][fr];
+        dmma(outr[0], outr[1], ar, br);
+        dmma(outr[0], outr[1], ai, bi);
+        dmma(outi[0], outi[1], ar, bi);
+        dmma(outi[0], outi[1], -ai, br);
+      }
+    }
+    const long long o = (long long)row * ld + pair_index(jp, jq, 2 * fk);
+    *reinterpret_cast<double2*>(Mr + o) = make_double2(outr[0], outr[1]);
+    *reinterpret_cast<double2*>(Mi + o) = make_double2(outi[0], outi[1]);
+  }
+}
+
+__global__ void jacobi_diag_kernel(const double* __restrict__ Gr, int ld, int m, double* __restrict__ lam) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < m) lam[k] = Gr[(long long)k * ld + k];
+}
+
+// Q_out[l, k] = V[l, perm[k]] (interleaved complex, m x m), lam_out[k] = lam_raw[perm[k]].
+__global__ void jacobi_gather_kernel(const double* __restrict__ Vr, const double* __restrict__ Vi, int ld, int m,
+                                     const int* __restrict__ perm, const double* __restrict__ lam_raw,
+                                     double* __restrict__ Q_out, double* __restrict__ lam_out) {
+  const long long total = (long long)m * m;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(e % m), l = (int)(e / m);
+    const long long o = (long long)l * ld + perm[k];
+    Q_out[2 * e] = Vr[o];
+    Q_out[2 * e + 1] = Vi[o];
+  }
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < m; k += gridDim.x * blockDim.x) lam_out[k] = lam_raw[perm[k]];
+}
+
+}  // namespace nls

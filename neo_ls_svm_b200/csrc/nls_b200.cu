@@ -15,6 +15,7 @@
 #include "../../include/nls_b200.h"
 #include "ops.cuh"
 #include "small_kernels.cuh"
+#include "jacobi.cuh"
 
 using namespace nls;
 
@@ -77,11 +78,19 @@ struct nls_ctx {
   int64_t chunk_rows = 32768;
   int64_t launches = 0;
   bool use_tma = true;
+  int eig_kind = 2;  // 0: hand-written block Jacobi, 1: cuSOLVER Zheevd (library comparator), 2: auto
+  int eig_sweeps = 0;  // sweeps used by the last Jacobi solve
+  cudaStream_t jac_stream = nullptr;  // side stream (graph capture is not allowed on the legacy default stream)
+  cudaGraphExec_t jac_graph = nullptr;
+  const void* jac_graph_key = nullptr;
+  int jac_graph_nb = 0;
+  int jac_inner = 2;  // cyclic sweeps per 8x8 pivot solve (partial diagonalisation is enough for block Jacobi)
   EncodeTiledFn encode = nullptr;
   cusolverDnHandle_t solver = nullptr;
   // scratch (grow-only, zero-filled when (re)allocated)
   DevBuf xc, wt, psi, psiT, pu, bt, rt, small, part, gram_ws, border, rowtmp, solver_ws, solver_mat;
   // dual path (state kept between nls_dual_sweep and nls_dual_finalize)
+  DevBuf jac_mat, jac_small;
   DevBuf d_xpad, d_xq, d_norm, d_fm, d_sq, d_sqt, d_g1, d_ab, d_ra, d_vec, d_ng, d_kq, d_btp;
   int dual_n = 0;
   // profiling
@@ -297,6 +306,11 @@ extern "C" int nls_ctx_create(int device, void* stream, nls_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   const char* env = getenv("NLS_NO_TMA");
   ctx->use_tma = !(env && env[0] == '1');
+  env = getenv("NLS_EIG");
+  if (env && strcmp(env, "cusolver") == 0) ctx->eig_kind = 1;
+  if (env && strcmp(env, "jacobi") == 0) ctx->eig_kind = 0;
+  env = getenv("NLS_JACOBI_INNER");
+  if (env && atoi(env) > 0) ctx->jac_inner = atoi(env);
   env = getenv("NLS_CHUNK_ROWS");
   if (env && atoll(env) > 0) ctx->chunk_rows = round_up(atoll(env), 128);
   void* fn = nullptr;
@@ -322,7 +336,7 @@ extern "C" int nls_ctx_destroy(nls_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->xc, &ctx->wt, &ctx->psi, &ctx->psiT, &ctx->pu, &ctx->bt, &ctx->rt, &ctx->small,
                     &ctx->part, &ctx->gram_ws, &ctx->border, &ctx->rowtmp, &ctx->solver_ws, &ctx->solver_mat,
-                    &ctx->d_xpad, &ctx->d_xq, &ctx->d_norm, &ctx->d_fm, &ctx->d_sq, &ctx->d_sqt, &ctx->d_g1,
+                    &ctx->jac_mat, &ctx->jac_small, &ctx->d_xpad, &ctx->d_xq, &ctx->d_norm, &ctx->d_fm, &ctx->d_sq, &ctx->d_sqt, &ctx->d_g1,
                     &ctx->d_ab, &ctx->d_ra, &ctx->d_vec, &ctx->d_ng, &ctx->d_kq, &ctx->d_btp};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
@@ -331,6 +345,8 @@ extern "C" int nls_ctx_destroy(nls_ctx* ctx) {
     cudaEventDestroy(s.b);
   }
   if (ctx->solver) cusolverDnDestroy(ctx->solver);
+  if (ctx->jac_graph) cudaGraphExecDestroy(ctx->jac_graph);
+  if (ctx->jac_stream) cudaStreamDestroy(ctx->jac_stream);
   delete ctx;
   return NLS_OK;
 }
@@ -477,10 +493,10 @@ extern "C" int nls_primal_gram(nls_ctx* ctx, const double* X, const double* y, c
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stage 3 (round 1: cuSOLVER divide & conquer as the library baseline; the hand-written blocked
-// Jacobi solver replaces it behind the same entry point — see DESIGN.md)
+// Stage 3: hand-written parallel block Jacobi (default) or cuSOLVER Zheevd (library comparator,
+// NLS_EIG=cusolver / nls_ctx_set_eigensolver) behind the same entry point.
 // ---------------------------------------------------------------------------------------------
-extern "C" int nls_heev(nls_ctx* ctx, const double* A, int m, double scale, double* lam_out, double* Q_out) {
+static int heev_cusolver(nls_ctx* ctx, const double* A, int m, double scale, double* lam_out, double* Q_out) {
   if (!ctx || !A || !lam_out || !Q_out || m < 1) return fail(NLS_ERR_INVALID, "bad argument to nls_heev");
   CUDA_TRY(cudaSetDevice(ctx->device));
   const long long mm = (long long)m * m;
@@ -507,6 +523,106 @@ extern "C" int nls_heev(nls_ctx* ctx, const double* A, int m, double scale, doub
   if (h_info != 0) return fail(NLS_ERR_SOLVER, "Hermitian eigensolver failed: info = %d", h_info);
   return NLS_OK;
 }
+
+
+// Hand-written parallel two-sided block Jacobi (csrc/jacobi.cuh).
+static int heev_jacobi(nls_ctx* ctx, const double* A, int m, double scale, double* lam_out, double* Q_out) {
+  if (!ctx || !A || !lam_out || !Q_out || m < 1) return fail(NLS_ERR_INVALID, "bad argument to nls_heev");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  int nb = (m + JB - 1) / JB;
+  if (nb & 1) ++nb;
+  if (nb < 2) nb = 2;
+  const int mp = nb * JB, np = nb / 2;
+  const size_t mm = (size_t)mp * mp;
+  NLS_TRY(ensure(ctx, ctx->jac_mat, 4 * mm * 8));
+  NLS_TRY(ensure(ctx, ctx->jac_small, (size_t)np * 128 * 8 + (size_t)(np + 8) * 4 + (size_t)(2 * mp + 8) * 8 + (size_t)mp * 4));
+  double* Gr = (double*)ctx->jac_mat.p;
+  double* Gi = Gr + mm;
+  double* Vr = Gi + mm;
+  double* Vi = Vr + mm;
+  double* Jbuf = (double*)ctx->jac_small.p;
+  double* lam_raw = Jbuf + (size_t)np * 128;
+  double* fro2 = lam_raw + mp;
+  int* flags = (int*)(fro2 + 8);
+  int* active = flags + np;
+  int* perm = active + 8;
+  ProfScope scope(ctx, NLS_PROF_OTHER);
+  jacobi_init_kernel<<<grid_for((long long)mm), 256, 0, ctx->stream>>>(A, m, mp, scale, Gr, Gi, Vr, Vi);
+  NLS_TRY(check_launch(ctx, "jacobi_init_kernel"));
+  sumsq_kernel<<<1, 1024, 0, ctx->stream>>>(Gr, Gi, (long long)mm, fro2);
+  NLS_TRY(check_launch(ctx, "sumsq_kernel"));
+  double h_fro2 = 0.0;
+  CUDA_TRY(cudaMemcpyAsync(&h_fro2, fro2, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  const double eps = 2.220446049250313e-16;
+  double h_thr[2] = {eps * eps * h_fro2, 0.0};  // squared thresholds: absolute (eps ||G||_F), relative (off)
+  double* thr = fro2 + 2;
+  CUDA_TRY(cudaMemcpyAsync(thr, h_thr, 16, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  const long long tasks = (long long)np * np + (long long)(mp / 8) * np;
+  const int upd_grid = (int)std::min<long long>((tasks + 7) / 8, (long long)ctx->sm_count * 8);
+  if (!ctx->jac_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->jac_stream, cudaStreamNonBlocking));
+  if (!ctx->jac_graph || ctx->jac_graph_key != (const void*)Gr || ctx->jac_graph_nb != nb) {
+    // Capture one sweep: reset the rotation counter, then nb-1 rounds of (pivot, update).
+    if (ctx->jac_graph) {
+      cudaGraphExecDestroy(ctx->jac_graph);
+      ctx->jac_graph = nullptr;
+    }
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(ctx->jac_stream, cudaStreamCaptureModeRelaxed));
+    cudaMemsetAsync(active, 0, sizeof(int), ctx->jac_stream);
+    for (int round = 0; round < nb - 1; ++round) {
+      jacobi_pivot_kernel<<<(np + 3) / 4, 128, 0, ctx->jac_stream>>>(Gr, Gi, mp, nb, round, thr, ctx->jac_inner, Jbuf, flags, active);
+      jacobi_update_kernel<<<upd_grid, 256, 0, ctx->jac_stream>>>(Gr, Gi, Vr, Vi, mp, nb, round, Jbuf, flags);
+    }
+    CUDA_TRY(cudaStreamEndCapture(ctx->jac_stream, &graph));
+    cudaError_t ge = cudaGraphInstantiate(&ctx->jac_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ge != cudaSuccess) return fail(NLS_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ge));
+    ctx->jac_graph_key = (const void*)Gr;
+    ctx->jac_graph_nb = nb;
+  }
+  int sweep = 0, h_active = 1;
+  const int max_sweeps = 60;
+  for (; sweep < max_sweeps && h_active > 0; ++sweep) {
+    CUDA_TRY(cudaGraphLaunch(ctx->jac_graph, ctx->jac_stream));
+    ctx->launches += 2 * (nb - 1);
+    CUDA_TRY(cudaMemcpyAsync(&h_active, active, sizeof(int), cudaMemcpyDeviceToHost, ctx->jac_stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->jac_stream));
+  }
+  ctx->eig_sweeps = sweep;
+  if (h_active > 0) return fail(NLS_ERR_SOLVER, "Jacobi eigensolver did not converge in %d sweeps", max_sweeps);
+  jacobi_diag_kernel<<<(mp + 255) / 256, 256, 0, ctx->stream>>>(Gr, mp, mp, lam_raw);
+  NLS_TRY(check_launch(ctx, "jacobi_diag_kernel"));
+  std::vector<double> h_lam(mp);
+  CUDA_TRY(cudaMemcpyAsync(h_lam.data(), lam_raw, (size_t)mp * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  std::vector<int> h_perm(m);
+  for (int k = 0; k < m; ++k) h_perm[k] = k;  // pad columns (index >= m) never rotate and are dropped
+  std::stable_sort(h_perm.begin(), h_perm.end(), [&](int a, int b) { return h_lam[a] < h_lam[b]; });
+  CUDA_TRY(cudaMemcpyAsync(perm, h_perm.data(), (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
+  jacobi_gather_kernel<<<grid_for((long long)m * m), 256, 0, ctx->stream>>>(Vr, Vi, mp, m, perm, lam_raw, Q_out, lam_out);
+  NLS_TRY(check_launch(ctx, "jacobi_gather_kernel"));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // h_perm must outlive the copy
+  return NLS_OK;
+}
+
+extern "C" int nls_heev(nls_ctx* ctx, const double* A, int m, double scale, double* lam_out, double* Q_out) {
+  if (!ctx) return fail(NLS_ERR_INVALID, "ctx is null");
+  // auto: the hand-written Jacobi kernels up to m = 1100 (the default D = 512 and C3's D = 1024); above
+  // that its O(sweeps m^3) work is >10x slower than cuSOLVER's tridiagonal solver, which takes over.
+  const bool jacobi = ctx->eig_kind == 0 || (ctx->eig_kind == 2 && m <= 1100);
+  ctx->eig_sweeps = 0;
+  return jacobi ? heev_jacobi(ctx, A, m, scale, lam_out, Q_out) : heev_cusolver(ctx, A, m, scale, lam_out, Q_out);
+}
+
+extern "C" int nls_ctx_set_eigensolver(nls_ctx* ctx, int kind) {
+  if (!ctx || kind < 0 || kind > 2) return fail(NLS_ERR_INVALID, "eigensolver kind must be 0 (Jacobi), 1 (cuSOLVER) or 2 (auto)");
+  ctx->eig_kind = kind;
+  return NLS_OK;
+}
+
+extern "C" int nls_ctx_last_eig_sweeps(const nls_ctx* ctx) { return ctx ? ctx->eig_sweeps : 0; }
 
 // v = Q^H b inv_c  and (optionally, gamma >= 0) beta_eig = Q (v / (lam + gamma)).
 extern "C" int nls_primal_coeffs(nls_ctx* ctx, const double* Q, const double* lam, const double* b, int m,

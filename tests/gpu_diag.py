@@ -160,6 +160,35 @@ def timing(ctx, n=262144, d=64, D=1024):
     report("timing/kernel_tflops", {k: flops[k] / (prof[k]["ms"] * 1e-3) / 1e12 for k in flops if prof[k]["ms"] > 0})
 
 
+def eig_timing(ctx):
+    """Hand-written block Jacobi vs cuSOLVER Zheevd on Gram matrices of the hot path."""
+    rng = np.random.default_rng(0)
+    for m in (513, 1025, 2049):
+        n = 4 * m
+        Z = rng.standard_normal((n, m - 1)) * 1.5
+        phi = np.concatenate([np.exp(-1j * Z) / np.sqrt(m - 1), np.ones((n, 1))], axis=1) / n
+        A = phi.conj().T @ phi
+        A = (A + A.conj().T) / 2
+        Ad = dev(A)
+        scale = float(n) * m
+        ref = np.linalg.eigvalsh(A * scale)
+        for kind in ("cusolver", "jacobi"):
+            ctx.set_eigensolver(kind)
+            ctx.heev(Ad, scale)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            lam, Q = ctx.heev(Ad, scale)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            Qn = Q.cpu().numpy()
+            report(f"eig/{kind}/m{m}", {
+                "ms": dt * 1e3, "sweeps": ctx.last_eig_sweeps(),
+                "lam_err": float(np.max(np.abs(lam.cpu().numpy() - ref)) / ref[-1]),
+                "resid": float(np.max(np.abs((A * scale) @ Qn - Qn * lam.cpu().numpy()[None, :])) / ref[-1]),
+                "unitary": float(np.max(np.abs(Qn.conj().T @ Qn - np.eye(m))))})
+    ctx.set_eigensolver("jacobi")
+
+
 def main():
     which = sys.argv[1:] or ["peaks", "tma", "plain", "timing"]
     print("device:", torch.cuda.get_device_name(0), flush=True)
@@ -181,6 +210,11 @@ def main():
                 stage_checks(ctx, "tma", name, chunk=chunk)
             except Exception as exc:  # noqa: BLE001
                 report(f"tma/{name}/EXC", repr(exc))
+    if "eig" in which:
+        try:
+            eig_timing(ctx)
+        except Exception as exc:  # noqa: BLE001
+            report("eig/EXC", repr(exc))
     if "timing" in which:
         try:
             timing(ctx)

@@ -211,3 +211,48 @@ def test_error_paths(gpu):
         _lib.check(ctx.lib.nls_feature_map(ctx.handle, None, 4, 2, None, None, 8, None))
     assert b"null" in ctx.lib.nls_last_error()
     del X
+
+
+@pytest.mark.parametrize("kind", ["jacobi", "cusolver"])
+@pytest.mark.parametrize("m", [5, 64, 257, 513])
+def test_heev_matches_lapack(kind, m, gpu):
+    """Stage 3: the hand-written block-Jacobi kernels and the cuSOLVER comparator both reproduce LAPACK's
+    spectrum of a Gram-like Hermitian matrix graded over 14 decades, with a unitary, residual-free basis."""
+    from neo_ls_svm_b200 import _lib
+
+    _, dev, _, torch = gpu
+    ctx = _lib.Context(0)
+    ctx.set_eigensolver(kind)
+    rng = np.random.default_rng(m)
+    U, _ = np.linalg.qr(rng.standard_normal((m, m)) + 1j * rng.standard_normal((m, m)))
+    lam_true = np.logspace(2, -12, m)
+    A = (U * lam_true) @ U.conj().T
+    A = (A + A.conj().T) / 2
+    scale = 3.0
+    lam, Q = ctx.heev(dev(A), scale)
+    lam, Q = lam.cpu().numpy(), Q.cpu().numpy()
+    ref = np.linalg.eigvalsh(A * scale)
+    assert np.all(np.diff(lam) >= 0), "eigenvalues must be ascending like scipy.linalg.eigh"
+    assert np.max(np.abs(lam - ref)) < 1e-13 * ref[-1]
+    assert np.max(np.abs(Q.conj().T @ Q - np.eye(m))) < 1e-12
+    assert np.max(np.abs((A * scale) @ Q - Q * lam[None, :])) < 1e-12 * ref[-1]
+    if kind == "jacobi":
+        assert 1 <= ctx.last_eig_sweeps() <= 40
+
+
+def test_fit_is_eigensolver_independent(golden, gpu):
+    """β̂, the LOO error curve and the selected γ do not depend on which eigensolver produced (λ, Q)."""
+    from neo_ls_svm_b200 import _lib
+
+    _, dev, _primal, _ = gpu
+    g = golden("c1")
+    X, y_, s, Xt, classifier, shift, W = _case("c1", g)
+    out = {}
+    for kind in ("jacobi", "cusolver"):
+        ctx = _lib.Context(0)
+        ctx.set_eigensolver(kind)
+        out[kind] = _primal.primal_fit(dev(X), dev(y_), dev(s), dev(shift), dev(W), classifier, ctx=ctx)
+        assert out[kind].opt == int(g["opt"])
+        assert rel_err(out[kind].beta_eig.cpu().numpy(), g["beta"]) < TOL_FIT
+        assert rel_err(out[kind].loo_errors, g["loo_errors"]) < TOL_FIT
+    assert rel_err(out["jacobi"].lam.cpu().numpy(), out["cusolver"].lam.cpu().numpy()) < 1e-12
