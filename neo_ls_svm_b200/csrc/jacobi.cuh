@@ -172,7 +172,8 @@ __global__ void __launch_bounds__(128) jacobi_pivot_kernel(const double* __restr
   }
 }
 
-// G <- J^H G J and V <- V J for one round, one warp per 8 x 8 tile.
+// G <- J^H G J and V <- V J for one round, one warp per 8 x 8 tile.  G stays Hermitian, so only the tiles
+// (i <= j) of the pair grid are computed; each is also written conjugate-transposed to its mirror (j, i).
 __global__ void __launch_bounds__(256) jacobi_update_kernel(double* __restrict__ Gr, double* __restrict__ Gi,
                                                             double* __restrict__ Vr, double* __restrict__ Vi, int ld,
                                                             int nb, int round, const double* __restrict__ Jbuf,
@@ -181,13 +182,30 @@ __global__ void __launch_bounds__(256) jacobi_update_kernel(double* __restrict__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int np = nb / 2;
   const int rb = nb * JB / 8;  // 8-row blocks of V
-  const long long n_g = (long long)np * np;
+  const long long n_g = (long long)np * (np + 1) / 2;  // upper-triangular tiles (i <= j)
   const long long total = n_g + (long long)rb * np;
   const int fr = lane >> 2, fk = lane & 3;
   for (long long task = (long long)blockIdx.x * 8 + warp; task < total; task += (long long)gridDim.x * 8) {
     const bool is_g = task < n_g;
-    const int i = is_g ? (int)(task / np) : (int)((task - n_g) / np);  // pair index (G) or row block (V)
-    const int j = is_g ? (int)(task % np) : (int)((task - n_g) % np);
+    int i, j;
+    if (is_g) {
+      // Row-major enumeration of the upper triangle: row i holds np - i tiles.
+      const double disc = (2.0 * np + 1.0) * (2.0 * np + 1.0) - 8.0 * (double)task;
+      i = (int)((2.0 * np + 1.0 - sqrt(disc)) * 0.5);
+      long long first = (long long)i * np - (long long)i * (i - 1) / 2;
+      while (first > task) {
+        --i;
+        first = (long long)i * np - (long long)i * (i - 1) / 2;
+      }
+      while (first + (np - i) <= task) {
+        first += np - i;
+        ++i;
+      }
+      j = i + (int)(task - first);
+    } else {
+      i = (int)((task - n_g) / np);  // row block of V
+      j = (int)((task - n_g) % np);
+    }
     const bool fj = flags[j] != 0;
     const bool fi = is_g && flags[i] != 0;
     if (!fi && !fj) continue;  // warp-uniform
@@ -235,9 +253,16 @@ __global__ void __launch_bounds__(256) jacobi_update_kernel(double* __restrict__
         dmma(outi[0], outi[1], -ai, br);
       }
     }
-    const long long o = (long long)row * ld + pair_index(jp, jq, 2 * fk);
+    const int col = pair_index(jp, jq, 2 * fk);
+    const long long o = (long long)row * ld + col;
     *reinterpret_cast<double2*>(Mr + o) = make_double2(outr[0], outr[1]);
     *reinterpret_cast<double2*>(Mi + o) = make_double2(outi[0], outi[1]);
+    if (is_g && i != j) {  // mirror tile: G[c, r] = conj(G[r, c])
+      Mr[(long long)col * ld + row] = outr[0];
+      Mi[(long long)col * ld + row] = -outi[0];
+      Mr[(long long)(col + 1) * ld + row] = outr[1];
+      Mi[(long long)(col + 1) * ld + row] = -outi[1];
+    }
   }
 }
 

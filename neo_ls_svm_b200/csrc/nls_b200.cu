@@ -259,6 +259,10 @@ static int feature_chunk(nls_ctx* ctx, const MapGeom& g, const double* X, const 
   return launch_gemm<MODE_REAL, OpFeatureMap>(ctx, p, grid, rows, g.D, NLS_PROF_FEATURE_MAP, "feature_map");
 }
 
+// Number of leading projection columns computed by 64-wide GEMM tiles.  When only a few columns spill into
+// a last tile (m = D + 1 with D a multiple of 64 leaves exactly one), they go to project_tail_kernel.
+static inline int tail_split(int m) { return (m % BN != 0 && m % BN <= 4 && m > BN) ? m - m % BN : m; }
+
 // Basis planes B^T (2Np x Dp) + constant-feature bias from a numpy-layout m x m complex basis.
 struct BasisScratch {
   double *bt, *bias_r, *bias_i, *v_r, *v_i, *w;
@@ -559,7 +563,7 @@ static int heev_jacobi(nls_ctx* ctx, const double* A, int m, double scale, doubl
   double* thr = fro2 + 2;
   CUDA_TRY(cudaMemcpyAsync(thr, h_thr, 16, cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  const long long tasks = (long long)np * np + (long long)(mp / 8) * np;
+  const long long tasks = (long long)np * (np + 1) / 2 + (long long)(mp / 8) * np;
   const int upd_grid = (int)std::min<long long>((tasks + 7) / 8, (long long)ctx->sm_count * 8);
   if (!ctx->jac_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->jac_stream, cudaStreamNonBlocking));
   if (!ctx->jac_graph || ctx->jac_graph_key != (const void*)Gr || ctx->jac_graph_nb != nb) {
@@ -719,8 +723,17 @@ extern "C" int nls_primal_loo_sweep(nls_ctx* ctx, const double* X, const double*
     pp.P = P;
     pp.U = U;
     pp.ld = g.ldp;
-    NLS_TRY((launch_gemm<MODE_COMPLEX, OpProject>(ctx, pp, dim3((g.m + BN - 1) / BN, mtiles), rows, 2 * g.Np,
+    const int full_cols = tail_split(g.m);  // columns handled by 64-wide tiles; the rest by the GEMV tail
+    pp.m = full_cols;
+    NLS_TRY((launch_gemm<MODE_COMPLEX, OpProject>(ctx, pp, dim3((full_cols + BN - 1) / BN, mtiles), rows, 2 * g.Np,
                                                    NLS_PROF_PROJECT, "project")));
+    if (full_cols < g.m) {
+      ProfScope scope(ctx, NLS_PROF_PROJECT);
+      project_tail_kernel<<<(rows * 32 + 255) / 256, 256, 0, ctx->stream>>>(
+          (const double*)ctx->psi.p, 2LL * g.Dp, g.Dp, rows, D, bs.bt, g.Dp, g.Np, full_cols, g.m, bs.bias_r, bs.bias_i, 0,
+          bs.v_r, bs.v_i, inv_c, P, U, g.ldp, nullptr, nullptr);
+      NLS_TRY(check_launch(ctx, "project_tail_kernel"));
+    }
     OpSweep::Params sp;
     sp.A = Operand{P, g.ldp, (int)(cap + rows), g.m, (int)cap, 0};
     sp.B = Operand{(const double*)ctx->rt.p, g.ldp, G, g.m, 0, 0};
@@ -744,21 +757,30 @@ extern "C" int nls_primal_loo_sweep(nls_ctx* ctx, const double* X, const double*
 // Shared by stage 4c and stage 5: per-row yhat (two coefficient vectors) and sigma2 for a chunk.
 // ---------------------------------------------------------------------------------------------
 static int variance_chunk(nls_ctx* ctx, const MapGeom& g, const BasisScratch& bs, int rows, double* sigma2_out) {
-  const int ntiles = (g.m + BN - 1) / BN;
+  const int full_cols = tail_split(g.m);
+  const int gemm_tiles = (full_cols + BN - 1) / BN;
+  const int ntiles = gemm_tiles + (full_cols < g.m ? 1 : 0);
   const long long cap = ctx->chunk_rows;
   NLS_TRY(ensure(ctx, ctx->part, (size_t)ntiles * cap * 8));
   OpVariance::Params vp;
   vp.A = psi_operand(ctx, g, rows);
   vp.B = basis_operand(g, bs.bt);
   vp.n_rows = rows;
-  vp.m = g.m;
+  vp.m = full_cols;
   vp.bias_r = bs.bias_r;
   vp.bias_i = bs.bias_i;
   vp.w = bs.w;
   vp.part = (double*)ctx->part.p;
   vp.part_ld = cap;
-  NLS_TRY((launch_gemm<MODE_COMPLEX, OpVariance>(ctx, vp, dim3(ntiles, (rows + BM - 1) / BM), rows, 2 * g.Np,
+  NLS_TRY((launch_gemm<MODE_COMPLEX, OpVariance>(ctx, vp, dim3(gemm_tiles, (rows + BM - 1) / BM), rows, 2 * g.Np,
                                                   NLS_PROF_VARIANCE, "variance")));
+  if (full_cols < g.m) {
+    ProfScope scope(ctx, NLS_PROF_VARIANCE);
+    project_tail_kernel<<<(rows * 32 + 255) / 256, 256, 0, ctx->stream>>>(
+        (const double*)ctx->psi.p, 2LL * g.Dp, g.Dp, rows, g.D, bs.bt, g.Dp, g.Np, full_cols, g.m, bs.bias_r, bs.bias_i, 1,
+        nullptr, nullptr, 0.0, nullptr, nullptr, 0, bs.w, (double*)ctx->part.p + (size_t)gemm_tiles * cap);
+    NLS_TRY(check_launch(ctx, "project_tail_kernel"));
+  }
   rowsum_reduce_kernel<<<(rows + 255) / 256, 256, 0, ctx->stream>>>((const double*)ctx->part.p, ntiles, cap, rows,
                                                                    sigma2_out);
   return check_launch(ctx, "rowsum_reduce_kernel");

@@ -234,6 +234,51 @@ __global__ void gemv_pair_kernel(const double* __restrict__ psi, long long ld, i
   }
 }
 
+// Tail columns of the projection T = phi B that do not fill a 64-wide GEMM tile (m = D + 1 leaves exactly
+// one such column for every power-of-two D): one warp per row, GEMV against the K-contiguous basis rows
+// bt[k, :] (Re) and bt[Np + k, :] (Im).  Cheaper than a 17th tile that would be 63/64 padding.
+//   mode 0: P[row, k] = Re(T v_k), U[row, k] = |T|^2 inv_c      (stage 4a)
+//   mode 1: part[row] = sum_k |T|^2 w_k                          (stage 4c / 5b), written as one extra partial
+__global__ void project_tail_kernel(const double* __restrict__ psi, long long ld, int plane_stride, int rows, int D,
+                                    const double* __restrict__ bt, long long ldk, int Np, int k0, int k1,
+                                    const double* __restrict__ bias_r, const double* __restrict__ bias_i, int mode,
+                                    const double* __restrict__ v_r, const double* __restrict__ v_i, double inv_c,
+                                    double* __restrict__ P, double* __restrict__ U, long long ldp,
+                                    const double* __restrict__ w, double* __restrict__ part) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const double* c = psi + (long long)warp * ld;
+  const double* s = c + plane_stride;
+  double acc = 0.0;
+  for (int k = k0; k < k1; ++k) {
+    const double* qr = bt + (long long)k * ldk;
+    const double* qi = bt + (long long)(Np + k) * ldk;
+    double tr = 0.0, ti = 0.0;
+    for (int l = lane; l < D; l += 32) {
+      const double cv = c[l], sv = s[l], a = qr[l], b = qi[l];
+      tr += cv * a + sv * b;  // Re((c - i s)(a + i b))
+      ti += cv * b - sv * a;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      tr += __shfl_xor_sync(0xffffffffu, tr, off);
+      ti += __shfl_xor_sync(0xffffffffu, ti, off);
+    }
+    tr += bias_r[k];
+    ti += bias_i[k];
+    if (mode == 0) {
+      if (lane == 0) {
+        P[(long long)warp * ldp + k] = tr * v_r[k] - ti * v_i[k];
+        U[(long long)warp * ldp + k] = (tr * tr + ti * ti) * inv_c;
+      }
+    } else {
+      acc += (tr * tr + ti * ti) * w[k];
+    }
+  }
+  if (mode == 1 && lane == 0) part[warp] = acc;
+}
+
 // Per-row outputs at the selected gamma.  _neo_ls_svm.py:149-155, :167-169, :179-187.
 __global__ void finalize_rows_kernel(int rows, const double* __restrict__ y, const double* __restrict__ s,
                                      const double* __restrict__ sigma2, const double* __restrict__ num,
