@@ -110,14 +110,29 @@ class AffineFeatureMap(BaseEstimator, TransformerMixin):
         return {"preserves_dtype": [np.float64, np.float32]}
 
 
-def _split_by_target_bin(X, y, sample_weight):
-    """Group rows by the quantised target: (masks, X per bin, total weight per bin, normalised row weights)."""
+def _target_bins(y, sample_weight):
+    """Group rows by the quantised target.
+
+    Returns (rows per bin, total weight per bin, normalised row weights per bin as 1×n_b arrays).  Only
+    index and weight vectors are built here; feature rows are gathered per bin when needed, so no second
+    copy of X is ever alive.
+    """
     codes = sample_bins_quantized_ecdf(y)
-    masks = [codes == c for c in range(np.min(codes), np.max(codes) + 1)]
-    X_bins = [X[mk, :] for mk in masks]
-    mass = [np.sum(sample_weight[mk]) for mk in masks]
-    s_bins = [sample_weight[np.newaxis, mk] / np.sum(sample_weight[mk]) for mk in masks]
-    return masks, X_bins, mass, s_bins
+    rows = [np.flatnonzero(codes == c) for c in range(np.min(codes), np.max(codes) + 1)]
+    mass = [np.sum(sample_weight[r]) for r in rows]
+    s_bins = [sample_weight[np.newaxis, r] / np.sum(sample_weight[r]) for r in rows]
+    return rows, mass, s_bins
+
+
+def _bin_location_spread(X, rows, s_bins):
+    """Per-bin weighted median and weighted mean absolute deviation of every feature (host NumPy)."""
+    centre, spread = [], []
+    for r, sb in zip(rows, s_bins):
+        Xb = X[r, :]
+        mu = weighted_quantile(Xb, sb.T, 0.5, axis=0)
+        centre.append(mu)
+        spread.append(sb @ np.abs(Xb - mu))
+    return centre, spread
 
 
 class AffineNormalizer(AffineFeatureMap):
@@ -129,21 +144,20 @@ class AffineNormalizer(AffineFeatureMap):
         self.A = None
         self.append_features = append_features
 
-    def fit(self, X, y=None, sample_weight=None):
+    def fit(self, X, y=None, sample_weight=None, _bins=None):
         X, y = check_X_y(X, y, dtype=(np.float64, np.float32))
         y = np.ravel(np.asarray(y)).astype(X.dtype)
         sw = (np.ones(y.shape) if sample_weight is None else np.ravel(np.asarray(sample_weight))).astype(y.dtype)
         check_consistent_length(y, sw)
-        _, X_bins, mass, s_bins = _split_by_target_bin(X, y, sw)
+        rows, mass, s_bins = _bins if _bins is not None else _target_bins(y, sw)
         d = X.shape[1]
-        if len(X_bins) <= 1:
+        if len(rows) <= 1:
             self.shift_ = np.zeros((1, d), dtype=X.dtype)
             self.scale_ = np.ones((1, d), dtype=X.dtype)
             AffineFeatureMap.fit(self, X, y, sw)
             return self
         # Per-bin robust location (weighted median) and spread (weighted mean absolute deviation).
-        centre = [weighted_quantile(Xb, sb.T, 0.5, axis=0) for Xb, sb in zip(X_bins, s_bins)]
-        spread = [sb @ np.abs(Xb - mu) for Xb, sb, mu in zip(X_bins, s_bins, centre)]
+        centre, spread = _bin_location_spread(X, rows, s_bins)
         eps = np.finfo(X.dtype).eps
         direction = np.zeros((1, d), dtype=X.dtype)
         weight_sum = np.zeros((1, d), dtype=X.dtype)
@@ -216,29 +230,43 @@ class AffineSeparator(AffineNormalizer):
         assert y is not None
         X, y = check_X_y(X, y, dtype=(np.float64, np.float32))
         y = np.ravel(np.asarray(y)).astype(X.dtype)
-        AffineNormalizer.fit(self, X, y, sample_weight)
-        X = AffineNormalizer.transform(self, X)  # A is still None here: shift and scale only
         sw = (np.ones(y.shape) if sample_weight is None else np.ravel(np.asarray(sample_weight))).astype(y.dtype)
         check_consistent_length(y, sw)
-        masks, X_bins, mass, s_bins = _split_by_target_bin(X, y, sw)
-        n_bins = len(X_bins)
+        bins = _target_bins(y, sw)  # the reference quantises y twice (normaliser and separator); once is enough
+        AffineNormalizer.fit(self, X, y, sample_weight, _bins=bins)
+        rows, mass, s_bins = bins
+        n_bins = len(rows)
         if n_bins <= 1:
             return self
         if n_bins == 2:  # the reference enlarges (and keeps) the sample size for two bins (:139-141)
             self.edge_sample_size = int(self.edge_sample_size * 4 / 3)
         E, wide = self.edge_sample_size, self.edge_sample_size * self.edge_search_multiplier
         rng = check_random_state(self.random_state)
+        shift = np.reshape(self.shift_, (1, -1))
+        scale = np.reshape(self.scale_, (1, -1))
+
+        def normalised(idx):
+            # Rows of the shifted/scaled matrix (:121) without materialising it: the separator only ever
+            # looks at a few thousand sampled rows.
+            return ((X[idx, :] - shift) / scale).astype(X.dtype)
+
+        sizes = np.array([len(r) for r in rows])
         directions, inside_edges, outside_edges = [], [], []
         for i in range(n_bins):
-            own = X_bins[i]
+            own_rows = rows[i]
             p_own = np.ravel(s_bins[i])
-            seeds = own[rng.choice(len(own), size=E, p=p_own), :]
-            rest = np.vstack([Xb for j, Xb in enumerate(X_bins) if j != i])
-            w_rest = np.hstack([sw[mk] for j, mk in enumerate(masks) if j != i])
-            rest_sample = rest[rng.choice(len(rest), size=wide, p=np.ravel(w_rest) / np.sum(w_rest)), :]
+            seeds = normalised(own_rows[rng.choice(len(own_rows), size=E, p=p_own)])
+            # Sample the complement of bin i ("vstack of the other bins", :150-156) through row indices.
+            others = [j for j in range(n_bins) if j != i]
+            w_rest = np.hstack([sw[rows[j]] for j in others])
+            pick = rng.choice(len(w_rest), size=wide, p=np.ravel(w_rest) / np.sum(w_rest))
+            offsets = np.concatenate([[0], np.cumsum(sizes[others])])
+            which = np.searchsorted(offsets, pick, side="right") - 1
+            rest_rows = np.array([rows[others[b]][k - offsets[b]] for b, k in zip(which, pick)])
+            rest_sample = normalised(rest_rows)
             # Points of the complement closest to bin i, then points of bin i closest to those.
             outside = nearest_neighbours(seeds, rest_sample)
-            own_sample = own[rng.choice(len(own), size=wide, p=p_own), :]
+            own_sample = normalised(own_rows[rng.choice(len(own_rows), size=wide, p=p_own)])
             inside = nearest_neighbours(outside, own_sample)
             outside_edges.append(outside)
             inside_edges.append(inside)

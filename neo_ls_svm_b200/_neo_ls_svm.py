@@ -408,7 +408,9 @@ class NeoLSSVM(BaseEstimator):
     def __sklearn_tags__(self):
         tags = super().__sklearn_tags__()
         tags.target_tags.required = True
-        est = getattr(self, "_estimator_type", None) or (self.estimator_type if self.estimator_type != "auto" else None)
+        # Like the reference, the task type is only known once `fit` has seen the target (`_estimator_type`
+        # is set there, :361-363); an unfitted instance is a generic estimator for sklearn's checks.
+        est = self.__dict__.get("_estimator_type")
         if est in ("classifier", "regressor"):
             tags.estimator_type = est
         if est == "classifier":
