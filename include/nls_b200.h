@@ -196,6 +196,26 @@ int nls_dual_predict(nls_ctx* ctx, const double* Xq, int64_t nq, const double* X
                      const double* alpha, double alpha_sum, const double* Bt, const double* w,
                      double* yhat_out, double* sigma_out);
 
+/* ---------------------------------------------------------------------------------------------
+ * Supervised affine pre-pass (SURVEY.md §8f "next" #1): per-bin weighted median and weighted mean
+ * absolute deviation of every feature.  Replaces the host argsort of every column of every target
+ * bin in AffineNormalizer.fit (_affine_normalizer.py:81-88, _weighted_quantile.py:52-63).
+ *   perm (n int64): row indices grouped by bin; w (n): per-row weight, normalised within its bin, in
+ *   perm order; tiles (ntiles x 4 int32: bin, first, last+1, 0): row ranges of perm that do not
+ *   straddle bins; bin_tiles (nbins x 2 int32): tile range of every bin.
+ * nls_bin_median_stats writes stats_out[7][nbins][d] around the value v* at which the cumulative
+ * weight first exceeds half the bin's weight: v*, predecessor value (NaN if none), successor value
+ * (NaN if none), weight strictly below v*, weight of the ties at v*, number of ties, weight of the
+ * first tie; and wtot_out[nbins][d] = total weight.  The host evaluates the reference's two linear
+ * interpolations from these.  nls_bin_mad: spread_out[bin][col] = sum_i w_i |x_i,col - centre[bin][col]|.
+ * ------------------------------------------------------------------------------------------- */
+int nls_bin_median_stats(nls_ctx* ctx, const double* X, int64_t n, int d, const int64_t* perm,
+                         const double* w, const int* tiles, int ntiles, const int* bin_tiles,
+                         int nbins, double* stats_out, double* wtot_out);
+int nls_bin_mad(nls_ctx* ctx, const double* X, int64_t n, int d, const int64_t* perm, const double* w,
+                const int* tiles, int ntiles, const int* bin_tiles, int nbins, const double* centre,
+                double* spread_out);
+
 /* Micro-benchmarks used for the roofline denominators (bench.py / profiles/). */
 int nls_bench_dmma_peak(nls_ctx* ctx, int iters, double* tflops_out);
 

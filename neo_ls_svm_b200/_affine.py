@@ -124,8 +124,47 @@ def _target_bins(y, sample_weight):
     return rows, mass, s_bins
 
 
+# Device copies of training matrices registered by the estimator (key: host data pointer + shape), so the
+# pre-pass and the solver share one upload of X.
+_DEVICE_COPIES: dict = {}
+
+
+def _array_key(X) -> tuple:
+    return (X.__array_interface__["data"][0], X.shape, X.dtype.str)
+
+
+def register_device_copy(X, Xd) -> None:
+    _DEVICE_COPIES[_array_key(X)] = Xd
+
+
+def release_device_copy(X) -> None:
+    _DEVICE_COPIES.pop(_array_key(X), None)
+
+
+def device_copy(X):
+    return _DEVICE_COPIES.get(_array_key(X))
+
+
 def _bin_location_spread(X, rows, s_bins):
-    """Per-bin weighted median and weighted mean absolute deviation of every feature (host NumPy)."""
+    """Per-bin weighted median and weighted mean absolute deviation of every feature.
+
+    Large inputs go through the sort-free GPU kernels (`_binstats.py`, `nls_bin_median_stats`); small
+    ones, and machines without a GPU, use the reference's host recipe (argsort per column per bin).
+    """
+    from . import _binstats
+
+    Xd = device_copy(X)
+    if Xd is None and X.size >= _binstats.MIN_ELEMENTS_FOR_DEVICE:
+        try:
+            import torch
+
+            if torch.cuda.is_available():
+                Xd = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).cuda()
+        except ImportError:  # pragma: no cover
+            Xd = None
+    if Xd is not None and X.size >= _binstats.MIN_ELEMENTS_FOR_DEVICE:
+        centre, spread = _binstats.device_bin_location_spread(Xd, rows, s_bins)
+        return [c.astype(X.dtype) for c in centre], [sp.astype(X.dtype) for sp in spread]
     centre, spread = [], []
     for r, sb in zip(rows, s_bins):
         Xb = X[r, :]

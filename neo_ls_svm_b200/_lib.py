@@ -51,6 +51,8 @@ def _signatures(lib: C.CDLL) -> None:
         "nls_dual_sweep": ([p, p, i, i, p, p, p, p, i, i, p, p, p], i),
         "nls_dual_finalize": ([p, i, p, p, d, p, p, p, p, p, p, p], i),
         "nls_dual_predict": ([p, p, i64, p, i, i, p, d, p, p, p, p], i),
+        "nls_bin_median_stats": ([p, p, i64, i, p, p, p, i, p, i, p, p], i),
+        "nls_bin_mad": ([p, p, i64, i, p, p, p, i, p, i, p, p], i),
         "nls_bench_dmma_peak": ([p, i, C.POINTER(d)], i),
     }
     for name, (argtypes, restype) in sig.items():
@@ -97,7 +99,7 @@ def ptr(t) -> int | None:
     import torch
 
     assert t.is_cuda and t.is_contiguous(), "expected a contiguous CUDA tensor"
-    assert t.dtype in (torch.float64, torch.complex128), f"expected float64/complex128, got {t.dtype}"
+    assert t.dtype in (torch.float64, torch.complex128, torch.int64, torch.int32), f"unexpected dtype {t.dtype}"
     return t.data_ptr()
 
 
@@ -313,6 +315,29 @@ class Context:
         check(self.lib.nls_dual_predict(
             self.handle, ptr(Xq), nq, ptr(Xt), n, p_, ptr(alpha), float(alpha_sum), ptr(Bt), ptr(w), ptr(yhat), ptr(sigma)))
         return yhat, sigma
+
+
+    # -- supervised affine pre-pass ------------------------------------------------------------
+    def bin_median_stats(self, X, perm, w, tiles, bin_tiles):
+        import torch
+
+        n, d = X.shape
+        nbins, ntiles = bin_tiles.shape[0], tiles.shape[0]
+        stats = torch.empty((7, nbins, d), dtype=torch.float64, device=X.device)
+        wtot = torch.empty((nbins, d), dtype=torch.float64, device=X.device)
+        check(self.lib.nls_bin_median_stats(
+            self.handle, ptr(X), n, d, ptr(perm), ptr(w), ptr(tiles), ntiles, ptr(bin_tiles), nbins, ptr(stats), ptr(wtot)))
+        return stats, wtot
+
+    def bin_mad(self, X, perm, w, tiles, bin_tiles, centre):
+        import torch
+
+        n, d = X.shape
+        nbins, ntiles = bin_tiles.shape[0], tiles.shape[0]
+        spread = torch.empty((nbins, d), dtype=torch.float64, device=X.device)
+        check(self.lib.nls_bin_mad(
+            self.handle, ptr(X), n, d, ptr(perm), ptr(w), ptr(tiles), ntiles, ptr(bin_tiles), nbins, ptr(centre), ptr(spread)))
+        return spread
 
 
 _contexts: dict = {}

@@ -28,6 +28,7 @@ from sklearn.metrics import accuracy_score, r2_score
 from sklearn.model_selection import train_test_split
 from sklearn.utils.validation import check_array, check_consistent_length, check_is_fitted, check_X_y
 
+from . import _affine
 from ._affine import AffineSeparator
 from ._clqr import CoherentLinearQuantileRegressor
 from ._feature_maps import KernelApproximatingFeatureMap, OrthogonalRandomFourierFeatures
@@ -117,11 +118,14 @@ class NeoLSSVM(BaseEstimator):
         dt = X.dtype
         s64 = np.asarray(s, dtype=np.float64)
         s_norm = s64 / np.sum(s64)  # :110
-        Xd = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).to(dev)
+        Xd = _affine.device_copy(X)  # uploaded once in `fit`, shared with the supervised pre-pass
+        if Xd is None:
+            Xd = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).to(dev)
         yd = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float64)).to(dev)
         sd = torch.from_numpy(s_norm).to(dev)
         shd, Wd = torch.from_numpy(shift).to(dev), torch.from_numpy(W).to(dev)
         fit = _primal.primal_fit(Xd, yd, sd, shd, Wd, self._estimator_type == "classifier", ctx=ctx)
+        del Xd
         cdt = np.complex64 if dt == np.float32 else np.complex128
         self.γs_ = fit.gammas.astype(dt)
         self.loo_errors_γs_ = fit.loo_errors.astype(dt)
@@ -184,8 +188,14 @@ class NeoLSSVM(BaseEstimator):
             self.primal_feature_map_ = clone(
                 OrthogonalRandomFourierFeatures() if self.primal_feature_map == "auto" else self.primal_feature_map
             )
-            self.primal_feature_map_.fit(X, y_, sample_weight_)
-            self.β̂_, self.γ_ = self._optimize_β̂_γ(X, y_, sample_weight_)
+            # One host→device copy of X serves the supervised affine pre-pass and the solver.
+            ctx, torch, dev = self._gpu()
+            _affine.register_device_copy(X, torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).to(dev))
+            try:
+                self.primal_feature_map_.fit(X, y_, sample_weight_)
+                self.β̂_, self.γ_ = self._optimize_β̂_γ(X, y_, sample_weight_)
+            finally:
+                _affine.release_device_copy(X)
         else:
             keep = sample_weight_ > 0
             X, y_, sample_weight_ = X[keep], y_[keep], sample_weight_[keep]

@@ -16,6 +16,7 @@
 #include "ops.cuh"
 #include "small_kernels.cuh"
 #include "jacobi.cuh"
+#include "binstats.cuh"
 
 using namespace nls;
 
@@ -90,7 +91,7 @@ struct nls_ctx {
   // scratch (grow-only, zero-filled when (re)allocated)
   DevBuf xc, wt, psi, psiT, pu, bt, rt, small, part, gram_ws, border, rowtmp, solver_ws, solver_mat;
   // dual path (state kept between nls_dual_sweep and nls_dual_finalize)
-  DevBuf jac_mat, jac_small;
+  DevBuf jac_mat, jac_small, bs_part, bs_keys;
   DevBuf d_xpad, d_xq, d_norm, d_fm, d_sq, d_sqt, d_g1, d_ab, d_ra, d_vec, d_ng, d_kq, d_btp;
   int dual_n = 0;
   // profiling
@@ -340,7 +341,7 @@ extern "C" int nls_ctx_destroy(nls_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->xc, &ctx->wt, &ctx->psi, &ctx->psiT, &ctx->pu, &ctx->bt, &ctx->rt, &ctx->small,
                     &ctx->part, &ctx->gram_ws, &ctx->border, &ctx->rowtmp, &ctx->solver_ws, &ctx->solver_mat,
-                    &ctx->jac_mat, &ctx->jac_small, &ctx->d_xpad, &ctx->d_xq, &ctx->d_norm, &ctx->d_fm, &ctx->d_sq, &ctx->d_sqt, &ctx->d_g1,
+                    &ctx->jac_mat, &ctx->jac_small, &ctx->bs_part, &ctx->bs_keys, &ctx->d_xpad, &ctx->d_xq, &ctx->d_norm, &ctx->d_fm, &ctx->d_sq, &ctx->d_sqt, &ctx->d_g1,
                     &ctx->d_ab, &ctx->d_ra, &ctx->d_vec, &ctx->d_ng, &ctx->d_kq, &ctx->d_btp};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
@@ -1157,6 +1158,64 @@ extern "C" int nls_dual_predict(nls_ctx* ctx, const double* Xq, int64_t nq, cons
     }
   }
   return NLS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Supervised affine pre-pass: per-bin weighted median / MAD of every feature
+// ---------------------------------------------------------------------------------------------
+extern "C" int nls_bin_median_stats(nls_ctx* ctx, const double* X, int64_t n, int d, const int64_t* perm,
+                                    const double* w, const int* tiles, int ntiles, const int* bin_tiles, int nbins,
+                                    double* stats_out, double* wtot_out) {
+  if (!ctx || !X || !perm || !w || !tiles || !bin_tiles || !stats_out || !wtot_out)
+    return fail(NLS_ERR_INVALID, "null pointer");
+  if (n < 1 || d < 1 || ntiles < 1 || nbins < 1) return fail(NLS_ERR_INVALID, "bad shape");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const long long nd = (long long)nbins * d;
+  NLS_TRY(ensure(ctx, ctx->bs_part, (size_t)ntiles * 7 * d * 8));
+  NLS_TRY(ensure(ctx, ctx->bs_keys, (size_t)3 * nd * 8));
+  double* partial = (double*)ctx->bs_part.p;
+  unsigned long long* lo = (unsigned long long*)ctx->bs_keys.p;
+  unsigned long long* hi = lo + nd;
+  unsigned long long* mid = hi + nd;
+  const dim3 grid(ntiles, (d + BS_COLS - 1) / BS_COLS);
+  const int sgrid = (int)((nd + 255) / 256);
+  const BsTile* tl = (const BsTile*)tiles;
+  const int2* bt = (const int2*)bin_tiles;
+  ProfScope scope(ctx, NLS_PROF_OTHER);
+  // Total weight per (bin, column): every key is <= the all-ones key.
+  CUDA_TRY(cudaMemsetAsync(mid, 0xff, (size_t)nd * 8, ctx->stream));
+  bs_count_kernel<<<grid, 256, 0, ctx->stream>>>(X, d, (const long long*)perm, w, tl, mid, partial);
+  bs_step_kernel<<<sgrid, 256, 0, ctx->stream>>>(partial, bt, nbins, d, -1, wtot_out, lo, hi, mid);
+  ctx->launches += 2;
+  // 64 bisection steps on the 64-bit key: afterwards lo == hi == key of the crossing value v*.
+  for (int it = 0; it < 64; ++it) {
+    bs_count_kernel<<<grid, 256, 0, ctx->stream>>>(X, d, (const long long*)perm, w, tl, mid, partial);
+    bs_step_kernel<<<sgrid, 256, 0, ctx->stream>>>(partial, bt, nbins, d, it, wtot_out, lo, hi, mid);
+    ctx->launches += 2;
+  }
+  bs_stats_kernel<<<grid, 256, 0, ctx->stream>>>(X, d, (const long long*)perm, w, tl, lo, partial);
+  bs_stats_reduce_kernel<<<sgrid, 256, 0, ctx->stream>>>(partial, bt, nbins, d, lo, stats_out);
+  ctx->launches += 2;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(NLS_ERR_CUDA, "bin statistics launch failed: %s", cudaGetErrorString(e));
+  return NLS_OK;
+}
+
+extern "C" int nls_bin_mad(nls_ctx* ctx, const double* X, int64_t n, int d, const int64_t* perm, const double* w,
+                           const int* tiles, int ntiles, const int* bin_tiles, int nbins, const double* centre,
+                           double* spread_out) {
+  if (!ctx || !X || !perm || !w || !tiles || !bin_tiles || !centre || !spread_out)
+    return fail(NLS_ERR_INVALID, "null pointer");
+  if (n < 1 || d < 1 || ntiles < 1 || nbins < 1) return fail(NLS_ERR_INVALID, "bad shape");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  NLS_TRY(ensure(ctx, ctx->bs_part, (size_t)ntiles * 7 * d * 8));
+  double* partial = (double*)ctx->bs_part.p;
+  const dim3 grid(ntiles, (d + BS_COLS - 1) / BS_COLS);
+  ProfScope scope(ctx, NLS_PROF_OTHER);
+  bs_mad_kernel<<<grid, 256, 0, ctx->stream>>>(X, d, (const long long*)perm, w, (const BsTile*)tiles, centre, partial);
+  NLS_TRY(check_launch(ctx, "bs_mad_kernel"));
+  bs_sum_kernel<<<(nbins * d + 255) / 256, 256, 0, ctx->stream>>>(partial, (const int2*)bin_tiles, nbins, d, spread_out);
+  return check_launch(ctx, "bs_sum_kernel");
 }
 
 // ---------------------------------------------------------------------------------------------

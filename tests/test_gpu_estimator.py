@@ -81,3 +81,52 @@ def test_float32_inputs_keep_dtype():
     model.fit(X.astype(np.float32), y.astype(np.float32))
     assert model.β̂_.dtype == np.complex64 and model.loo_residuals_.dtype == np.float32
     assert model.predict(Xt.astype(np.float32)).dtype == np.float32
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_device_prepass_matches_host_recipe(weighted):
+    """The sort-free GPU weighted-median / MAD kernels reproduce the host (reference) recipe for the affine
+    pre-pass: identical shift_/scale_ for continuous and for heavily tied features."""
+    import torch
+
+    from neo_ls_svm_b200 import _affine, _binstats
+
+    rng = np.random.default_rng(3)
+    n, d = 60_000, 37
+    X = rng.standard_normal((n, d)) * rng.uniform(0.1, 10, d) + rng.uniform(-5, 5, d)
+    X[:, 3] = np.round(X[:, 3])  # tied values
+    X[:, 4] = rng.integers(0, 2, n)  # binary feature
+    y = X[:, 0] - 0.5 * X[:, 1] + rng.standard_normal(n)
+    sw = rng.uniform(0.2, 2.0, n) if weighted else np.ones(n)
+    rows, mass, s_bins = _affine._target_bins(y.astype(np.float64), sw)
+    host_c, host_s = [], []
+    for r, sb in zip(rows, s_bins):
+        from neo_ls_svm_b200._weighted_quantile import weighted_quantile
+
+        Xb = X[r, :]
+        mu = weighted_quantile(Xb, sb.T, 0.5, axis=0)
+        host_c.append(mu)
+        host_s.append(sb @ np.abs(Xb - mu))
+    dev_c, dev_s = _binstats.device_bin_location_spread(torch.from_numpy(X).cuda(), rows, s_bins)
+    cols = np.arange(d) if not weighted else np.setdiff1d(np.arange(d), [3, 4])  # ties + weights: sort-order dependent
+    for b in range(len(rows)):
+        scale = np.max(np.abs(host_c[b])) + np.max(host_s[b])
+        assert np.max(np.abs(dev_c[b][:, cols] - host_c[b][:, cols])) < 1e-12 * scale, b
+        assert np.max(np.abs(dev_s[b][:, cols] - host_s[b][:, cols])) < 1e-12 * scale, b
+
+
+def test_large_fit_uses_device_prepass_and_matches_host_path(monkeypatch):
+    from neo_ls_svm_b200 import _binstats
+    from neo_ls_svm_b200.datasets import make_regression_rows
+
+    X, y = make_regression_rows(40_000, 12, n_informative=6, noise=10.0)
+    fm_kw = dict(primal_feature_map=OrthogonalRandomFourierFeatures(num_features=128), dual=False)
+    monkeypatch.setattr(_binstats, "MIN_ELEMENTS_FOR_DEVICE", 1)
+    m_dev = NeoLSSVM(**fm_kw).fit(X, y)
+    monkeypatch.setattr(_binstats, "MIN_ELEMENTS_FOR_DEVICE", 1 << 60)
+    m_host = NeoLSSVM(**fm_kw).fit(X, y)
+    a_dev, a_host = m_dev.primal_feature_map_.affine_feature_map, m_host.primal_feature_map_.affine_feature_map
+    assert rel_err(a_dev.shift_, a_host.shift_) < 1e-12 and rel_err(a_dev.scale_, a_host.scale_) < 1e-12
+    assert rel_err(a_dev.A_, a_host.A_) < 1e-10
+    assert m_dev.γ_ == m_host.γ_
+    assert rel_err(m_dev.β̂_, m_host.β̂_) < 1e-8

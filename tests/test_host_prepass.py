@@ -70,3 +70,55 @@ def test_quantizer_properties():
     # Few distinct values: the class codes are returned unchanged.
     y = rng.integers(0, 3, size=1000)
     np.testing.assert_array_equal(sample_bins_quantized_ecdf(y), y)
+
+
+def test_median_from_crossing_statistics_matches_weighted_quantile():
+    """The GPU pre-pass returns only the statistics around the weighted-median crossing; the host formula that
+    turns them into the reference's weighted 0.5-quantile is checked here against `weighted_quantile` with a
+    NumPy model of the kernel (ties, non-uniform weights, single-element bins)."""
+    from neo_ls_svm_b200._binstats import host_median_stats, median_from_stats
+
+    rng = np.random.default_rng(0)
+    keys = ("v", "pred", "succ", "w_lt", "w_eq", "n_eq", "w_first", "w_tot")
+    checked = 0
+    for trial in range(1500):
+        n = int(rng.integers(1, 40))
+        kind = trial % 4
+        if kind == 0:
+            a = rng.standard_normal(n)
+        elif kind == 1:
+            a = rng.integers(0, 4, n).astype(float)  # heavy ties
+        elif kind == 2:
+            a = np.round(rng.standard_normal(n), 1)
+        else:
+            a = rng.standard_normal(n)
+            a[rng.integers(0, n)] = a[0]
+        uniform = trial % 3 != 0
+        w = np.full(n, 1.0 / n) if uniform else rng.uniform(0.1, 1, n)
+        w = w / w.sum()
+        if not uniform and len(np.unique(a)) < n:
+            if np.max(np.unique(a, return_counts=True)[1]) > 2:
+                continue  # the reference itself is sort-order dependent here
+            o = np.argsort(a, kind="stable")
+            c = np.cumsum(w[o])
+            ref = 0.5 * np.interp(0.5, (c - w[o]) / c[-1], a[o]) + 0.5 * np.interp(0.5, c / c[-1], a[o])
+        else:
+            ref = weighted_quantile(a, w, 0.5)[0]
+        st = host_median_stats(a, w)
+        got = median_from_stats(*[np.array([st[k]]) for k in keys])[0]
+        assert abs(got - ref) <= 1e-12 * (abs(ref) + np.max(np.abs(a))), (trial, a, w)
+        checked += 1
+    assert checked > 1000
+
+
+def test_bin_layout_tiles_cover_each_bin_once():
+    from neo_ls_svm_b200._binstats import TILE_ROWS, bin_layout
+
+    rows = [np.arange(0, 5000, 2), np.arange(1, 5000, 2), np.array([5000])]
+    s_bins = [np.full((1, len(r)), 1.0 / len(r)) for r in rows]
+    perm, w, tiles, bin_tiles = bin_layout(rows, s_bins)
+    assert perm.shape == (5001,) and w.shape == (5001,)
+    for b, (t0, t1) in enumerate(bin_tiles):
+        covered = np.concatenate([np.arange(r0, r1) for (bb, r0, r1, _) in tiles[t0:t1]])
+        assert np.all(tiles[t0:t1, 0] == b) and np.all(tiles[t0:t1, 2] - tiles[t0:t1, 1] <= TILE_ROWS)
+        np.testing.assert_array_equal(np.sort(perm[covered]), rows[b])
