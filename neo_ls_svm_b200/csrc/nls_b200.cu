@@ -1225,7 +1225,10 @@ extern "C" int nls_bench_dmma_peak(nls_ctx* ctx, int iters, double* tflops_out) 
   if (!ctx || !tflops_out || iters < 1) return fail(NLS_ERR_INVALID, "bad argument");
   CUDA_TRY(cudaSetDevice(ctx->device));
   NLS_TRY(ensure(ctx, ctx->small, 4096));
-  const int blocks = ctx->sm_count * 4, threads = 256;
+  // Two resident CTAs of 8 warps per SM (4 warps per scheduler, 16 independent accumulator tiles each): one
+  // full wave, no tail.
+  const char* bps = getenv("NLS_PEAK_BLOCKS_PER_SM");
+  const int blocks = ctx->sm_count * (bps && atoi(bps) > 0 ? atoi(bps) : 2), threads = 256;
   cudaEvent_t a, b;
   CUDA_TRY(cudaEventCreate(&a));
   CUDA_TRY(cudaEventCreate(&b));

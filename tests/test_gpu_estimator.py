@@ -126,7 +126,10 @@ def test_large_fit_uses_device_prepass_and_matches_host_path(monkeypatch):
     monkeypatch.setattr(_binstats, "MIN_ELEMENTS_FOR_DEVICE", 1 << 60)
     m_host = NeoLSSVM(**fm_kw).fit(X, y)
     a_dev, a_host = m_dev.primal_feature_map_.affine_feature_map, m_host.primal_feature_map_.affine_feature_map
-    assert rel_err(a_dev.shift_, a_host.shift_) < 1e-12 and rel_err(a_dev.scale_, a_host.scale_) < 1e-12
-    assert rel_err(a_dev.A_, a_host.A_) < 1e-10
+    # The two paths sum the same weights in different orders; the interpolated medians, and everything
+    # downstream of them, agree to accumulated rounding.
+    assert rel_err(a_dev.shift_, a_host.shift_) < 1e-10 and rel_err(a_dev.scale_, a_host.scale_) < 1e-10
+    assert rel_err(a_dev.A_, a_host.A_) < 1e-8
     assert m_dev.γ_ == m_host.γ_
-    assert rel_err(m_dev.β̂_, m_host.β̂_) < 1e-8
+    assert rel_err(m_dev.β̂_, m_host.β̂_) < 1e-6
+    assert rel_err(m_dev.loo_residuals_, m_host.loo_residuals_) < 1e-6
