@@ -77,34 +77,26 @@ __global__ void sumsq_kernel(const double* __restrict__ a, const double* __restr
   }
 }
 
-// One warp per pivot pair: J_i = eigenvectors of G[I_i, I_i] by cyclic two-sided Jacobi.
-// Jbuf: [pair][2][8][8] (Re, Im), flags[pair] = 1 if any rotation was applied, *active += #rotating pairs.
-__global__ void __launch_bounds__(128) jacobi_pivot_kernel(const double* __restrict__ Gr, const double* __restrict__ Gi,
-                                                           int ld, int nb, int round,
-                                                           const double* __restrict__ thr /* [abs^2, rel^2] */,
-                                                           int max_inner, double* __restrict__ Jbuf, int* __restrict__ flags,
-                                                           int* __restrict__ active) {
-  __shared__ double sm[4][4][8][9];  // per warp: Sr, Si, Jr, Ji
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pair = blockIdx.x * 4 + warp;
-  if (pair >= nb / 2) return;
-  double(*Sr)[9] = sm[warp][0];
-  double(*Si)[9] = sm[warp][1];
-  double(*Jr)[9] = sm[warp][2];
-  double(*Ji)[9] = sm[warp][3];
-  int bp, bq;
-  rr_pair(nb, round, pair, bp, bq);
+// One warp: J = eigenvectors of the 8 x 8 pivot block G[I, I] (I = blocks bp, bq) by cyclic two-sided
+// Jacobi in shared memory (32 lanes = 8 rows x 4 disjoint rotations per inner round).
+// sm: [4][8][9] doubles (Sr, Si, Jr, Ji).  Writes J to out[2][8][8]; returns whether anything rotated.
+__device__ __forceinline__ bool pivot_solve(const double* __restrict__ Gr, const double* __restrict__ Gi, int ld,
+                                            int bp, int bq, double thr_abs2, double thr_rel2, int max_inner,
+                                            double (*sm)[8][9], double* __restrict__ out, int lane) {
+  double(*Sr)[9] = sm[0];
+  double(*Si)[9] = sm[1];
+  double(*Jr)[9] = sm[2];
+  double(*Ji)[9] = sm[3];
   for (int e = lane; e < 64; e += 32) {
     const int a = e >> 3, b = e & 7;
     const long long o = (long long)pair_index(bp, bq, a) * ld + pair_index(bp, bq, b);
-    Sr[a][b] = Gr[o];
-    Si[a][b] = Gi[o];
+    Sr[a][b] = __ldcg(Gr + o);
+    Si[a][b] = __ldcg(Gi + o);
     Jr[a][b] = (a == b) ? 1.0 : 0.0;
     Ji[a][b] = 0.0;
   }
   __syncwarp();
   const int i = lane >> 2, slot = lane & 3;
-  const double thr_abs2 = thr[0], thr_rel2 = thr[1];
   bool any_total = false;
   for (int sweep = 0; sweep < max_inner; ++sweep) {
     bool any = false;
@@ -161,109 +153,311 @@ __global__ void __launch_bounds__(128) jacobi_pivot_kernel(const double* __restr
     if (!__any_sync(0xffffffffu, any)) break;
     any_total = true;
   }
-  double* out = Jbuf + (long long)pair * 128;
   for (int e = lane; e < 64; e += 32) {
     out[e] = Jr[e >> 3][e & 7];
     out[64 + e] = Ji[e >> 3][e & 7];
   }
+  return any_total;
+}
+
+// Two-kernel variant, kernel 1: one warp per pivot pair.
+// Jbuf: [pair][2][8][8] (Re, Im), flags[pair] = 1 if any rotation was applied, *active += #rotating pairs.
+__global__ void __launch_bounds__(128) jacobi_pivot_kernel(const double* __restrict__ Gr, const double* __restrict__ Gi,
+                                                           int ld, int nb, int round,
+                                                           const double* __restrict__ thr /* [abs^2, rel^2] */,
+                                                           int max_inner, double* __restrict__ Jbuf,
+                                                           int* __restrict__ flags, int* __restrict__ active) {
+  __shared__ double sm[4][4][8][9];  // per warp: Sr, Si, Jr, Ji
+  // Programmatic dependent launch: this grid may be scheduled while its predecessor drains; it must not touch
+  // G before the predecessor has completed, and lets its own successor start launching right away.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = blockIdx.x * 4 + warp;
+  if (pair >= nb / 2) return;
+  int bp, bq;
+  rr_pair(nb, round, pair, bp, bq);
+  const bool any = pivot_solve(Gr, Gi, ld, bp, bq, thr[0], thr[1], max_inner, sm[warp], Jbuf + (long long)pair * 128, lane);
   if (lane == 0) {
-    flags[pair] = any_total ? 1 : 0;
-    if (any_total) atomicAdd(active, 1);
+    flags[pair] = any ? 1 : 0;
+    if (any) atomicAdd(active, 1);
   }
 }
 
-// G <- J^H G J and V <- V J for one round, one warp per 8 x 8 tile.  G stays Hermitian, so only the tiles
-// (i <= j) of the pair grid are computed; each is also written conjugate-transposed to its mirror (j, i).
+// Row-major enumeration of the upper triangle of an np x np tile grid (row i holds np - i tiles).
+__device__ __forceinline__ void upper_tile(long long task, int np, int& i, int& j) {
+  const double disc = (2.0 * np + 1.0) * (2.0 * np + 1.0) - 8.0 * (double)task;
+  i = (int)((2.0 * np + 1.0 - sqrt(disc)) * 0.5);
+  long long first = (long long)i * np - (long long)i * (i - 1) / 2;
+  while (first > task) {
+    --i;
+    first = (long long)i * np - (long long)i * (i - 1) / 2;
+  }
+  while (first + (np - i) <= task) {
+    first += np - i;
+    ++i;
+  }
+  j = i + (int)(task - first);
+}
+
+// One warp: tile (i, j) of G <- J^H G J (is_g; i <= j, also written conjugate-transposed to (j, i)) or row block
+// i of V <- V J (!is_g), for the pairing of `round`, as complex 8x8x8 products on DMMA.8x8x4.  The tile is read
+// and written by this warp only, so the update is in place.  ts: [2][8][9] doubles of per-warp scratch.
+__device__ __forceinline__ void update_tile(double* __restrict__ Gr, double* __restrict__ Gi, double* __restrict__ Vr,
+                                            double* __restrict__ Vi, int ld, int nb, int round,
+                                            const double* __restrict__ Jbuf, const int* __restrict__ flags,
+                                            bool is_g, int i, int j, double (*ts)[8][9], int lane) {
+  const bool fj = __ldcg(flags + j) != 0;
+  const bool fi = is_g && __ldcg(flags + i) != 0;
+  if (!fi && !fj) return;  // warp-uniform
+  const int fr = lane >> 2, fk = lane & 3;
+  int jp, jq;
+  rr_pair(nb, round, j, jp, jq);
+  int ip = 0, iq = 0;
+  if (is_g) rr_pair(nb, round, i, ip, iq);
+  double* Mr = is_g ? Gr : Vr;
+  double* Mi = is_g ? Gi : Vi;
+  const int row = is_g ? pair_index(ip, iq, fr) : i * 8 + fr;
+  // ---- T = M_tile * J_j  (identity if pair j did not rotate) ----
+  double tr[2] = {0.0, 0.0}, ti[2] = {0.0, 0.0};
+  const double* Jj = Jbuf + (long long)j * 128;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    const long long o = (long long)row * ld + pair_index(jp, jq, 4 * ks + fk);
+    const double ar = __ldcg(Mr + o), ai = __ldcg(Mi + o);
+    const double br = __ldcg(Jj + (4 * ks + fk) * 8 + fr), bi = __ldcg(Jj + 64 + (4 * ks + fk) * 8 + fr);
+    dmma(tr[0], tr[1], ar, br);
+    dmma(tr[0], tr[1], -ai, bi);
+    dmma(ti[0], ti[1], ar, bi);
+    dmma(ti[0], ti[1], ai, br);
+  }
+  double outr[2] = {tr[0], tr[1]}, outi[2] = {ti[0], ti[1]};
+  if (is_g) {
+    // ---- out = J_i^H * T ----
+    double(*Tr)[9] = ts[0];
+    double(*Ti)[9] = ts[1];
+    __syncwarp();
+    Tr[fr][2 * fk] = tr[0];
+    Tr[fr][2 * fk + 1] = tr[1];
+    Ti[fr][2 * fk] = ti[0];
+    Ti[fr][2 * fk + 1] = ti[1];
+    __syncwarp();
+    const double* Ji_ = Jbuf + (long long)i * 128;
+    outr[0] = outr[1] = outi[0] = outi[1] = 0.0;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      // A operand: (J_i^H)[m = fr][k] = conj(J_i[k][fr]);  B operand: T[k][n = fr]
+      const double ar = __ldcg(Ji_ + (4 * ks + fk) * 8 + fr), ai = __ldcg(Ji_ + 64 + (4 * ks + fk) * 8 + fr);
+      const double br = Tr[4 * ks + fk][fr], bi = Ti[4 * ks + fk][fr];
+      dmma(outr[0], outr[1], ar, br);
+      dmma(outr[0], outr[1], ai, bi);
+      dmma(outi[0], outi[1], ar, bi);
+      dmma(outi[0], outi[1], -ai, br);
+    }
+  }
+  const int col = pair_index(jp, jq, 2 * fk);
+  const long long o = (long long)row * ld + col;
+  *reinterpret_cast<double2*>(Mr + o) = make_double2(outr[0], outr[1]);
+  *reinterpret_cast<double2*>(Mi + o) = make_double2(outi[0], outi[1]);
+  if (is_g && i != j) {  // mirror tile: G[c, r] = conj(G[r, c])
+    Mr[(long long)col * ld + row] = outr[0];
+    Mi[(long long)col * ld + row] = -outi[0];
+    Mr[(long long)(col + 1) * ld + row] = outr[1];
+    Mi[(long long)(col + 1) * ld + row] = -outi[1];
+  }
+}
+
+// Two-kernel variant, kernel 2: G <- J^H G J (upper tiles + mirrors) and V <- V J, one warp per 8 x 8 tile.
 __global__ void __launch_bounds__(256) jacobi_update_kernel(double* __restrict__ Gr, double* __restrict__ Gi,
                                                             double* __restrict__ Vr, double* __restrict__ Vi, int ld,
                                                             int nb, int round, const double* __restrict__ Jbuf,
                                                             const int* __restrict__ flags) {
-  __shared__ double ts[8][2][8][9];  // per warp: T (Re, Im) for the accumulator -> operand relayout
+  __shared__ double ts[8][2][8][9];
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int np = nb / 2;
   const int rb = nb * JB / 8;  // 8-row blocks of V
-  const long long n_g = (long long)np * (np + 1) / 2;  // upper-triangular tiles (i <= j)
+  const long long n_g = (long long)np * (np + 1) / 2;
   const long long total = n_g + (long long)rb * np;
-  const int fr = lane >> 2, fk = lane & 3;
   for (long long task = (long long)blockIdx.x * 8 + warp; task < total; task += (long long)gridDim.x * 8) {
     const bool is_g = task < n_g;
     int i, j;
     if (is_g) {
-      // Row-major enumeration of the upper triangle: row i holds np - i tiles.
-      const double disc = (2.0 * np + 1.0) * (2.0 * np + 1.0) - 8.0 * (double)task;
-      i = (int)((2.0 * np + 1.0 - sqrt(disc)) * 0.5);
-      long long first = (long long)i * np - (long long)i * (i - 1) / 2;
-      while (first > task) {
-        --i;
-        first = (long long)i * np - (long long)i * (i - 1) / 2;
-      }
-      while (first + (np - i) <= task) {
-        first += np - i;
-        ++i;
-      }
-      j = i + (int)(task - first);
+      upper_tile(task, np, i, j);
     } else {
-      i = (int)((task - n_g) / np);  // row block of V
+      i = (int)((task - n_g) / np);
       j = (int)((task - n_g) % np);
     }
-    const bool fj = flags[j] != 0;
-    const bool fi = is_g && flags[i] != 0;
-    if (!fi && !fj) continue;  // warp-uniform
-    int jp, jq;
-    rr_pair(nb, round, j, jp, jq);
-    int ip = 0, iq = 0;
-    if (is_g) rr_pair(nb, round, i, ip, iq);
-    double* Mr = is_g ? Gr : Vr;
-    double* Mi = is_g ? Gi : Vi;
-    const int row = is_g ? pair_index(ip, iq, fr) : i * 8 + fr;
-    // ---- T = M_tile * J_j  (identity if pair j did not rotate) ----
-    double tr[2] = {0.0, 0.0}, ti[2] = {0.0, 0.0};
-    const double* Jj = Jbuf + (long long)j * 128;
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      const long long o = (long long)row * ld + pair_index(jp, jq, 4 * ks + fk);
-      const double ar = Mr[o], ai = Mi[o];
-      const double br = Jj[(4 * ks + fk) * 8 + fr], bi = Jj[64 + (4 * ks + fk) * 8 + fr];
-      dmma(tr[0], tr[1], ar, br);
-      dmma(tr[0], tr[1], -ai, bi);
-      dmma(ti[0], ti[1], ar, bi);
-      dmma(ti[0], ti[1], ai, br);
+    update_tile(Gr, Gi, Vr, Vi, ld, nb, round, Jbuf, flags, is_g, i, j, ts[warp], lane);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent variant: the whole iteration (all rounds of all sweeps) in ONE cooperative launch.
+//
+// Kernel boundaries cost ~4.4 us each on this part (measured with empty kernels in a CUDA graph) — 43% of a
+// 20 us round.  Here all CTAs are co-resident and synchronise through a software grid barrier (~1.5 us); in
+// addition the pivot solves of round r+1 overlap the bulk of the update of round r:
+//   phase 1  all warps : update(r) of the 2 np "priority" tiles that contain next round's pivot blocks
+//   barrier
+//   phase 2  pivot warps: J(r+1) from those tiles   ||   all other warps: the rest of update(r), V <- V J(r)
+//   barrier
+// J and the rotation flags are double-buffered by round parity.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch, unsigned int nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    epoch += 1;
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const unsigned int target = epoch * nblocks;
+    unsigned int spins = 0;
+    while (true) {
+      unsigned int v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (v >= target) break;
+      __nanosleep(32);
+      if (++spins > (1u << 25)) __trap();  // a lost CTA surfaces as an error, never as a hung GPU
     }
-    double outr[2] = {tr[0], tr[1]}, outi[2] = {ti[0], ti[1]};
-    if (is_g) {
-      // ---- out = J_i^H * T ----
-      double(*Tr)[9] = ts[warp][0];
-      double(*Ti)[9] = ts[warp][1];
-      __syncwarp();
-      Tr[fr][2 * fk] = tr[0];
-      Tr[fr][2 * fk + 1] = tr[1];
-      Ti[fr][2 * fk] = ti[0];
-      Ti[fr][2 * fk + 1] = ti[1];
-      __syncwarp();
-      const double* Ji_ = Jbuf + (long long)i * 128;
-      outr[0] = outr[1] = outi[0] = outi[1] = 0.0;
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        // A operand: (J_i^H)[m = fr][k] = conj(J_i[k][fr]);  B operand: T[k][n = fr]
-        const double ar = Ji_[(4 * ks + fk) * 8 + fr], ai = Ji_[64 + (4 * ks + fk) * 8 + fr];
-        const double br = Tr[4 * ks + fk][fr], bi = Ti[4 * ks + fk][fr];
-        dmma(outr[0], outr[1], ar, br);
-        dmma(outr[0], outr[1], ai, bi);
-        dmma(outi[0], outi[1], ar, bi);
-        dmma(outi[0], outi[1], -ai, br);
-      }
-    }
-    const int col = pair_index(jp, jq, 2 * fk);
-    const long long o = (long long)row * ld + col;
-    *reinterpret_cast<double2*>(Mr + o) = make_double2(outr[0], outr[1]);
-    *reinterpret_cast<double2*>(Mi + o) = make_double2(outi[0], outi[1]);
-    if (is_g && i != j) {  // mirror tile: G[c, r] = conj(G[r, c])
-      Mr[(long long)col * ld + row] = outr[0];
-      Mi[(long long)col * ld + row] = -outi[0];
-      Mr[(long long)(col + 1) * ld + row] = outr[1];
-      Mi[(long long)(col + 1) * ld + row] = -outi[1];
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// Round-robin bookkeeping: partner of block B in round rho, and the pair slot of block B in round r.
+__device__ __forceinline__ int rr_partner(int n, int rho, int B) {
+  const int R = n - 1;
+  if (B == R) return rho;
+  if (B == rho) return R;
+  return ((2 * rho - B) % R + R) % R;
+}
+__device__ __forceinline__ int rr_slot(int n, int r, int B) {
+  const int R = n - 1;
+  if (B == R || B == r) return 0;
+  const int s = ((B - r) % R + R) % R;
+  return s <= n / 2 - 1 ? s : ((r - B) % R + R) % R;
+}
+
+struct JacobiArgs {
+  double *Gr, *Gi, *Vr, *Vi;
+  int ld, nb, max_inner, max_sweeps;
+  const double* thr;     // [abs^2, rel^2]
+  double* Jbuf;          // [2][np][128]
+  int* flags;            // [2][np]
+  int* active;           // [max_sweeps + 2] rotation counters per sweep window
+  unsigned int* barrier; // grid barrier counter (zeroed by the host)
+  int* sweeps_out;       // number of sweeps executed; negative if not converged
+};
+
+constexpr int JPW = 32;  // warps per CTA of the persistent kernel: one 1024-thread CTA per SM keeps the grid
+                         // barrier at one atomic per SM and the register budget at 64 per thread
+
+__global__ void __launch_bounds__(JPW * 32, 1) jacobi_persistent_kernel(const JacobiArgs a) {
+  __shared__ double ts[JPW][2][8][9];
+  __shared__ double psm[4][8][9];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb = a.nb, np = nb / 2, R = nb - 1, ld = a.ld;
+  const int rb = nb * JB / 8;
+  const long long n_g = (long long)np * (np + 1) / 2;
+  const long long total = n_g + (long long)rb * np;
+  const unsigned int nblocks = gridDim.x;
+  unsigned int epoch = 0;
+  const double thr_abs2 = a.thr[0], thr_rel2 = a.thr[1];
+  // Pivot p is solved by warp 0 of CTA p (np <= gridDim.x is checked by the host); everyone else is a worker.
+  const bool pivot_warp = warp == 0 && (int)blockIdx.x < np;
+  const long long n_workers = (long long)gridDim.x * JPW - np;
+  const long long worker =
+      pivot_warp ? -1 : (long long)blockIdx.x * JPW + warp - ((int)blockIdx.x < np ? blockIdx.x + 1 : np);
+
+  // Prologue: J(0) of the first round.
+  if (pivot_warp) {
+    int bp, bq;
+    rr_pair(nb, 0, blockIdx.x, bp, bq);
+    const bool any = pivot_solve(a.Gr, a.Gi, ld, bp, bq, thr_abs2, thr_rel2, a.max_inner, psm,
+                                 a.Jbuf + (long long)blockIdx.x * 128, lane);
+    if (lane == 0) {
+      a.flags[blockIdx.x] = any ? 1 : 0;
+      if (any) atomicAdd(a.active, 1);
     }
   }
+  grid_barrier(a.barrier, epoch, nblocks);
+
+  int sweeps_done = 0;
+  bool converged = false;
+  for (int sweep = 0; sweep < a.max_sweeps && !converged; ++sweep) {
+    for (int r = 0; r < R; ++r) {
+      const int g = sweep * R + r;  // global round number
+      const int cur = g & 1, nxt = cur ^ 1;
+      const double* Jcur = a.Jbuf + (long long)cur * np * 128;
+      const int* fcur = a.flags + cur * np;
+      const int rho = (r + 1) % R;  // pairing of the next round
+      // ---- phase 1: priority tiles (all diagonal tiles + the tile joining the two blocks of each next pair)
+      for (long long task = (long long)blockIdx.x * JPW + warp; task < 2 * np; task += (long long)gridDim.x * JPW) {
+        int i, j;
+        if (task < np) {
+          i = j = (int)task;
+        } else {
+          int bp, bq;
+          rr_pair(nb, rho, (int)task - np, bp, bq);
+          const int sa = rr_slot(nb, r, bp), sb = rr_slot(nb, r, bq);
+          if (sa == sb) continue;  // only when nb == 2: the pivot block is the diagonal tile itself
+          i = sa < sb ? sa : sb;
+          j = sa < sb ? sb : sa;
+          // Two next-round pairs can join the same two current pairs; the tile is then updated once, by the
+          // task whose block is the first block of pair i.
+          const int xi = sa < sb ? bp : bq;
+          int ip, iq, jp, jq;
+          rr_pair(nb, r, i, ip, iq);
+          rr_pair(nb, r, j, jp, jq);
+          if (xi != ip) {
+            const int pa = rr_partner(nb, rho, ip);
+            if (pa == jp || pa == jq) continue;
+          }
+        }
+        update_tile(a.Gr, a.Gi, a.Vr, a.Vi, ld, nb, r, Jcur, fcur, true, i, j, ts[warp], lane);
+      }
+      grid_barrier(a.barrier, epoch, nblocks);
+      // ---- phase 2: next round's pivots || the rest of this round's update
+      if (pivot_warp) {
+        int bp, bq;
+        rr_pair(nb, rho, blockIdx.x, bp, bq);
+        const bool any = pivot_solve(a.Gr, a.Gi, ld, bp, bq, thr_abs2, thr_rel2, a.max_inner, psm,
+                                     a.Jbuf + ((long long)nxt * np + blockIdx.x) * 128, lane);
+        if (lane == 0) {
+          a.flags[nxt * np + blockIdx.x] = any ? 1 : 0;
+          // rotations found while preparing round g + 1 are counted in the sweep that round belongs to
+          if (any) atomicAdd(a.active + (g + 1) / R, 1);
+        }
+      } else {
+        for (long long task = worker; task < total; task += n_workers) {
+          const bool is_g = task < n_g;
+          int i, j;
+          if (is_g) {
+            upper_tile(task, np, i, j);
+            if (i == j) continue;  // diagonal tiles were done in phase 1
+            int ip, iq, jp, jq;
+            rr_pair(nb, r, i, ip, iq);
+            rr_pair(nb, r, j, jp, jq);
+            const int pa = rr_partner(nb, rho, ip), pb = rr_partner(nb, rho, iq);
+            if (pa == jp || pa == jq || pb == jp || pb == jq) continue;  // priority tile, done in phase 1
+          } else {
+            i = (int)((task - n_g) / np);
+            j = (int)((task - n_g) % np);
+          }
+          update_tile(a.Gr, a.Gi, a.Vr, a.Vi, ld, nb, r, Jcur, fcur, is_g, i, j, ts[warp], lane);
+        }
+      }
+      grid_barrier(a.barrier, epoch, nblocks);
+    }
+    sweeps_done = sweep + 1;
+    // Converged when no pivot of this sweep rotated (the counters were completed before the last barrier;
+    // the pivots prepared for the next sweep's first round are counted there and are then identities too).
+    int act;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(act) : "l"(a.active + sweep) : "memory");
+    converged = act == 0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.sweeps_out = converged ? sweeps_done : -sweeps_done;
 }
 
 __global__ void jacobi_diag_kernel(const double* __restrict__ Gr, int ld, int m, double* __restrict__ lam) {

@@ -540,17 +540,20 @@ static int heev_jacobi(nls_ctx* ctx, const double* A, int m, double scale, doubl
   const int mp = nb * JB, np = nb / 2;
   const size_t mm = (size_t)mp * mp;
   NLS_TRY(ensure(ctx, ctx->jac_mat, 4 * mm * 8));
-  NLS_TRY(ensure(ctx, ctx->jac_small, (size_t)np * 128 * 8 + (size_t)(np + 8) * 4 + (size_t)(2 * mp + 8) * 8 + (size_t)mp * 4));
+  const int max_sweeps = 60;
+  NLS_TRY(ensure(ctx, ctx->jac_small, (size_t)2 * np * 128 * 8 + (size_t)(2 * mp + 8) * 8 +
+                                          (size_t)(2 * np + max_sweeps + 16 + mp) * 4));
   double* Gr = (double*)ctx->jac_mat.p;
   double* Gi = Gr + mm;
   double* Vr = Gi + mm;
   double* Vi = Vr + mm;
-  double* Jbuf = (double*)ctx->jac_small.p;
-  double* lam_raw = Jbuf + (size_t)np * 128;
+  double* Jbuf = (double*)ctx->jac_small.p;  // [2][np][128] (double-buffered by the persistent kernel)
+  double* lam_raw = Jbuf + (size_t)2 * np * 128;
   double* fro2 = lam_raw + mp;
-  int* flags = (int*)(fro2 + 8);
-  int* active = flags + np;
-  int* perm = active + 8;
+  int* flags = (int*)(fro2 + 8);            // [2][np]
+  int* active = flags + 2 * np;             // [max_sweeps + 2]
+  int* misc = active + max_sweeps + 2;      // [0] grid barrier counter, [1] sweeps executed
+  int* perm = misc + 8;
   ProfScope scope(ctx, NLS_PROF_OTHER);
   jacobi_init_kernel<<<grid_for((long long)mm), 256, 0, ctx->stream>>>(A, m, mp, scale, Gr, Gi, Vr, Vi);
   NLS_TRY(check_launch(ctx, "jacobi_init_kernel"));
@@ -565,6 +568,32 @@ static int heev_jacobi(nls_ctx* ctx, const double* A, int m, double scale, doubl
   CUDA_TRY(cudaMemcpyAsync(thr, h_thr, 16, cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   const long long tasks = (long long)np * (np + 1) / 2 + (long long)(mp / 8) * np;
+  int sweep = 0, h_active = 1;
+  const char* pers = getenv("NLS_JACOBI_PERSISTENT");
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jacobi_persistent_kernel, JPW * 32, 0));
+  const int coop_grid = ctx->sm_count;  // one 1024-thread CTA per SM
+  // The persistent variant is correct but measured slower than the graph of short kernels on B200 (the pivot
+  // chains share the FP64 pipe with the update's DMMAs): opt-in with NLS_JACOBI_PERSISTENT=1.
+  const bool persistent = (pers && pers[0] == '1') && occ >= 1 && np <= coop_grid && !getenv("NLS_JACOBI_DIAG");
+  if (persistent) {
+    // One cooperative launch runs every round of every sweep (software grid barrier, pivots of round r+1
+    // overlapped with the bulk of update r); the host only reads back the sweep count.
+    CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)(2 * np + max_sweeps + 16) * 4, ctx->stream));
+    JacobiArgs ja;
+    ja.Gr = Gr; ja.Gi = Gi; ja.Vr = Vr; ja.Vi = Vi;
+    ja.ld = mp; ja.nb = nb; ja.max_inner = ctx->jac_inner; ja.max_sweeps = max_sweeps;
+    ja.thr = thr; ja.Jbuf = Jbuf; ja.flags = flags; ja.active = active;
+    ja.barrier = (unsigned int*)misc; ja.sweeps_out = misc + 1;
+    void* kargs[] = {&ja};
+    CUDA_TRY(cudaLaunchCooperativeKernel((void*)jacobi_persistent_kernel, dim3(coop_grid), dim3(JPW * 32), kargs, 0, ctx->stream));
+    ctx->launches += 1;
+    int h_sweeps = 0;
+    CUDA_TRY(cudaMemcpyAsync(&h_sweeps, misc + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    sweep = h_sweeps < 0 ? -h_sweeps : h_sweeps;
+    h_active = h_sweeps > 0 ? 0 : 1;
+  } else {
   const int upd_grid = (int)std::min<long long>((tasks + 7) / 8, (long long)ctx->sm_count * 8);
   if (!ctx->jac_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->jac_stream, cudaStreamNonBlocking));
   if (!ctx->jac_graph || ctx->jac_graph_key != (const void*)Gr || ctx->jac_graph_nb != nb) {
@@ -576,9 +605,32 @@ static int heev_jacobi(nls_ctx* ctx, const double* A, int m, double scale, doubl
     cudaGraph_t graph = nullptr;
     CUDA_TRY(cudaStreamBeginCapture(ctx->jac_stream, cudaStreamCaptureModeRelaxed));
     cudaMemsetAsync(active, 0, sizeof(int), ctx->jac_stream);
+    const char* diag = getenv("NLS_JACOBI_DIAG");  // timing experiments only: "pivot" / "update" runs one kernel kind
+    const bool do_pivot = !diag || strcmp(diag, "update") != 0, do_update = !diag || strcmp(diag, "pivot") != 0;
+    // Programmatic dependent launch (griddepcontrol.wait at the top of both kernels) is wired but OFF by
+    // default: on B200 it measured slower (82.8 vs 70.2 ms at m = 1025); NLS_JACOBI_PDL=1 enables it.
+    const char* pdl_env = getenv("NLS_JACOBI_PDL");
+    cudaLaunchAttribute pdl;
+    pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl.val.programmaticStreamSerializationAllowed = (pdl_env && pdl_env[0] == '1') ? 1 : 0;
+    cudaLaunchConfig_t cfg_p = {}, cfg_u = {};
+    cfg_p.gridDim = dim3((np + 3) / 4);
+    cfg_p.blockDim = dim3(128);
+    cfg_p.stream = ctx->jac_stream;
+    cfg_p.attrs = &pdl;
+    cfg_p.numAttrs = 1;
+    cfg_u = cfg_p;
+    cfg_u.gridDim = dim3(upd_grid);
+    cfg_u.blockDim = dim3(256);
+    const double* thr_c = thr;
+    const double* Jbuf_c = Jbuf;
+    const int* flags_c = flags;
+    const double *Gr_c = Gr, *Gi_c = Gi;
     for (int round = 0; round < nb - 1; ++round) {
-      jacobi_pivot_kernel<<<(np + 3) / 4, 128, 0, ctx->jac_stream>>>(Gr, Gi, mp, nb, round, thr, ctx->jac_inner, Jbuf, flags, active);
-      jacobi_update_kernel<<<upd_grid, 256, 0, ctx->jac_stream>>>(Gr, Gi, Vr, Vi, mp, nb, round, Jbuf, flags);
+      if (do_pivot)
+        cudaLaunchKernelEx(&cfg_p, jacobi_pivot_kernel, Gr_c, Gi_c, mp, nb, round, thr_c, ctx->jac_inner, Jbuf, flags, active);
+      if (do_update)
+        cudaLaunchKernelEx(&cfg_u, jacobi_update_kernel, Gr, Gi, Vr, Vi, mp, nb, round, Jbuf_c, flags_c);
     }
     CUDA_TRY(cudaStreamEndCapture(ctx->jac_stream, &graph));
     cudaError_t ge = cudaGraphInstantiate(&ctx->jac_graph, graph, 0);
@@ -587,16 +639,17 @@ static int heev_jacobi(nls_ctx* ctx, const double* A, int m, double scale, doubl
     ctx->jac_graph_key = (const void*)Gr;
     ctx->jac_graph_nb = nb;
   }
-  int sweep = 0, h_active = 1;
-  const int max_sweeps = 60;
-  for (; sweep < max_sweeps && h_active > 0; ++sweep) {
+  const int graph_sweeps = getenv("NLS_JACOBI_DIAG") ? 12 : max_sweeps;
+  for (; sweep < graph_sweeps && h_active > 0; ++sweep) {
     CUDA_TRY(cudaGraphLaunch(ctx->jac_graph, ctx->jac_stream));
     ctx->launches += 2 * (nb - 1);
     CUDA_TRY(cudaMemcpyAsync(&h_active, active, sizeof(int), cudaMemcpyDeviceToHost, ctx->jac_stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->jac_stream));
   }
+  }
   ctx->eig_sweeps = sweep;
-  if (h_active > 0) return fail(NLS_ERR_SOLVER, "Jacobi eigensolver did not converge in %d sweeps", max_sweeps);
+  if (h_active > 0 && !getenv("NLS_JACOBI_DIAG"))
+    return fail(NLS_ERR_SOLVER, "Jacobi eigensolver did not converge in %d sweeps", max_sweeps);
   jacobi_diag_kernel<<<(mp + 255) / 256, 256, 0, ctx->stream>>>(Gr, mp, mp, lam_raw);
   NLS_TRY(check_launch(ctx, "jacobi_diag_kernel"));
   std::vector<double> h_lam(mp);
