@@ -149,12 +149,13 @@ int nls_primal_finalize(nls_ctx* ctx, const double* X, const double* y, const do
  * and predict_std (:467-469, :477) with one pass over phi(x):
  *     yhat_i = Re(phi_i beta);   sigma_i = sqrt( sum_k |(phi_i B)_k|^2 w_k )
  * B (m x m complex128) and w (m) describe (gamma C + A)^-1 = B diag(w) B^H: either the
- * eigenbasis (B = Q, w = inv_c/(lam+gamma)) or the inverse Cholesky factor (B = U^-1, w = 1).
+ * eigenbasis (B = Q, w = inv_c/(lam+gamma)) or the inverse Cholesky factor (B = U^-1, w = 1; pass
+ * b_upper = 1 so that only the non-zero half of the triangular contraction is computed).
  * yhat_out / sigma_out may be NULL to skip that output.
  * ------------------------------------------------------------------------------------------- */
 int nls_primal_predict(nls_ctx* ctx, const double* X, int64_t n, int d, const double* shift,
                        const double* W, int D, const double* beta, const double* B,
-                       const double* w, double* yhat_out, double* sigma_out);
+                       const double* w, int b_upper, double* yhat_out, double* sigma_out);
 
 /* ---------------------------------------------------------------------------------------------
  * Stage 5c — conformal quantile epilogue.  Replaces the per-row part of predict_quantiles

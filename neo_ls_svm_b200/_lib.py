@@ -46,7 +46,7 @@ def _signatures(lib: C.CDLL) -> None:
         "nls_cholesky_solve": ([p, p, i, d, p, p, p], i),
         "nls_primal_loo_sweep": ([p, p, p, p, i64, i, p, p, i, p, p, p, d, p, i, i, p, p], i),
         "nls_primal_finalize": ([p, p, p, p, i64, i, p, p, i, p, p, d, d, p, p, i, p, p, p, p, p, p], i),
-        "nls_primal_predict": ([p, p, i64, i, p, p, i, p, p, p, p, p], i),
+        "nls_primal_predict": ([p, p, i64, i, p, p, i, p, p, p, i, p, p], i),
         "nls_quantile_epilogue": ([p, p, p, i64, p, p, p, p, i, i, p, p, i, p], i),
         "nls_dual_sweep": ([p, p, i, i, p, p, p, p, i, i, p, p, p], i),
         "nls_dual_finalize": ([p, i, p, p, d, p, p, p, p, p, p, p], i),
@@ -246,7 +246,7 @@ class Context:
         return {"loo_residuals": out[0], "yhat_loo": out[1], "loo_leverage": out[2], "residuals": out[3],
                 "loo_std": out[4]}
 
-    def primal_predict(self, X, shift, W, beta=None, B=None, w=None, want_std: bool = False):
+    def primal_predict(self, X, shift, W, beta=None, B=None, w=None, want_std: bool = False, b_upper: bool = False):
         import torch
 
         n, d = X.shape
@@ -254,7 +254,7 @@ class Context:
         yhat = torch.empty((n,), dtype=torch.float64, device=X.device) if beta is not None else None
         sigma = torch.empty((n,), dtype=torch.float64, device=X.device) if want_std else None
         check(self.lib.nls_primal_predict(
-            self.handle, ptr(X), n, d, ptr(shift), ptr(W), D, ptr(beta), ptr(B), ptr(w), ptr(yhat), ptr(sigma)))
+            self.handle, ptr(X), n, d, ptr(shift), ptr(W), D, ptr(beta), ptr(B), ptr(w), int(b_upper), ptr(yhat), ptr(sigma)))
         return yhat, sigma
 
     def quantile_epilogue(self, yhat, sigma, beta_abs, beta_rel, bias_abs, bias_rel, regressor: bool,

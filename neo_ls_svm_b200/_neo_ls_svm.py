@@ -84,26 +84,27 @@ class NeoLSSVM(BaseEstimator):
         ctx = _lib.context()
         return ctx, torch, torch.device("cuda", ctx.device)
 
-    def _primal_device_state(self):
+    def _primal_device_state(self, want_std: bool = False):
         """Device copies of what predict needs (rebuilt lazily, e.g. after unpickling)."""
         st = self.__dict__.get(_DEVICE_STATE)
-        if st is not None and st.get("kind") == "primal":
-            return st
         ctx, torch, dev = self._gpu()
-        shift, W = self.primal_feature_map_.device_weights(self.n_features_in_)
-        m = W.shape[1] + 1
-        U = torch.from_numpy(np.triu(np.asarray(self.L_[0], dtype=np.complex128))).to(dev)
-        # (γC + A)⁻¹ = U⁻¹ U⁻ᴴ: the variance kernel takes B = U⁻¹ with unit weights.
-        B = torch.linalg.solve_triangular(U, torch.eye(m, dtype=torch.complex128, device=dev), upper=True)
-        st = {
-            "kind": "primal",
-            "shift": torch.from_numpy(shift).to(dev),
-            "W": torch.from_numpy(W).to(dev),
-            "beta": torch.from_numpy(np.asarray(self.β̂_, dtype=np.complex128)).to(dev),
-            "B": B.contiguous(),
-            "w": torch.ones(m, dtype=torch.float64, device=dev),
-        }
-        self.__dict__[_DEVICE_STATE] = st
+        if st is None or st.get("kind") != "primal":
+            shift, W = self.primal_feature_map_.device_weights(self.n_features_in_)
+            st = {
+                "kind": "primal",
+                "shift": torch.from_numpy(shift).to(dev),
+                "W": torch.from_numpy(W).to(dev),
+                "beta": torch.from_numpy(np.asarray(self.β̂_, dtype=np.complex128)).to(dev),
+                "U": torch.from_numpy(np.asarray(self.L_[0], dtype=np.complex128)).to(dev),
+            }
+            self.__dict__[_DEVICE_STATE] = st
+        if want_std and "B" not in st:
+            # (γC + A)⁻¹ = U⁻¹ U⁻ᴴ: the variance kernel takes the triangular B = U⁻¹ with unit weights and
+            # skips the zero half of the contraction (4m² instead of 8m² flops per row).  Built once, lazily.
+            m = st["U"].shape[0]
+            U = torch.triu(st["U"])
+            st["B"] = torch.linalg.solve_triangular(U, torch.eye(m, dtype=torch.complex128, device=dev), upper=True).contiguous()
+            st["w"] = torch.ones(m, dtype=torch.float64, device=dev)
         return st
 
     # ------------------------------------------------------------------------------------------
@@ -138,11 +139,7 @@ class NeoLSSVM(BaseEstimator):
         self.L_ = (fit.U.cpu().numpy().astype(cdt), False)  # scipy.linalg.cho_factor layout (:177)
         self.residuals_ = rows["residuals"].astype(dt)
         self.loo_std_ = rows["loo_std"].astype(dt)
-        m = W.shape[1] + 1
-        self.__dict__[_DEVICE_STATE] = {
-            "kind": "primal", "shift": shd, "W": Wd, "beta": fit.beta, "B": fit.Q,
-            "w": _primal.variance_weights(fit.lam, fit.inv_c, fit.gamma), "m": m,
-        }
+        self.__dict__[_DEVICE_STATE] = {"kind": "primal", "shift": shd, "W": Wd, "beta": fit.beta, "U": fit.U}
         return fit.beta.cpu().numpy().astype(cdt), self.γs_[fit.opt]
 
     def _optimize_α̂_γ(self, X, y, s, ρ: float = 1.0):
@@ -231,11 +228,11 @@ class NeoLSSVM(BaseEstimator):
         dt = X.dtype
         ctx, torch, dev = self._gpu()
         if self.primal_:
-            st = self._primal_device_state()
+            st = self._primal_device_state(want_std)
             Xd = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).to(dev)
             yhat, sigma = ctx.primal_predict(
                 Xd, st["shift"], st["W"], beta=st["beta"] if want_decision else None,
-                B=st["B"] if want_std else None, w=st["w"] if want_std else None, want_std=want_std,
+                B=st["B"] if want_std else None, w=st["w"] if want_std else None, want_std=want_std, b_upper=True,
             )
         else:
             from . import _dual

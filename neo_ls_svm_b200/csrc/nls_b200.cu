@@ -268,7 +268,7 @@ static inline int tail_split(int m) { return (m % BN != 0 && m % BN <= 4 && m > 
 struct BasisScratch {
   double *bt, *bias_r, *bias_i, *v_r, *v_i, *w;
 };
-static int prep_basis(nls_ctx* ctx, const MapGeom& g, const double* B, BasisScratch* out) {
+static int prep_basis(nls_ctx* ctx, const MapGeom& g, const double* B, BasisScratch* out, int upper = 0) {
   const size_t bt_bytes = (size_t)2 * g.Np * g.Dp * 8;
   NLS_TRY(ensure(ctx, ctx->bt, bt_bytes));
   NLS_TRY(ensure(ctx, ctx->small, (size_t)8 * g.Np * 8));
@@ -280,7 +280,7 @@ static int prep_basis(nls_ctx* ctx, const MapGeom& g, const double* B, BasisScra
   out->v_i = sm + 3 * g.Np;
   out->w = sm + 4 * g.Np;
   dim3 grid((g.m + 31) / 32, (g.m + 31) / 32), block(32, 8);
-  split_basis_kernel<<<grid, block, 0, ctx->stream>>>(B, g.m, g.D, g.Np, g.Dp, out->bt, out->bias_r, out->bias_i);
+  split_basis_kernel<<<grid, block, 0, ctx->stream>>>(B, g.m, g.D, g.Np, g.Dp, upper, out->bt, out->bias_r, out->bias_i);
   return check_launch(ctx, "split_basis_kernel");
 }
 
@@ -810,7 +810,8 @@ extern "C" int nls_primal_loo_sweep(nls_ctx* ctx, const double* X, const double*
 // ---------------------------------------------------------------------------------------------
 // Shared by stage 4c and stage 5: per-row yhat (two coefficient vectors) and sigma2 for a chunk.
 // ---------------------------------------------------------------------------------------------
-static int variance_chunk(nls_ctx* ctx, const MapGeom& g, const BasisScratch& bs, int rows, double* sigma2_out) {
+static int variance_chunk(nls_ctx* ctx, const MapGeom& g, const BasisScratch& bs, int rows, double* sigma2_out,
+                          int b_upper = 0) {
   const int full_cols = tail_split(g.m);
   const int gemm_tiles = (full_cols + BN - 1) / BN;
   const int ntiles = gemm_tiles + (full_cols < g.m ? 1 : 0);
@@ -826,6 +827,7 @@ static int variance_chunk(nls_ctx* ctx, const MapGeom& g, const BasisScratch& bs
   vp.w = bs.w;
   vp.part = (double*)ctx->part.p;
   vp.part_ld = cap;
+  vp.b_upper = b_upper;
   NLS_TRY((launch_gemm<MODE_COMPLEX, OpVariance>(ctx, vp, dim3(gemm_tiles, (rows + BM - 1) / BM), rows, 2 * g.Np,
                                                   NLS_PROF_VARIANCE, "variance")));
   if (full_cols < g.m) {
@@ -883,7 +885,7 @@ extern "C" int nls_primal_finalize(nls_ctx* ctx, const double* X, const double* 
 
 extern "C" int nls_primal_predict(nls_ctx* ctx, const double* X, int64_t n, int d, const double* shift,
                                   const double* W, int D, const double* beta, const double* B, const double* w,
-                                  double* yhat_out, double* sigma_out) {
+                                  int b_upper, double* yhat_out, double* sigma_out) {
   NLS_TRY(check_map_args(ctx, X, n, d, shift, W, D));
   if (yhat_out && !beta) return fail(NLS_ERR_INVALID, "beta is required for yhat_out");
   if (sigma_out && (!B || !w)) return fail(NLS_ERR_INVALID, "B and w are required for sigma_out");
@@ -891,7 +893,7 @@ extern "C" int nls_primal_predict(nls_ctx* ctx, const double* X, int64_t n, int 
   NLS_TRY(prep_weights(ctx, g, W));
   BasisScratch bs;
   if (sigma_out) {
-    NLS_TRY(prep_basis(ctx, g, B, &bs));
+    NLS_TRY(prep_basis(ctx, g, B, &bs, b_upper));
     CUDA_TRY(cudaMemcpyAsync(bs.w, w, (size_t)g.m * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   }
   const long long cap = ctx->chunk_rows;
@@ -908,7 +910,7 @@ extern "C" int nls_primal_predict(nls_ctx* ctx, const double* X, int64_t n, int 
       NLS_TRY(check_launch(ctx, "gemv_pair_kernel"));
     }
     if (sigma_out) {
-      NLS_TRY(variance_chunk(ctx, g, bs, rows, sigma2));
+      NLS_TRY(variance_chunk(ctx, g, bs, rows, sigma2, b_upper));
       sqrt_kernel<<<(rows + 255) / 256, 256, 0, ctx->stream>>>(sigma2, rows, sigma_out + i0);
       NLS_TRY(check_launch(ctx, "sqrt_kernel"));
     }
@@ -1202,6 +1204,7 @@ extern "C" int nls_dual_predict(nls_ctx* ctx, const double* Xq, int64_t nq, cons
       vp.w = w;
       vp.part = (double*)ctx->part.p;
       vp.part_ld = cq;
+      vp.b_upper = 0;
       NLS_TRY((launch_gemm<MODE_REAL, OpRowQuad>(ctx, vp, dim3(ntiles, (rows + BM - 1) / BM), rows, n, NLS_PROF_VARIANCE,
                                                   "dual_variance")));
       rowsum_reduce_kernel<<<(rows + 255) / 256, 256, 0, ctx->stream>>>((const double*)ctx->part.p, ntiles, cq, rows, q);

@@ -358,6 +358,7 @@ struct OpVarianceT {
     const double* w;
     double* part;     // [gridDim.x][part_ld]
     long long part_ld;
+    int b_upper;      // B is upper triangular (B = U^-1): column k only needs rows l <= k of the contraction
   };
   static __device__ __forceinline__ Tile tile(const Params& p) {
     Tile t;
@@ -365,6 +366,7 @@ struct OpVarianceT {
     t.m0 = blockIdx.y * BM;
     t.k_begin = 0;
     t.k_end = p.A.kext < p.B.kext ? p.A.kext : p.B.kext;
+    if (p.b_upper && t.n0 + BN < t.k_end) t.k_end = t.n0 + BN;  // halves the flops of predict_std
     t.valid = true;
     return t;
   }

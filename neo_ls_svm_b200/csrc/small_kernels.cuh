@@ -48,14 +48,14 @@ __global__ void transpose_w_kernel(const double* __restrict__ W, int d, int D, i
 
 // Split a complex m x m basis B (numpy layout B[l, k]) into K-contiguous transposed planes
 //   bt[k, l] = Re B[l, k],  bt[Np + k, l] = Im B[l, k]   (l < D),   bias = B[D, :].
-__global__ void split_basis_kernel(const double* __restrict__ B, int m, int D, int Np, long long ldk,
+__global__ void split_basis_kernel(const double* __restrict__ B, int m, int D, int Np, long long ldk, int upper,
                                    double* __restrict__ bt, double* __restrict__ bias_r, double* __restrict__ bias_i) {
   __shared__ double tr[32][33], ti[32][33];
   const int k0 = blockIdx.x * 32, l0 = blockIdx.y * 32;
   for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
     const int l = l0 + dy, k = k0 + threadIdx.x;
     double re = 0.0, im = 0.0;
-    if (l < m && k < m) {
+    if (l < m && k < m && !(upper && l > k)) {  // a triangular basis is taken from its upper triangle only
       re = B[((long long)l * m + k) * 2];
       im = B[((long long)l * m + k) * 2 + 1];
     }

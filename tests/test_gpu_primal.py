@@ -72,9 +72,14 @@ def test_primal_fit_matches_reference(name, chunk, stash, golden, gpu):
     assert rel_err(sigma.cpu().numpy(), g["std"]) < TOL_PRED
     m = U.shape[0]
     Uinv = torch.linalg.solve_triangular(torch.triu(fit.U), torch.eye(m, dtype=torch.complex128, device="cuda"), upper=True)
-    _, sigma2 = ctx.primal_predict(dev(Xt), dev(shift), dev(W), B=Uinv.contiguous(),
-                                   w=torch.ones(m, dtype=torch.float64, device="cuda"), want_std=True)
+    ones = torch.ones(m, dtype=torch.float64, device="cuda")
+    _, sigma2 = ctx.primal_predict(dev(Xt), dev(shift), dev(W), B=Uinv.contiguous(), w=ones, want_std=True)
     assert rel_err(sigma2.cpu().numpy(), g["std"]) < TOL_PRED
+    # ... and with the triangular shortcut (only the non-zero half of the contraction), on the raw factor whose
+    # strict lower triangle holds garbage as scipy.linalg.cho_factor's does
+    Uinv_dirty = Uinv + torch.tril(torch.full_like(Uinv, 7.0), diagonal=-1)
+    _, sigma3 = ctx.primal_predict(dev(Xt), dev(shift), dev(W), B=Uinv_dirty.contiguous(), w=ones, want_std=True, b_upper=True)
+    assert rel_err(sigma3.cpu().numpy(), g["std"]) < TOL_PRED
 
 
 @pytest.mark.parametrize("name", ["reg_small", "c3_small"])
