@@ -32,41 +32,56 @@ struct BsTile {
 };
 
 // partial[tile, col] = sum over the tile's rows of w * [key(x) <= mid[bin, col]]
+// K = columns per lane (32 K columns per CTA); templated so that narrow matrices do not pay registers for
+// 256 columns.  Four rows are in flight per warp (independent gathers through perm).
+template <int K>
 __global__ void __launch_bounds__(256) bs_count_kernel(const double* __restrict__ X, int d,
                                                        const long long* __restrict__ perm,
                                                        const double* __restrict__ w, const BsTile* __restrict__ tiles,
                                                        const unsigned long long* __restrict__ mid,
                                                        double* __restrict__ partial) {
-  __shared__ double red[8][BS_COLS];
+  __shared__ double red[8][32 * K];
   const BsTile t = tiles[blockIdx.x];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int col0 = blockIdx.y * BS_COLS;
-  unsigned long long m[BS_K];
-  double acc[BS_K];
+  const int col0 = blockIdx.y * 32 * K;
+  unsigned long long m[K];
+  double acc[K];
 #pragma unroll
-  for (int k = 0; k < BS_K; ++k) {
+  for (int k = 0; k < K; ++k) {
     const int col = col0 + lane + 32 * k;
     m[k] = col < d ? mid[(long long)t.bin * d + col] : 0ull;
     acc[k] = 0.0;
   }
-  for (int r = t.r0 + warp; r < t.r1; r += 8) {
-    const double* x = X + perm[r] * d;
-    const double wr = w[r];
+  for (int r = t.r0 + warp; r < t.r1; r += 32) {
+    double xv[4][K], wv[4];
 #pragma unroll
-    for (int k = 0; k < BS_K; ++k) {
-      const int col = col0 + lane + 32 * k;
-      if (col < d) acc[k] += (dkey(x[col]) <= m[k]) ? wr : 0.0;
+    for (int u = 0; u < 4; ++u) {
+      const int rr = r + 8 * u;
+      const bool ok = rr < t.r1;
+      const double* x = X + (ok ? perm[rr] : perm[r]) * d;
+      wv[u] = ok ? w[rr] : 0.0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int col = col0 + lane + 32 * k;
+        xv[u][k] = col < d ? x[col] : 0.0;
+      }
     }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc[k] += (dkey(xv[u][k]) <= m[k]) ? wv[u] : 0.0;  // accumulated in row order
   }
 #pragma unroll
-  for (int k = 0; k < BS_K; ++k) red[warp][lane + 32 * k] = acc[k];
+  for (int k = 0; k < K; ++k) red[warp][lane + 32 * k] = acc[k];
   __syncthreads();
-  const int col = col0 + threadIdx.x;
-  if (col < d) {
-    double s = 0.0;
+  for (int c = threadIdx.x; c < 32 * K; c += 256) {
+    const int col = col0 + c;
+    if (col < d) {
+      double s = 0.0;
 #pragma unroll
-    for (int wv = 0; wv < 8; ++wv) s += red[wv][threadIdx.x];
-    partial[(long long)blockIdx.x * d + col] = s;
+      for (int q = 0; q < 8; ++q) s += red[q][c];
+      partial[(long long)blockIdx.x * d + col] = s;
+    }
   }
 }
 

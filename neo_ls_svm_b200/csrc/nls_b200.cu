@@ -1238,14 +1238,21 @@ extern "C" int nls_bin_median_stats(nls_ctx* ctx, const double* X, int64_t n, in
   const BsTile* tl = (const BsTile*)tiles;
   const int2* bt = (const int2*)bin_tiles;
   ProfScope scope(ctx, NLS_PROF_OTHER);
+  const long long* pm = (const long long*)perm;
+  auto count = [&]() {  // columns per lane: 1, 2, 4 or 8
+    if (d <= 32) bs_count_kernel<1><<<dim3(ntiles, 1), 256, 0, ctx->stream>>>(X, d, pm, w, tl, mid, partial);
+    else if (d <= 64) bs_count_kernel<2><<<dim3(ntiles, 1), 256, 0, ctx->stream>>>(X, d, pm, w, tl, mid, partial);
+    else if (d <= 128) bs_count_kernel<4><<<dim3(ntiles, 1), 256, 0, ctx->stream>>>(X, d, pm, w, tl, mid, partial);
+    else bs_count_kernel<8><<<dim3(ntiles, (d + 255) / 256), 256, 0, ctx->stream>>>(X, d, pm, w, tl, mid, partial);
+  };
   // Total weight per (bin, column): every key is <= the all-ones key.
   CUDA_TRY(cudaMemsetAsync(mid, 0xff, (size_t)nd * 8, ctx->stream));
-  bs_count_kernel<<<grid, 256, 0, ctx->stream>>>(X, d, (const long long*)perm, w, tl, mid, partial);
+  count();
   bs_step_kernel<<<sgrid, 256, 0, ctx->stream>>>(partial, bt, nbins, d, -1, wtot_out, lo, hi, mid);
   ctx->launches += 2;
   // 64 bisection steps on the 64-bit key: afterwards lo == hi == key of the crossing value v*.
   for (int it = 0; it < 64; ++it) {
-    bs_count_kernel<<<grid, 256, 0, ctx->stream>>>(X, d, (const long long*)perm, w, tl, mid, partial);
+    count();
     bs_step_kernel<<<sgrid, 256, 0, ctx->stream>>>(partial, bt, nbins, d, it, wtot_out, lo, hi, mid);
     ctx->launches += 2;
   }
