@@ -206,30 +206,51 @@ __device__ __forceinline__ void upper_tile(long long task, int np, int& i, int& 
 __device__ __forceinline__ void update_tile(double* __restrict__ Gr, double* __restrict__ Gi, double* __restrict__ Vr,
                                             double* __restrict__ Vi, int ld, int nb, int round,
                                             const double* __restrict__ Jbuf, const int* __restrict__ flags,
-                                            bool is_g, int i, int j, double (*ts)[8][9], int lane) {
+                                            bool is_g, int i, int j, double (*ts)[8][9], int lane,
+                                            const int2* __restrict__ pair_tab = nullptr) {
   const bool fj = __ldcg(flags + j) != 0;
   const bool fi = is_g && __ldcg(flags + i) != 0;
   if (!fi && !fj) return;  // warp-uniform
   const int fr = lane >> 2, fk = lane & 3;
-  int jp, jq;
-  rr_pair(nb, round, j, jp, jq);
-  int ip = 0, iq = 0;
-  if (is_g) rr_pair(nb, round, i, ip, iq);
+  int jp, jq, ip = 0, iq = 0;
+  if (pair_tab) {  // blocks of every pair of this round, tabulated once per CTA (no integer divisions here)
+    jp = pair_tab[j].x;
+    jq = pair_tab[j].y;
+    if (is_g) {
+      ip = pair_tab[i].x;
+      iq = pair_tab[i].y;
+    }
+  } else {
+    rr_pair(nb, round, j, jp, jq);
+    if (is_g) rr_pair(nb, round, i, ip, iq);
+  }
   double* Mr = is_g ? Gr : Vr;
   double* Mi = is_g ? Gi : Vi;
   const int row = is_g ? pair_index(ip, iq, fr) : i * 8 + fr;
-  // ---- T = M_tile * J_j  (identity if pair j did not rotate) ----
-  double tr[2] = {0.0, 0.0}, ti[2] = {0.0, 0.0};
+  // All global loads of the task are issued up front (one L2 round trip instead of two).
   const double* Jj = Jbuf + (long long)j * 128;
+  const double* Ji_ = Jbuf + (long long)i * 128;
+  double ar[2], ai[2], br[2], bi[2], cr[2] = {0.0, 0.0}, ci[2] = {0.0, 0.0};
 #pragma unroll
   for (int ks = 0; ks < 2; ++ks) {
     const long long o = (long long)row * ld + pair_index(jp, jq, 4 * ks + fk);
-    const double ar = __ldcg(Mr + o), ai = __ldcg(Mi + o);
-    const double br = __ldcg(Jj + (4 * ks + fk) * 8 + fr), bi = __ldcg(Jj + 64 + (4 * ks + fk) * 8 + fr);
-    dmma(tr[0], tr[1], ar, br);
-    dmma(tr[0], tr[1], -ai, bi);
-    dmma(ti[0], ti[1], ar, bi);
-    dmma(ti[0], ti[1], ai, br);
+    ar[ks] = __ldcg(Mr + o);
+    ai[ks] = __ldcg(Mi + o);
+    br[ks] = __ldcg(Jj + (4 * ks + fk) * 8 + fr);
+    bi[ks] = __ldcg(Jj + 64 + (4 * ks + fk) * 8 + fr);
+    if (is_g) {  // A operand of the second product: (J_i^H)[m = fr][k] = conj(J_i[k][fr])
+      cr[ks] = __ldcg(Ji_ + (4 * ks + fk) * 8 + fr);
+      ci[ks] = __ldcg(Ji_ + 64 + (4 * ks + fk) * 8 + fr);
+    }
+  }
+  // ---- T = M_tile * J_j  (identity if pair j did not rotate) ----
+  double tr[2] = {0.0, 0.0}, ti[2] = {0.0, 0.0};
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    dmma(tr[0], tr[1], ar[ks], br[ks]);
+    dmma(tr[0], tr[1], -ai[ks], bi[ks]);
+    dmma(ti[0], ti[1], ar[ks], bi[ks]);
+    dmma(ti[0], ti[1], ai[ks], br[ks]);
   }
   double outr[2] = {tr[0], tr[1]}, outi[2] = {ti[0], ti[1]};
   if (is_g) {
@@ -242,17 +263,14 @@ __device__ __forceinline__ void update_tile(double* __restrict__ Gr, double* __r
     Ti[fr][2 * fk] = ti[0];
     Ti[fr][2 * fk + 1] = ti[1];
     __syncwarp();
-    const double* Ji_ = Jbuf + (long long)i * 128;
     outr[0] = outr[1] = outi[0] = outi[1] = 0.0;
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
-      // A operand: (J_i^H)[m = fr][k] = conj(J_i[k][fr]);  B operand: T[k][n = fr]
-      const double ar = __ldcg(Ji_ + (4 * ks + fk) * 8 + fr), ai = __ldcg(Ji_ + 64 + (4 * ks + fk) * 8 + fr);
-      const double br = Tr[4 * ks + fk][fr], bi = Ti[4 * ks + fk][fr];
-      dmma(outr[0], outr[1], ar, br);
-      dmma(outr[0], outr[1], ai, bi);
-      dmma(outi[0], outi[1], ar, bi);
-      dmma(outi[0], outi[1], -ai, br);
+      const double tbr = Tr[4 * ks + fk][fr], tbi = Ti[4 * ks + fk][fr];  // B operand: T[k][n = fr]
+      dmma(outr[0], outr[1], cr[ks], tbr);
+      dmma(outr[0], outr[1], ci[ks], tbi);
+      dmma(outi[0], outi[1], cr[ks], tbi);
+      dmma(outi[0], outi[1], -ci[ks], tbr);
     }
   }
   const int col = pair_index(jp, jq, 2 * fk);
@@ -458,6 +476,147 @@ __global__ void __launch_bounds__(JPW * 32, 1) jacobi_persistent_kernel(const Ja
     converged = act == 0;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) *a.sweeps_out = converged ? sweeps_done : -sweeps_done;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused round (default): ONE kernel per round.  The CTAs first update the 2 np priority tiles that hold next
+// round's pivot blocks and publish their completion on a counter; warp 0 of CTA p then waits for that
+// counter and solves pivot p of round g + 1, while every other warp streams through the rest of update(g).
+// The wait only ever depends on lower-numbered CTAs doing non-blocking work, so it cannot deadlock.
+// Compared with the two-kernel round this removes one 4.4 us kernel boundary and hides the pivot latency.
+//   state[0] = g (global round counter, advanced by the kernel), state[1 + (g & 3)] = priority tiles done.
+// ---------------------------------------------------------------------------------------------
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) jacobi_round_kernel(const JacobiArgs a, int* __restrict__ state) {
+  __shared__ double ts[8][2][8][9];
+  __shared__ double psm[4][8][9];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb = a.nb, np = nb / 2, R = nb - 1, ld = a.ld;
+  const int rb = nb * JB / 8;
+  const long long n_g = (long long)np * (np + 1) / 2;
+  const long long total = n_g + (long long)rb * np;
+  const int g = __ldcg(state);  // written by the previous round's kernel
+  const int r = g % R, rho = (r + 1) % R;
+  const int cur = g & 1, nxt = cur ^ 1;
+  const double* Jcur = a.Jbuf + (long long)cur * np * 128;
+  const int* fcur = a.flags + cur * np;
+  int* done = state + 1 + (g & 3);
+  if (blockIdx.x == 0 && threadIdx.x == 0) state[1 + ((g + 2) & 3)] = 0;  // recycle a counter nobody is using
+  // Round-robin tables of this round: blocks of every pair, and every block's partner in the next round.
+  __shared__ int2 pair_tab[160];
+  __shared__ int partner_tab[320];
+  for (int e = threadIdx.x; e < np; e += 256) {
+    int p, q;
+    rr_pair(nb, r, e, p, q);
+    pair_tab[e] = make_int2(p, q);
+  }
+  for (int e = threadIdx.x; e < nb; e += 256) partner_tab[e] = rr_partner(nb, rho, e);
+  __syncthreads();
+  // ---- priority tiles: all diagonal tiles + the tile joining the two blocks of each next-round pair
+  const long long wid = (long long)blockIdx.x * 8 + warp;
+  if (wid < 2 * np) {
+    int i = -1, j = -1;
+    if (wid < np) {
+      i = j = (int)wid;
+    } else {
+      int bp, bq;
+      rr_pair(nb, rho, (int)wid - np, bp, bq);
+      const int sa = rr_slot(nb, r, bp), sb = rr_slot(nb, r, bq);
+      if (sa != sb) {
+        i = sa < sb ? sa : sb;
+        j = sa < sb ? sb : sa;
+        const int xi = sa < sb ? bp : bq;
+        int ip, iq, jp, jq;
+        rr_pair(nb, r, i, ip, iq);
+        rr_pair(nb, r, j, jp, jq);
+        if (xi != ip) {
+          const int pa = rr_partner(nb, rho, ip);
+          if (pa == jp || pa == jq) i = -1;  // the other next-round pair joining these two pairs owns the tile
+        }
+      }
+    }
+    if (i >= 0) update_tile(a.Gr, a.Gi, a.Vr, a.Vi, ld, nb, r, Jcur, fcur, true, i, j, ts[warp], lane, pair_tab);
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence();
+      atomicAdd(done, 1);
+    }
+  }
+  const bool pivot_warp = warp == 0 && (int)blockIdx.x < np;
+  if (pivot_warp) {
+    // ---- pivot of round g + 1, as soon as every priority tile has landed
+    if (lane == 0) {
+      unsigned int spins = 0;
+      while (true) {
+        int v;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(done) : "memory");
+        if (v >= 2 * np) break;
+        __nanosleep(64);
+        if (++spins > (1u << 24)) __trap();
+      }
+    }
+    __syncwarp();
+    int bp, bq;
+    rr_pair(nb, rho, blockIdx.x, bp, bq);
+    const bool any = pivot_solve(a.Gr, a.Gi, ld, bp, bq, a.thr[0], a.thr[1], a.max_inner, psm,
+                                 a.Jbuf + ((long long)nxt * np + blockIdx.x) * 128, lane);
+    if (lane == 0) {
+      a.flags[nxt * np + blockIdx.x] = any ? 1 : 0;
+      if (any) atomicAdd(a.active + (g + 1) / R, 1);
+    }
+  } else {
+    // ---- the rest of update(g): the upper tiles are walked incrementally (no divisions), then V's tiles
+    const long long n_workers = (long long)gridDim.x * 8 - np;
+    const long long worker = wid - ((int)blockIdx.x < np ? blockIdx.x + 1 : np);
+    long long task = worker;
+    if (task < n_g) {
+      int i, j;
+      upper_tile(task, np, i, j);
+      int pos = j - i;
+      while (true) {
+        if (i != j) {
+          const int2 pi = pair_tab[i], pj = pair_tab[j];
+          const int pa = partner_tab[pi.x], pb = partner_tab[pi.y];
+          if (!(pa == pj.x || pa == pj.y || pb == pj.x || pb == pj.y))  // priority tiles were done above
+            update_tile(a.Gr, a.Gi, a.Vr, a.Vi, ld, nb, r, Jcur, fcur, true, i, j, ts[warp], lane, pair_tab);
+        }
+        task += n_workers;
+        if (task >= n_g) break;
+        long long adv = n_workers + pos;
+        while (adv >= np - i) {
+          adv -= np - i;
+          ++i;
+        }
+        pos = (int)adv;
+        j = i + pos;
+      }
+    }
+    {
+      long long vt = task - n_g;  // first V task of this worker
+      int i = (int)(vt / np), j = (int)(vt % np);
+      const int di = (int)(n_workers / np), dj = (int)(n_workers % np);
+      for (; vt < (long long)rb * np; vt += n_workers) {
+        update_tile(a.Gr, a.Gi, a.Vr, a.Vi, ld, nb, r, Jcur, fcur, false, i, j, ts[warp], lane, pair_tab);
+        i += di;
+        j += dj;
+        if (j >= np) {
+          j -= np;
+          ++i;
+        }
+      }
+    }
+  }
+  // Advance the round counter once the whole grid is done with state[0]: the last CTA to finish does it.
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int arrived = atomicAdd(state + 5, 1);
+    if (arrived == (int)gridDim.x - 1) {
+      state[5] = 0;
+      __threadfence();
+      state[0] = g + 1;
+    }
+  }
 }
 
 __global__ void jacobi_diag_kernel(const double* __restrict__ Gr, int ld, int m, double* __restrict__ lam) {

@@ -85,7 +85,7 @@ struct nls_ctx {
   cudaGraphExec_t jac_graph = nullptr;
   const void* jac_graph_key = nullptr;
   int jac_graph_nb = 0;
-  int jac_inner = 2;  // cyclic sweeps per 8x8 pivot solve (partial diagonalisation is enough for block Jacobi)
+  int jac_inner = 1;  // cyclic sweeps per 8x8 pivot solve (partial diagonalisation is enough for block Jacobi)
   EncodeTiledFn encode = nullptr;
   cusolverDnHandle_t solver = nullptr;
   // scratch (grow-only, zero-filled when (re)allocated)
@@ -576,7 +576,55 @@ static int heev_jacobi(nls_ctx* ctx, const double* A, int m, double scale, doubl
   // The persistent variant is correct but measured slower than the graph of short kernels on B200 (the pivot
   // chains share the FP64 pipe with the update's DMMAs): opt-in with NLS_JACOBI_PERSISTENT=1.
   const bool persistent = (pers && pers[0] == '1') && occ >= 1 && np <= coop_grid && !getenv("NLS_JACOBI_DIAG");
-  if (persistent) {
+  const char* mode_env = getenv("NLS_JACOBI_MODE");  // "fused" (default) or "split" (two kernels per round)
+  const char* occ_env = getenv("NLS_JACOBI_OCC");  // resident CTAs per SM of the fused round kernel: 4, 5 or 6
+  const int fused_occ = occ_env && atoi(occ_env) >= 4 && atoi(occ_env) <= 6 ? atoi(occ_env) : 4;
+  const int fused_grid = ctx->sm_count * fused_occ;
+  // Measured on B200: fused 58 ms vs split 70 ms at m = 1025, but 21 vs 19.5 ms at m = 513 (fewer tiles per
+  // round to hide the pivot behind), so small problems keep the two-kernel round unless forced.
+  const bool want_fused = mode_env ? strcmp(mode_env, "fused") == 0 : np >= 96;
+  const bool fused = !persistent && want_fused && np <= fused_grid && np <= 160 && !getenv("NLS_JACOBI_DIAG");
+  if (fused) {
+    // One kernel per round (priority tiles -> next pivots overlapped with the bulk update); one sweep
+    // (nb - 1 identical launches; the round number lives on the device) is replayed as a CUDA graph.
+    int* state = misc + 2;  // [0] round counter, [1..4] priority-tile counters, [5] CTA arrival counter
+    CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)(2 * np + max_sweeps + 16) * 4, ctx->stream));
+    JacobiArgs ja;
+    ja.Gr = Gr; ja.Gi = Gi; ja.Vr = Vr; ja.Vi = Vi;
+    ja.ld = mp; ja.nb = nb; ja.max_inner = ctx->jac_inner; ja.max_sweeps = max_sweeps;
+    ja.thr = thr; ja.Jbuf = Jbuf; ja.flags = flags; ja.active = active;
+    ja.barrier = nullptr; ja.sweeps_out = nullptr;
+    // J(0): pivots of the very first round.
+    jacobi_pivot_kernel<<<(np + 3) / 4, 128, 0, ctx->stream>>>(Gr, Gi, mp, nb, 0, thr, ctx->jac_inner, Jbuf, flags, active);
+    NLS_TRY(check_launch(ctx, "jacobi_pivot_kernel"));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->jac_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->jac_stream, cudaStreamNonBlocking));
+    if (!ctx->jac_graph || ctx->jac_graph_key != (const void*)Gr || ctx->jac_graph_nb != -(nb * 8 + fused_occ)) {
+      if (ctx->jac_graph) {
+        cudaGraphExecDestroy(ctx->jac_graph);
+        ctx->jac_graph = nullptr;
+      }
+      cudaGraph_t graph = nullptr;
+      CUDA_TRY(cudaStreamBeginCapture(ctx->jac_stream, cudaStreamCaptureModeRelaxed));
+      for (int round = 0; round < nb - 1; ++round) {
+        if (fused_occ == 4) jacobi_round_kernel<4><<<fused_grid, 256, 0, ctx->jac_stream>>>(ja, state);
+        else if (fused_occ == 5) jacobi_round_kernel<5><<<fused_grid, 256, 0, ctx->jac_stream>>>(ja, state);
+        else jacobi_round_kernel<6><<<fused_grid, 256, 0, ctx->jac_stream>>>(ja, state);
+      }
+      CUDA_TRY(cudaStreamEndCapture(ctx->jac_stream, &graph));
+      cudaError_t ge = cudaGraphInstantiate(&ctx->jac_graph, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ge != cudaSuccess) return fail(NLS_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ge));
+      ctx->jac_graph_key = (const void*)Gr;
+      ctx->jac_graph_nb = -(nb * 8 + fused_occ);  // negative: fused-round graph
+    }
+    for (; sweep < max_sweeps && h_active > 0; ++sweep) {
+      CUDA_TRY(cudaGraphLaunch(ctx->jac_graph, ctx->jac_stream));
+      ctx->launches += nb - 1;
+      CUDA_TRY(cudaMemcpyAsync(&h_active, active + sweep, sizeof(int), cudaMemcpyDeviceToHost, ctx->jac_stream));
+      CUDA_TRY(cudaStreamSynchronize(ctx->jac_stream));
+    }
+  } else if (persistent) {
     // One cooperative launch runs every round of every sweep (software grid barrier, pivots of round r+1
     // overlapped with the bulk of update r); the host only reads back the sweep count.
     CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)(2 * np + max_sweeps + 16) * 4, ctx->stream));
