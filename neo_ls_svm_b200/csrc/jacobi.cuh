@@ -77,6 +77,13 @@ __global__ void sumsq_kernel(const double* __restrict__ a, const double* __restr
   }
 }
 
+// thr[0] = (eps ||G||_F)^2 : squared absolute rotation threshold, thr[1] = 0 (relative test off).
+__global__ void jacobi_threshold_kernel(const double* __restrict__ fro2, double* __restrict__ thr) {
+  const double eps = 2.220446049250313e-16;
+  thr[0] = eps * eps * fro2[0];
+  thr[1] = 0.0;
+}
+
 // One warp: J = eigenvectors of the 8 x 8 pivot block G[I, I] (I = blocks bp, bq) by cyclic two-sided
 // Jacobi in shared memory (32 lanes = 8 rows x 4 disjoint rotations per inner round).
 // sm: [4][8][9] doubles (Sr, Si, Jr, Ji).  Writes J to out[2][8][8]; returns whether anything rotated.

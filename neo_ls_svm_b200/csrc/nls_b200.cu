@@ -16,6 +16,7 @@
 #include "ops.cuh"
 #include "small_kernels.cuh"
 #include "jacobi.cuh"
+#include "jacobi_wide.cuh"
 #include "binstats.cuh"
 
 using namespace nls;
@@ -530,6 +531,122 @@ static int heev_cusolver(nls_ctx* ctx, const double* A, int m, double scale, dou
 }
 
 
+// Common tail of the Jacobi drivers: eigenvalues = diag(G), ascending order (stable), Q = V[:, perm].
+static int jacobi_finish(nls_ctx* ctx, const double* Gr, const double* Vr, const double* Vi, int mp, int m,
+                         double* lam_raw, int* perm, double* lam_out, double* Q_out) {
+  jacobi_diag_kernel<<<(mp + 255) / 256, 256, 0, ctx->stream>>>(Gr, mp, mp, lam_raw);
+  NLS_TRY(check_launch(ctx, "jacobi_diag_kernel"));
+  std::vector<double> h_lam(mp);
+  CUDA_TRY(cudaMemcpyAsync(h_lam.data(), lam_raw, (size_t)mp * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  std::vector<int> h_perm(m);
+  for (int k = 0; k < m; ++k) h_perm[k] = k;  // pad columns (index >= m) never rotate and are dropped
+  std::stable_sort(h_perm.begin(), h_perm.end(), [&](int a, int b) { return h_lam[a] < h_lam[b]; });
+  CUDA_TRY(cudaMemcpyAsync(perm, h_perm.data(), (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
+  jacobi_gather_kernel<<<grid_for((long long)m * m), 256, 0, ctx->stream>>>(Vr, Vi, mp, m, perm, lam_raw, Q_out, lam_out);
+  NLS_TRY(check_launch(ctx, "jacobi_gather_kernel"));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // h_perm must outlive the copy
+  return NLS_OK;
+}
+
+// Wide-block driver (csrc/jacobi_wide.cuh): 8-wide blocks, ping-pong G, one dependency-free kernel per round; one
+// sweep (nb - 1 launches + an off-diagonal census) is replayed as a CUDA graph, and the host reads the rotation
+// counter and the census after each sweep, so the iteration stops without a final no-op sweep.
+template <int JBW>
+static int heev_jacobi_wide(nls_ctx* ctx, const double* A, int m, double scale, double* lam_out, double* Q_out) {
+  using C = WideCfg<JBW>;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  int nb = (m + JBW - 1) / JBW;
+  if (nb & 1) ++nb;
+  if (nb < 2) nb = 2;
+  const int mp = nb * JBW, np = nb / 2;
+  const size_t mm = (size_t)mp * mp;
+  const int max_sweeps = 60;
+  NLS_TRY(ensure(ctx, ctx->jac_mat, 6 * mm * 8));
+  NLS_TRY(ensure(ctx, ctx->jac_small, (size_t)4 * np * C::JSZ * 8 + (size_t)(2 * mp + 8) * 8 +
+                                          (size_t)(2 * np + max_sweeps + 16 + mp) * 4));
+  double* base = (double*)ctx->jac_mat.p;
+  double* Vr = base + 4 * mm;
+  double* Vi = base + 5 * mm;
+  double* Jbuf = (double*)ctx->jac_small.p;        // [2][np][JSZ]
+  double* Sbuf = Jbuf + (size_t)2 * np * C::JSZ;   // [2][np][JSZ]
+  double* lam_raw = Sbuf + (size_t)2 * np * C::JSZ;
+  double* fro2 = lam_raw + mp;
+  double* thr = fro2 + 2;
+  int* flags = (int*)(fro2 + 8);        // [2][np]
+  int* active = flags + 2 * np;         // [max_sweeps + 2]
+  int* misc = active + max_sweeps + 2;  // [0] off-diagonal census, [2] sweeps completed
+  int* perm = misc + 8;
+  WideArgs wa;
+  for (int b = 0; b < 2; ++b)
+    for (int c = 0; c < 2; ++c) wa.G[b][c] = base + (size_t)(2 * b + c) * mm;
+  wa.Vr = Vr; wa.Vi = Vi;
+  wa.ld = mp; wa.nb = nb; wa.max_inner = ctx->jac_inner;
+  wa.thr = thr; wa.Jbuf = Jbuf; wa.Sbuf = Sbuf; wa.flags = flags; wa.active = active; wa.state = misc + 2;
+  ProfScope scope(ctx, NLS_PROF_OTHER);
+  jacobi_init_kernel<<<grid_for((long long)mm), 256, 0, ctx->stream>>>(A, m, mp, scale, wa.G[0][0], wa.G[0][1], Vr, Vi);
+  NLS_TRY(check_launch(ctx, "jacobi_init_kernel"));
+  sumsq_kernel<<<1, 1024, 0, ctx->stream>>>(wa.G[0][0], wa.G[0][1], (long long)mm, fro2);
+  NLS_TRY(check_launch(ctx, "sumsq_kernel"));
+  jacobi_threshold_kernel<<<1, 1, 0, ctx->stream>>>(fro2, thr);
+  CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)(2 * np + max_sweeps + 16) * 4, ctx->stream));
+  const size_t piv_smem = (size_t)4 * C::PIV_SM * 8, round_smem = (size_t)wide_smem_doubles<JBW>() * 8;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(jacobi_pivot0_w_kernel<JBW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)piv_smem));
+    CUDA_TRY(cudaFuncSetAttribute(jacobi_round_w_kernel<JBW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)round_smem));
+    attr_done = true;
+  }
+  // Two 8-warp CTAs per SM; warp 0 of the first np CTAs solves a pivot, every other warp updates tiles.
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jacobi_round_w_kernel<JBW>, WIDE_WARPS * 32, round_smem));
+  if (occ < 1) return fail(NLS_ERR_CUDA, "jacobi_round_w_kernel does not fit on an SM");
+  const long long tasks = (long long)np * (np + 1) / 2 + (long long)(mp / C::P) * np;
+  const int grid = (int)std::max<long long>(np, std::min<long long>((long long)ctx->sm_count * occ, (tasks + np + WIDE_WARPS - 1) / WIDE_WARPS));
+  if (np > 160) return fail(NLS_ERR_INVALID, "wide Jacobi: m = %d is outside the supported range", m);
+  // J(0), S(0): pivots of the very first round.
+  jacobi_pivot0_w_kernel<JBW><<<(np + 3) / 4, 128, piv_smem, ctx->stream>>>(wa);
+  NLS_TRY(check_launch(ctx, "jacobi_pivot0_w_kernel"));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (!ctx->jac_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->jac_stream, cudaStreamNonBlocking));
+  // Timing experiments only (results are then meaningless): bit 0 skips the pivot solves, bit 1 the tile updates.
+  const char* diag_env = getenv("NLS_JACOBI_DIAG");
+  const int diag = diag_env ? atoi(diag_env) & 3 : 0;
+  const int graph_code = -(1 << 24) - ((nb * 64 + JBW * 4) * 4 + diag);
+  if (!ctx->jac_graph || ctx->jac_graph_key != (const void*)base || ctx->jac_graph_nb != graph_code) {
+    if (ctx->jac_graph) {
+      cudaGraphExecDestroy(ctx->jac_graph);
+      ctx->jac_graph = nullptr;
+    }
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(ctx->jac_stream, cudaStreamCaptureModeRelaxed));
+    for (int round = 0; round < nb - 1; ++round)
+      jacobi_round_w_kernel<JBW><<<grid, WIDE_WARPS * 32, round_smem, ctx->jac_stream>>>(wa, round, diag);
+    cudaMemsetAsync(misc, 0, sizeof(int), ctx->jac_stream);
+    jacobi_offdiag_count_w_kernel<<<grid_for((long long)mm), 256, 0, ctx->jac_stream>>>(wa, mp, misc);
+    jacobi_sweep_done_w_kernel<<<1, 1, 0, ctx->jac_stream>>>(wa.state);
+    CUDA_TRY(cudaStreamEndCapture(ctx->jac_stream, &graph));
+    cudaError_t ge = cudaGraphInstantiate(&ctx->jac_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ge != cudaSuccess) return fail(NLS_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ge));
+    ctx->jac_graph_key = (const void*)base;
+    ctx->jac_graph_nb = graph_code;
+  }
+  int sweep = 0, h_active = 1, h_misc[4] = {1, 0, 0, 0};
+  for (; sweep < (diag ? 10 : max_sweeps) && (diag || (h_active > 0 && h_misc[0] > 0)); ++sweep) {
+    CUDA_TRY(cudaGraphLaunch(ctx->jac_graph, ctx->jac_stream));
+    ctx->launches += nb;
+    CUDA_TRY(cudaMemcpyAsync(&h_active, active + sweep, sizeof(int), cudaMemcpyDeviceToHost, ctx->jac_stream));
+    CUDA_TRY(cudaMemcpyAsync(h_misc, misc, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->jac_stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->jac_stream));
+  }
+  ctx->eig_sweeps = sweep;
+  if (h_active > 0 && h_misc[0] > 0 && !diag)
+    return fail(NLS_ERR_SOLVER, "Jacobi eigensolver did not converge in %d sweeps", max_sweeps);
+  const double* Gfinal = wa.G[(sweep * (nb - 1)) & 1][0];  // the buffer the last round wrote
+  return jacobi_finish(ctx, Gfinal, Vr, Vi, mp, m, lam_raw, perm, lam_out, Q_out);
+}
+
 // Hand-written parallel two-sided block Jacobi (csrc/jacobi.cuh).
 static int heev_jacobi(nls_ctx* ctx, const double* A, int m, double scale, double* lam_out, double* Q_out) {
   if (!ctx || !A || !lam_out || !Q_out || m < 1) return fail(NLS_ERR_INVALID, "bad argument to nls_heev");
@@ -698,19 +815,7 @@ static int heev_jacobi(nls_ctx* ctx, const double* A, int m, double scale, doubl
   ctx->eig_sweeps = sweep;
   if (h_active > 0 && !getenv("NLS_JACOBI_DIAG"))
     return fail(NLS_ERR_SOLVER, "Jacobi eigensolver did not converge in %d sweeps", max_sweeps);
-  jacobi_diag_kernel<<<(mp + 255) / 256, 256, 0, ctx->stream>>>(Gr, mp, mp, lam_raw);
-  NLS_TRY(check_launch(ctx, "jacobi_diag_kernel"));
-  std::vector<double> h_lam(mp);
-  CUDA_TRY(cudaMemcpyAsync(h_lam.data(), lam_raw, (size_t)mp * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  std::vector<int> h_perm(m);
-  for (int k = 0; k < m; ++k) h_perm[k] = k;  // pad columns (index >= m) never rotate and are dropped
-  std::stable_sort(h_perm.begin(), h_perm.end(), [&](int a, int b) { return h_lam[a] < h_lam[b]; });
-  CUDA_TRY(cudaMemcpyAsync(perm, h_perm.data(), (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
-  jacobi_gather_kernel<<<grid_for((long long)m * m), 256, 0, ctx->stream>>>(Vr, Vi, mp, m, perm, lam_raw, Q_out, lam_out);
-  NLS_TRY(check_launch(ctx, "jacobi_gather_kernel"));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // h_perm must outlive the copy
-  return NLS_OK;
+  return jacobi_finish(ctx, Gr, Vr, Vi, mp, m, lam_raw, perm, lam_out, Q_out);
 }
 
 extern "C" int nls_heev(nls_ctx* ctx, const double* A, int m, double scale, double* lam_out, double* Q_out) {
@@ -719,7 +824,13 @@ extern "C" int nls_heev(nls_ctx* ctx, const double* A, int m, double scale, doub
   // that its O(sweeps m^3) work is >10x slower than cuSOLVER's tridiagonal solver, which takes over.
   const bool jacobi = ctx->eig_kind == 0 || (ctx->eig_kind == 2 && m <= 1100);
   ctx->eig_sweeps = 0;
-  return jacobi ? heev_jacobi(ctx, A, m, scale, lam_out, Q_out) : heev_cusolver(ctx, A, m, scale, lam_out, Q_out);
+  if (!jacobi) return heev_cusolver(ctx, A, m, scale, lam_out, Q_out);
+  if (!A || !lam_out || !Q_out || m < 1) return fail(NLS_ERR_INVALID, "bad argument to nls_heev");
+  // Block width: 8 (16 x 16 pivots, default) or the original 4 (8 x 8 pivots; NLS_JACOBI_JB=4, all its variants).
+  const char* jb_env = getenv("NLS_JACOBI_JB");
+  const int jb = jb_env ? atoi(jb_env) : 8;
+  if (jb == 8 && m <= 2552) return heev_jacobi_wide<8>(ctx, A, m, scale, lam_out, Q_out);
+  return heev_jacobi(ctx, A, m, scale, lam_out, Q_out);
 }
 
 extern "C" int nls_ctx_set_eigensolver(nls_ctx* ctx, int kind) {
