@@ -239,7 +239,7 @@ template <int JBW>
 __global__ void __launch_bounds__(128) jacobi_pivot0_w_kernel(const WideArgs a) {
   using C = WideCfg<JBW>;
   constexpr int P = C::P, SP = C::SP;
-  extern __shared__ double dyn_sm[];
+  extern __shared__ __align__(16) double dyn_sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = blockIdx.x * 4 + warp, np = a.nb / 2;
   if (pair >= np) return;
@@ -261,19 +261,71 @@ __global__ void __launch_bounds__(128) jacobi_pivot0_w_kernel(const WideArgs a) 
   }
 }
 
-// One warp: dst tile (i, j) = J_i^H src[I_i, I_j] J_j, plus its conjugate-transposed mirror (is_g; i < j), or, in
-// place, P-row block i of V <- V J_j (!is_g): complex P x P x P products as (P/8)^2 DMMA.8x8x4 sub-tiles.  A G
-// tile whose pairs did not rotate is copied; a V tile is skipped.  ts: WideCfg::TS_WARP doubles of scratch.
+// A unit of tile work of a round: upper tile (i, j) of G (is_g) or P-row block i x pair j of V.
+struct TileTask {
+  bool valid, is_g;
+  int i, j;
+};
+
+__device__ __forceinline__ TileTask decode_tile_task(long long t, long long n_g, long long total, int np) {
+  TileTask k;
+  k.valid = t < total;
+  k.is_g = t < n_g;
+  k.i = k.j = 0;
+  if (!k.valid) return k;
+  if (k.is_g) {
+    upper_tile(t, np, k.i, k.j);
+  } else {
+    k.i = (int)((t - n_g) / np);
+    k.j = (int)((t - n_g) % np);
+  }
+  return k;
+}
+
+// Does the task read its source tile?  (Diagonal G tiles come from Sbuf; V tiles of a pair that did not rotate do
+// not change.)
+__device__ __forceinline__ bool tile_task_loads(const TileTask& k, const int* __restrict__ sflags) {
+  return k.valid && (k.is_g ? k.i != k.j : sflags[k.j] != 0);
+}
+
+// One warp: start the asynchronous copy (cp.async, 16 B granules, L2 only) of the task's P x P source tile into a
+// staging buffer [2][P][TP] (Re plane, Im plane).  One commit group per call, even when nothing is copied.
 template <int JBW>
-__device__ __forceinline__ void update_tile_w(const double* Sr_, const double* Si_, double* Dr, double* Di, int ld,
-                                              const double* __restrict__ Jbuf, const int* __restrict__ flags, bool is_g,
-                                              int i, int j, double* __restrict__ ts, int lane,
-                                              const int2* __restrict__ pair_tab) {
+__device__ __forceinline__ void stage_tile_w(const TileTask& k, const double* Sr_, const double* Si_, int ld,
+                                             const int2* __restrict__ pair_tab, const int* __restrict__ sflags,
+                                             double* __restrict__ buf, int lane) {
+  using C = WideCfg<JBW>;
+  constexpr int P = C::P, TP = C::TP, GPR = P / 2;  // granules (2 doubles) per tile row
+  if (tile_task_loads(k, sflags)) {
+    const int2 pj = pair_tab[k.j];
+    const int2 pi = k.is_g ? pair_tab[k.i] : make_int2(0, 0);
+#pragma unroll
+    for (int e = lane; e < P * GPR; e += 32) {
+      const int row = e / GPR, gq = e % GPR;
+      const int grow = k.is_g ? pair_index_w<JBW>(pi.x, pi.y, row) : k.i * P + row;
+      const long long o = (long long)grow * ld + pair_index_w<JBW>(pj.x, pj.y, 2 * gq);
+      const uint32_t d = smem_u32(buf + row * TP + 2 * gq);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(Sr_ + o) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + P * TP * 8), "l"(Si_ + o) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// One warp: dst tile (i, j) = J_i^H M J_j, plus its conjugate-transposed mirror (is_g; i < j), or P-row block i of
+// V <- V J_j (!is_g), where the source tile M has been staged in `buf` ([2][P][TP]): complex P x P x P products as
+// (P/8)^2 DMMA.8x8x4 sub-tiles.  A G tile whose pairs did not rotate is copied.  `buf` doubles as the scratch that
+// turns the first product into a B operand once the tile is in registers.
+template <int JBW>
+__device__ __forceinline__ void update_tile_w(double* Dr, double* Di, int ld, const double* __restrict__ Jbuf,
+                                              const int* __restrict__ sflags, const TileTask& k,
+                                              double* __restrict__ buf, int lane, const int2* __restrict__ pair_tab) {
   using C = WideCfg<JBW>;
   constexpr int P = C::P, NS = C::NS, KS = C::KS, TP = C::TP;
-  const bool fj = __ldcg(flags + j) != 0;
-  const bool fi = is_g && __ldcg(flags + i) != 0;
-  if (!is_g && !fj) return;  // warp-uniform
+  const bool is_g = k.is_g;
+  const int i = k.i, j = k.j;
+  const bool fj = sflags[j] != 0;
+  const bool fi = is_g && sflags[i] != 0;
   const int fr = lane >> 2, fk = lane & 3;
   const int2 pj = pair_tab[j];
   const int2 pi = is_g ? pair_tab[i] : make_int2(0, 0);
@@ -282,15 +334,12 @@ __device__ __forceinline__ void update_tile_w(const double* Sr_, const double* S
   for (int rs = 0; rs < NS; ++rs) rowi[rs] = is_g ? pair_index_w<JBW>(pi.x, pi.y, rs * 8 + fr) : i * P + rs * 8 + fr;
   double ar[NS][KS], ai[NS][KS];
 #pragma unroll
-  for (int ks = 0; ks < KS; ++ks) {
-    const int col = pair_index_w<JBW>(pj.x, pj.y, 4 * ks + fk);
+  for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
     for (int rs = 0; rs < NS; ++rs) {
-      const long long o = (long long)rowi[rs] * ld + col;
-      ar[rs][ks] = Sr_[o];
-      ai[rs][ks] = Si_[o];
+      ar[rs][ks] = buf[(rs * 8 + fr) * TP + 4 * ks + fk];
+      ai[rs][ks] = buf[P * TP + (rs * 8 + fr) * TP + 4 * ks + fk];
     }
-  }
   if (!fi && !fj) {  // nothing rotated: carry the tile (and its mirror) over to the other buffer
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
@@ -330,9 +379,9 @@ __device__ __forceinline__ void update_tile_w(const double* Sr_, const double* S
   }
   if (is_g) {
     // ---- out = J_i^H * T : T goes through shared memory to become a B operand ----
-    double* Tr = ts;
-    double* Ti = ts + P * TP;
-    __syncwarp();
+    double* Tr = buf;
+    double* Ti = buf + P * TP;
+    __syncwarp();  // every lane holds its part of M in registers: the staging buffer is free
 #pragma unroll
     for (int rs = 0; rs < NS; ++rs)
 #pragma unroll
@@ -505,11 +554,14 @@ __device__ __forceinline__ void next_pivot_w(const WideArgs& a, const double* __
 // Layouts that keep the pivot warps away from the tile updates' DMMAs (dedicated pivot CTAs at 8 pivots per SM,
 // or 16-warp CTAs with the pivot's SM sub-partition otherwise idle) were measured and were not faster at
 // m = 1025: what the pivot chain gains, the tile updates lose in workers (profiles/r1_jacobi_wide_layouts.log).
-// Dynamic shared memory: 8 warps x TS_WARP + PIV_SM doubles.
+// Every tile-update warp runs a two-stage pipeline over its tasks: the source tile of task t + 1 is on its way into
+// shared memory (cp.async) while task t is in the DMMA pipe (ncu before this: long-scoreboard stalls 8.4 warps per
+// issue against 3.8 for the math pipe, DMMA pipe 42 % active).
+// Dynamic shared memory: 8 warps x 2 staging buffers (TS_WARP doubles each) + PIV_SM doubles.
 constexpr int WIDE_WARPS = 8;
 template <int JBW>
 constexpr int wide_smem_doubles() {
-  return WIDE_WARPS * WideCfg<JBW>::TS_WARP + WideCfg<JBW>::PIV_SM;
+  return WIDE_WARPS * 2 * WideCfg<JBW>::TS_WARP + WideCfg<JBW>::PIV_SM;
 }
 
 template <int JBW>
@@ -517,7 +569,7 @@ __global__ void __launch_bounds__(WIDE_WARPS * 32, 2) jacobi_round_w_kernel(cons
                                                                             const int diag) {
   using C = WideCfg<JBW>;
   constexpr int P = C::P;
-  extern __shared__ double dyn_sm[];
+  extern __shared__ __align__(16) double dyn_sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb = a.nb, np = nb / 2, R = nb - 1, ld = a.ld;
   const int rb = nb * JBW / P;  // P-row blocks of V
@@ -530,56 +582,46 @@ __global__ void __launch_bounds__(WIDE_WARPS * 32, 2) jacobi_round_w_kernel(cons
   const double *Sr_ = cur ? a.G[1][0] : a.G[0][0], *Si_ = cur ? a.G[1][1] : a.G[0][1];
   double *Dr = cur ? a.G[0][0] : a.G[1][0], *Di = cur ? a.G[0][1] : a.G[1][1];
   __shared__ int2 pair_tab[160];
+  __shared__ int sflags[160];
   for (int e = threadIdx.x; e < np; e += WIDE_WARPS * 32) {
     int p, q;
     rr_pair(nb, r, e, p, q);
     pair_tab[e] = make_int2(p, q);
+    sflags[e] = __ldcg(fcur + e);
   }
   __syncthreads();
-  double* ts = dyn_sm + warp * C::TS_WARP;
+  double* stage = dyn_sm + warp * 2 * C::TS_WARP;
   const bool pivot_cta = (int)blockIdx.x < np;
   if (pivot_cta && warp == 0) {
     if (!(diag & 1))
-      next_pivot_w<JBW>(a, Sr_, Si_, r, rho, blockIdx.x, cur, (g + 1) / R, ts, dyn_sm + WIDE_WARPS * C::TS_WARP, lane);
+      next_pivot_w<JBW>(a, Sr_, Si_, r, rho, blockIdx.x, cur, (g + 1) / R, stage, dyn_sm + WIDE_WARPS * 2 * C::TS_WARP,
+                        lane);
     return;
   }
   if (diag & 2) return;
   const long long n_workers = (long long)gridDim.x * WIDE_WARPS - np;
-  long long task = (long long)blockIdx.x * WIDE_WARPS + warp - (pivot_cta ? blockIdx.x + 1 : np);
-  if (task < n_g) {
-    int i, j;
-    upper_tile(task, np, i, j);
-    int pos = j - i;
-    while (true) {
-      if (i != j)
-        update_tile_w<JBW>(Sr_, Si_, Dr, Di, ld, Jcur, fcur, true, i, j, ts, lane, pair_tab);
-      else
-        copy_diag_tile_w<JBW>(a.Sbuf + ((long long)cur * np + i) * C::JSZ, Dr, Di, ld, pair_tab[i], lane);
-      task += n_workers;
-      if (task >= n_g) break;
-      long long adv = n_workers + pos;
-      while (adv >= np - i) {
-        adv -= np - i;
-        ++i;
-      }
-      pos = (int)adv;
-      j = i + pos;
-    }
+  const long long total = n_g + (long long)rb * np;
+  long long t = (long long)blockIdx.x * WIDE_WARPS + warp - (pivot_cta ? blockIdx.x + 1 : np);
+  TileTask k = decode_tile_task(t, n_g, total, np);
+  int b = 0;
+  stage_tile_w<JBW>(k, k.is_g ? Sr_ : a.Vr, k.is_g ? Si_ : a.Vi, ld, pair_tab, sflags, stage, lane);
+  while (k.valid) {
+    const TileTask kn = decode_tile_task(t + n_workers, n_g, total, np);
+    stage_tile_w<JBW>(kn, kn.is_g ? Sr_ : a.Vr, kn.is_g ? Si_ : a.Vi, ld, pair_tab, sflags,
+                      stage + (b ^ 1) * C::TS_WARP, lane);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // the tile of task k has landed (per thread) ...
+    __syncwarp();                                          // ... for every lane of the warp
+    if (k.is_g && k.i == k.j)
+      copy_diag_tile_w<JBW>(a.Sbuf + ((long long)cur * np + k.i) * C::JSZ, Dr, Di, ld, pair_tab[k.i], lane);
+    else if (tile_task_loads(k, sflags))
+      update_tile_w<JBW>(k.is_g ? Dr : a.Vr, k.is_g ? Di : a.Vi, ld, Jcur, sflags, k, stage + b * C::TS_WARP, lane,
+                         pair_tab);
+    __syncwarp();  // the buffer of task k is refilled two iterations from now, by the next call of stage_tile_w
+    k = kn;
+    t += n_workers;
+    b ^= 1;
   }
-  {
-    long long vt = task - n_g;  // first V task of this worker
-    int i = (int)(vt / np), j = (int)(vt % np);
-    const int di = (int)(n_workers / np), dj = (int)(n_workers % np);
-    for (; vt < (long long)rb * np; vt += n_workers) {
-      update_tile_w<JBW>(a.Vr, a.Vi, a.Vr, a.Vi, ld, Jcur, fcur, false, i, j, ts, lane, pair_tab);
-      i += di;
-      j += dj;
-      if (j >= np) {
-        j -= np;
-        ++i;
-      }
-    }
-  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // Number of off-diagonal entries of the current G still above the rotation threshold: zero means that a further
