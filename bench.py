@@ -14,7 +14,8 @@ affine pre-pass that produces W is host code outside the hot path (SURVEY.md §8
 on the first 100k rows before timing.
 
 * `value`  : rows/s with X, y, s resident in HBM when the timed region starts.
-* `e2e`    : rows/s with HOST (pinned) X, y, s copied H2D and all results copied D2H inside every step.
+* `e2e`    : rows/s with HOST (pinned) X, y, s copied H2D and all results copied D2H inside every step; the upload
+  goes through `nls_primal_gram_h2d`, which streams row groups on a copy stream underneath the Gram pass.
 * `roofline`: FP64 tensor (DMMA) roofline of the dominant kernel (the eigenbasis projection T = φQ),
   timed with CUDA events around each launch; peak = DMMA register-loop peak measured in the same run.
 * `cpu_baseline`: the CPU oracle port of the reference algorithm on a bounded row sample, host cores.
@@ -227,11 +228,16 @@ def run_ours(args) -> None:
     # ---- end-to-end arm: host buffers in, host results out, every step ---------------------------
     out_host = {}
 
+    rows_host = torch.empty((5, r1 - r0), dtype=torch.float64).pin_memory()
+
     def e2e_step():
-        Xs, ys, ss = Xh.to(dev, non_blocking=True), yh.to(dev, non_blocking=True), sh.to(dev, non_blocking=True)
-        f = solve(Xs, ys, ss)
+        # Host rows in through the C ABI (nls_primal_gram_h2d uploads them underneath the Gram pass), every per-row
+        # result and β̂ back out to host memory.
+        f = _primal.primal_fit(None, None, None, shd, Wd, classifier=False, n_global=n, ctx=ctx, host_rows=(Xh, yh, sh))
+        rows_host.copy_(f.rows["_stacked"], non_blocking=True)
         out_host["beta"] = f.beta.cpu()
-        out_host["rows"] = torch.stack([f.rows[k] for k in ("loo_residuals", "yhat_loo", "loo_leverage", "residuals", "loo_std")]).cpu()
+        torch.cuda.synchronize()
+        out_host["rows"] = rows_host
 
     del Xd, yd, sd
     torch.cuda.empty_cache()

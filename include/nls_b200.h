@@ -78,6 +78,15 @@ int nls_affine_map(nls_ctx* ctx, const double* X, int64_t n, int d, const double
 int nls_primal_gram(nls_ctx* ctx, const double* X, const double* y, const double* s, int64_t n,
                     int d, const double* shift, const double* W, int D, double* A_out,
                     double* b_out);
+/* The same with the training rows still on the HOST (the reference's fit receives host ndarrays,
+ * _neo_ls_svm.py:327-335): X_host (n x d), y_host, s_host are copied into the caller's device buffers
+ * X_dev / y_dev / s_dev in row groups on a copy stream while the Gram of the groups that have already
+ * arrived is computed, so the upload costs no time; the device copies stay valid for stages 4a-4c.
+ * Page-locked host buffers give a truly asynchronous copy; pageable ones are staged by the driver. */
+int nls_primal_gram_h2d(nls_ctx* ctx, const double* X_host, const double* y_host,
+                        const double* s_host, int64_t n, int d, double* X_dev, double* y_dev,
+                        double* s_dev, const double* shift, const double* W, int D, double* A_out,
+                        double* b_out);
 
 /* ---------------------------------------------------------------------------------------------
  * Stage 3 — Hermitian eigendecomposition.  Replaces scipy.linalg.eigh at _neo_ls_svm.py:120:

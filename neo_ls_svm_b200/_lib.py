@@ -39,6 +39,7 @@ def _signatures(lib: C.CDLL) -> None:
         "nls_feature_map": ([p, p, i64, i, p, p, i, p], i),
         "nls_affine_map": ([p, p, i64, i, p, p, i, p], i),
         "nls_primal_gram": ([p, p, p, p, i64, i, p, p, i, p, p], i),
+        "nls_primal_gram_h2d": ([p, p, p, p, i64, i, p, p, p, p, p, i, p, p], i),
         "nls_heev": ([p, p, i, d, p, p], i),
         "nls_ctx_set_eigensolver": ([p, i], i),
         "nls_ctx_last_eig_sweeps": ([p], i),
@@ -186,6 +187,26 @@ class Context:
         check(self.lib.nls_primal_gram(self.handle, ptr(X), ptr(y), ptr(s), n, d, ptr(shift), ptr(W), D, ptr(A), ptr(b)))
         return A, b
 
+    def primal_gram_h2d(self, Xh, yh, sh, shift, W):
+        """Stage 1+2 from HOST tensors (contiguous float64 CPU tensors, ideally pinned): the rows are uploaded in
+        groups on a copy stream underneath the Gram pass.  Returns (A, b, X, y, s) with the device copies."""
+        import torch
+
+        n, d = Xh.shape
+        D = W.shape[1]
+        m = D + 1
+        dev = W.device
+        for t in (Xh, yh, sh):
+            assert t.device.type == "cpu" and t.dtype == torch.float64 and t.is_contiguous()
+        X = torch.empty((n, d), dtype=torch.float64, device=dev)
+        y = torch.empty((n,), dtype=torch.float64, device=dev)
+        s = torch.empty((n,), dtype=torch.float64, device=dev)
+        A = torch.empty((m, m), dtype=torch.complex128, device=dev)
+        b = torch.empty((m,), dtype=torch.complex128, device=dev)
+        check(self.lib.nls_primal_gram_h2d(self.handle, Xh.data_ptr(), yh.data_ptr(), sh.data_ptr(), n, d, ptr(X), ptr(y), ptr(s),
+                                           ptr(shift), ptr(W), D, ptr(A), ptr(b)))
+        return A, b, X, y, s
+
     def heev(self, A, scale: float):
         import torch
 
@@ -244,7 +265,7 @@ class Context:
             float(gamma), ptr(beta_eig), ptr(beta), int(classifier), ptr(sigma2),
             ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(out[3]), ptr(out[4])))
         return {"loo_residuals": out[0], "yhat_loo": out[1], "loo_leverage": out[2], "residuals": out[3],
-                "loo_std": out[4]}
+                "loo_std": out[4], "_stacked": out}
 
     def primal_predict(self, X, shift, W, beta=None, B=None, w=None, want_std: bool = False, b_upper: bool = False):
         import torch

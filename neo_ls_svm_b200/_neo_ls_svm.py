@@ -131,7 +131,8 @@ class NeoLSSVM(BaseEstimator):
         cdt = np.complex64 if dt == np.float32 else np.complex128
         self.γs_ = fit.gammas.astype(dt)
         self.loo_errors_γs_ = fit.loo_errors.astype(dt)
-        rows = {k: v.cpu().numpy() for k, v in fit.rows.items()}
+        stacked = fit.rows["_stacked"].cpu().numpy()  # one device -> host copy for the five per-row vectors
+        rows = dict(zip(("loo_residuals", "yhat_loo", "loo_leverage", "residuals", "loo_std"), stacked))
         self.loo_residuals_ = rows["loo_residuals"].astype(dt)
         self.loo_ŷ_ = (np.asarray(y, dtype=np.float64) + rows["loo_residuals"]).astype(dt)
         self.loo_leverage_ = rows["loo_leverage"].astype(dt)

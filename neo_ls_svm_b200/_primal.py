@@ -77,6 +77,7 @@ def primal_fit(
     ctx: _lib.Context | None = None,
     time_stages: bool = False,
     stash: bool | str = "auto",
+    host_rows: tuple | None = None,
 ) -> PrimalFit:
     """Run stages 1–4 for the local row shard.
 
@@ -86,9 +87,13 @@ def primal_fit(
     `stash`: keep σ²ᵢ(γ_g) for every local row and γ (n×G doubles, 8 KB/row) while sweeping, so that the
     per-row outputs at the selected γ are a column gather instead of a second n·m² projection pass.
     "auto" enables it when the buffer fits in 60% of the free HBM.
+
+    `host_rows=(Xh, yh, sh)`: the rows are still on the host (contiguous float64 CPU tensors, ideally pinned); pass
+    X = y = s = None.  They are uploaded underneath the Gram pass (`nls_primal_gram_h2d`) and the device copies
+    serve the later passes.
     """
-    ctx = ctx or _lib.context(X.device.index)
-    n, d = X.shape
+    ctx = ctx or _lib.context((X if X is not None else W).device.index)
+    n, d = (X if X is not None else host_rows[0]).shape
     D = W.shape[1]
     m = D + 1
     n_global = int(n_global if n_global is not None else n)
@@ -102,7 +107,10 @@ def primal_fit(
             ev.append((name, e))
 
     mark("start")
-    A, b = ctx.primal_gram(X, y, s, shift, W)  # stage 1+2
+    if host_rows is not None:
+        A, b, X, y, s = ctx.primal_gram_h2d(*host_rows, shift, W)  # upload + stage 1+2
+    else:
+        A, b = ctx.primal_gram(X, y, s, shift, W)  # stage 1+2
     _all_reduce(A)
     _all_reduce(b)
     mark("gram")

@@ -87,6 +87,8 @@ struct nls_ctx {
   const void* jac_graph_key = nullptr;
   int jac_graph_nb = 0;
   int jac_inner = 1;  // cyclic sweeps per 8x8 pivot solve (partial diagonalisation is enough for block Jacobi)
+  cudaStream_t copy_stream = nullptr;        // host -> device row groups of nls_primal_gram_h2d
+  std::vector<cudaEvent_t> copy_events;      // one per row group, reused
   EncodeTiledFn encode = nullptr;
   cusolverDnHandle_t solver = nullptr;
   // scratch (grow-only, zero-filled when (re)allocated)
@@ -353,6 +355,8 @@ extern "C" int nls_ctx_destroy(nls_ctx* ctx) {
   if (ctx->solver) cusolverDnDestroy(ctx->solver);
   if (ctx->jac_graph) cudaGraphExecDestroy(ctx->jac_graph);
   if (ctx->jac_stream) cudaStreamDestroy(ctx->jac_stream);
+  for (cudaEvent_t e : ctx->copy_events) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
   return NLS_OK;
 }
@@ -456,10 +460,40 @@ extern "C" int nls_affine_map(nls_ctx* ctx, const double* X, int64_t n, int d, c
 // ---------------------------------------------------------------------------------------------
 // Stage 2
 // ---------------------------------------------------------------------------------------------
-extern "C" int nls_primal_gram(nls_ctx* ctx, const double* X, const double* y, const double* s, int64_t n, int d,
-                               const double* shift, const double* W, int D, double* A_out, double* b_out) {
+// Host rows streamed into the device buffers while the Gram pass runs (nls_primal_gram_h2d).
+struct UploadPlan {
+  const double *Xh, *yh, *sh;
+  double *Xd, *yd, *sd;
+  int64_t group_rows;
+};
+
+static int gram_impl(nls_ctx* ctx, const double* X, const double* y, const double* s, int64_t n, int d,
+                     const double* shift, const double* W, int D, double* A_out, double* b_out,
+                     const UploadPlan* up) {
   NLS_TRY(check_map_args(ctx, X, n, d, shift, W, D));
   if (!y || !s || !A_out || !b_out) return fail(NLS_ERR_INVALID, "null pointer");
+  if (up) {
+    // Enqueue every row group on the copy stream now (the copy engine works through them in order) with one
+    // event per group; the compute stream waits for a group's event right before its first chunk.
+    if (!ctx->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    const int64_t groups = (n + up->group_rows - 1) / up->group_rows;
+    while ((int64_t)ctx->copy_events.size() < groups) {
+      cudaEvent_t e;
+      CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ctx->copy_events.push_back(e);
+    }
+    // The destination buffers may still be in use by work queued on the compute stream (allocator reuse).
+    cudaEvent_t fence = ctx->copy_events[0];
+    CUDA_TRY(cudaEventRecord(fence, ctx->stream));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, fence, 0));
+    for (int64_t gi = 0; gi < groups; ++gi) {
+      const int64_t r0 = gi * up->group_rows, rows = std::min<int64_t>(up->group_rows, n - r0);
+      CUDA_TRY(cudaMemcpyAsync(up->Xd + r0 * d, up->Xh + r0 * d, (size_t)rows * d * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+      CUDA_TRY(cudaMemcpyAsync(up->yd + r0, up->yh + r0, (size_t)rows * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+      CUDA_TRY(cudaMemcpyAsync(up->sd + r0, up->sh + r0, (size_t)rows * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+      CUDA_TRY(cudaEventRecord(ctx->copy_events[gi], ctx->copy_stream));
+    }
+  }
   const MapGeom g = geom(d, D);
   NLS_TRY(prep_weights(ctx, g, W));
   const long long ldT = ctx->chunk_rows;
@@ -475,8 +509,13 @@ extern "C" int nls_primal_gram(nls_ctx* ctx, const double* X, const double* y, c
   CUDA_TRY(cudaMemsetAsync(ctx->border.p, 0, (size_t)(4 * D + 2) * 8, ctx->stream));
   double* border = (double*)ctx->border.p;
   double* scal = border + 4 * D;
+  int64_t arrived = 0;  // rows whose upload the compute stream has been ordered after
   for (int64_t i0 = 0; i0 < n; i0 += ctx->chunk_rows) {
     const int rows = (int)std::min<int64_t>(ctx->chunk_rows, n - i0);
+    while (up && arrived < i0 + rows) {
+      CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->copy_events[arrived / up->group_rows], 0));
+      arrived = std::min<int64_t>(n, (arrived / up->group_rows + 1) * up->group_rows);
+    }
     NLS_TRY(feature_chunk(ctx, g, X + i0 * d, shift, rows, FM_TRANSPOSED, (double*)ctx->psiT.p, ldT, g.DpT, s + i0));
     OpGram::Params p;
     p.A = Operand{(const double*)ctx->psiT.p, ldT, 2 * g.DpT, rows, g.DpT, 0};
@@ -496,6 +535,20 @@ extern "C" int nls_primal_gram(nls_ctx* ctx, const double* X, const double* y, c
   gram_assemble_kernel<<<grid_for((long long)g.m * g.m), 256, 0, ctx->stream>>>((const double*)ctx->gram_ws.p, splits,
                                                                                D, border, scal, A_out, b_out);
   return check_launch(ctx, "gram_assemble_kernel");
+}
+
+extern "C" int nls_primal_gram(nls_ctx* ctx, const double* X, const double* y, const double* s, int64_t n, int d,
+                               const double* shift, const double* W, int D, double* A_out, double* b_out) {
+  return gram_impl(ctx, X, y, s, n, d, shift, W, D, A_out, b_out, nullptr);
+}
+
+extern "C" int nls_primal_gram_h2d(nls_ctx* ctx, const double* X_host, const double* y_host, const double* s_host,
+                                   int64_t n, int d, double* X_dev, double* y_dev, double* s_dev, const double* shift,
+                                   const double* W, int D, double* A_out, double* b_out) {
+  if (!ctx) return fail(NLS_ERR_INVALID, "ctx is null");
+  if (!X_host || !y_host || !s_host || !X_dev || !y_dev || !s_dev) return fail(NLS_ERR_INVALID, "null pointer");
+  UploadPlan up{X_host, y_host, s_host, X_dev, y_dev, s_dev, ctx->chunk_rows * 4};
+  return gram_impl(ctx, X_dev, y_dev, s_dev, n, d, shift, W, D, A_out, b_out, &up);
 }
 
 // ---------------------------------------------------------------------------------------------

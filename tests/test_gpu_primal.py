@@ -288,3 +288,24 @@ def test_fit_is_eigensolver_independent(golden, gpu):
         assert rel_err(out[kind].beta_eig.cpu().numpy(), g["beta"]) < TOL_FIT
         assert rel_err(out[kind].loo_errors, g["loo_errors"]) < TOL_FIT
     assert rel_err(out["jacobi"].lam.cpu().numpy(), out["cusolver"].lam.cpu().numpy()) < 1e-12
+
+
+def test_gram_from_host_rows_equals_device_rows(golden, gpu):
+    """nls_primal_gram_h2d (rows streamed from pinned host memory underneath the Gram pass, several row groups and a
+    ragged tail) gives bitwise the same A, b as the device-resident entry point, and the uploaded copies are exact."""
+    from neo_ls_svm_b200 import _lib
+
+    _, dev, _primal, torch = gpu
+    g = golden("c1")
+    X, y_, s, Xt, classifier, shift, W = _case("c1", g)
+    ctx = _lib.Context(0)
+    ctx.set_chunk_rows(512)  # 10,000 rows -> 5 upload groups of 2048 rows, the last one ragged
+    A0, b0 = ctx.primal_gram(dev(X), dev(y_), dev(s), dev(shift), dev(W))
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).pin_memory()  # noqa: E731
+    A1, b1, Xd, yd, sd = ctx.primal_gram_h2d(pin(X), pin(y_), pin(s), dev(shift), dev(W))
+    torch.cuda.synchronize()
+    assert torch.equal(A0, A1) and torch.equal(b0, b1)
+    assert np.array_equal(Xd.cpu().numpy(), X) and np.array_equal(yd.cpu().numpy(), y_) and np.array_equal(sd.cpu().numpy(), s)
+    fit = _primal.primal_fit(None, None, None, dev(shift), dev(W), classifier, ctx=ctx, host_rows=(pin(X), pin(y_), pin(s)))
+    assert fit.opt == int(g["opt"])
+    assert rel_err(fit.beta_eig.cpu().numpy(), g["beta"]) < TOL_FIT
