@@ -1,4 +1,5 @@
-// jacobi.cuh — hand-written Hermitian eigensolver for stage 3: parallel two-sided block Jacobi.
+// jacobi.cuh — hand-written Hermitian eigensolver for stage 3, 4-wide-block variant (comparator and fallback of the
+// default 8-wide solver in jacobi_wide.cuh; NLS_JACOBI_JB=4 selects it).
 //
 // Replaces scipy.linalg.eigh at _neo_ls_svm.py:120 for the m x m complex Hermitian matrix A/c.
 // (One-sided / Hestenes Jacobi on A was prototyped first and rejected: it implicitly works on A^2,
@@ -6,18 +7,21 @@
 //
 // The index range [0, mp) (mp = m padded to an even number of 4-wide blocks) is cut into 4-wide blocks;
 // a round-robin tournament pairs the blocks so that every round holds nb/2 disjoint pivot pairs of 8
-// indices.  One round is two kernels:
+// indices.  A round is either two kernels ("split"):
 //   jacobi_pivot_kernel  : one warp per pair diagonalises its 8 x 8 Hermitian pivot block with cyclic
 //                          Jacobi rotations in shared memory (32 lanes = 8 rows x 4 disjoint rotations),
 //                          accumulating the 8 x 8 unitary J_i.
 //   jacobi_update_kernel : G <- J^H G J tile by tile (tile (i,j) = J_i^H G[I_i, I_j] J_j, read and written
 //                          by one warp only, so the update is in place) and V <- V J, as complex 8x8x8
 //                          products on DMMA.8x8x4.
+// or one ("fused", jacobi_round_kernel: the tiles that hold next round's pivots are updated first and published
+// through a counter, the pivot warps wait for it and solve while the other warps finish the update).
 // A rotation is skipped when |g_pq| <= eps ||G||_F (absolute threshold: the decomposition is backward
 // stable w.r.t. ||A||, like LAPACK's zheevr); the sweep loop ends when no pair rotated.  Pad
-// rows/columns are exactly zero, never rotate, and are dropped at the end.  One sweep (nb-1 rounds x 2
-// kernels) is captured once into a CUDA graph and replayed, so the ~500 launches per sweep cost no
-// host time.
+// rows/columns are exactly zero, never rotate, and are dropped at the end.  One sweep is captured once
+// into a CUDA graph and replayed.  A persistent cooperative kernel (software grid barrier) and programmatic
+// dependent launch were also built and measured slower than the graph of short kernels (73 and 83 ms against 70 ms
+// at m = 1025; profiles/r1_eigensolver_timing.log, r1_jacobi_pdl_experiment.log); they were removed.
 #pragma once
 #include "ptx.cuh"
 
@@ -175,10 +179,6 @@ __global__ void __launch_bounds__(128) jacobi_pivot_kernel(const double* __restr
                                                            int max_inner, double* __restrict__ Jbuf,
                                                            int* __restrict__ flags, int* __restrict__ active) {
   __shared__ double sm[4][4][8][9];  // per warp: Sr, Si, Jr, Ji
-  // Programmatic dependent launch: this grid may be scheduled while its predecessor drains; it must not touch
-  // G before the predecessor has completed, and lets its own successor start launching right away.
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = blockIdx.x * 4 + warp;
   if (pair >= nb / 2) return;
@@ -298,8 +298,6 @@ __global__ void __launch_bounds__(256) jacobi_update_kernel(double* __restrict__
                                                             int nb, int round, const double* __restrict__ Jbuf,
                                                             const int* __restrict__ flags) {
   __shared__ double ts[8][2][8][9];
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int np = nb / 2;
   const int rb = nb * JB / 8;  // 8-row blocks of V
@@ -316,38 +314,6 @@ __global__ void __launch_bounds__(256) jacobi_update_kernel(double* __restrict__
     }
     update_tile(Gr, Gi, Vr, Vi, ld, nb, round, Jbuf, flags, is_g, i, j, ts[warp], lane);
   }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Persistent variant: the whole iteration (all rounds of all sweeps) in ONE cooperative launch.
-//
-// Kernel boundaries cost ~4.4 us each on this part (measured with empty kernels in a CUDA graph) — 43% of a
-// 20 us round.  Here all CTAs are co-resident and synchronise through a software grid barrier (~1.5 us); in
-// addition the pivot solves of round r+1 overlap the bulk of the update of round r:
-//   phase 1  all warps : update(r) of the 2 np "priority" tiles that contain next round's pivot blocks
-//   barrier
-//   phase 2  pivot warps: J(r+1) from those tiles   ||   all other warps: the rest of update(r), V <- V J(r)
-//   barrier
-// J and the rotation flags are double-buffered by round parity.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch, unsigned int nblocks) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    epoch += 1;
-    __threadfence();
-    atomicAdd(counter, 1u);
-    const unsigned int target = epoch * nblocks;
-    unsigned int spins = 0;
-    while (true) {
-      unsigned int v;
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-      if (v >= target) break;
-      __nanosleep(32);
-      if (++spins > (1u << 25)) __trap();  // a lost CTA surfaces as an error, never as a hung GPU
-    }
-    __threadfence();
-  }
-  __syncthreads();
 }
 
 // Round-robin bookkeeping: partner of block B in round rho, and the pair slot of block B in round r.
@@ -371,119 +337,7 @@ struct JacobiArgs {
   double* Jbuf;          // [2][np][128]
   int* flags;            // [2][np]
   int* active;           // [max_sweeps + 2] rotation counters per sweep window
-  unsigned int* barrier; // grid barrier counter (zeroed by the host)
-  int* sweeps_out;       // number of sweeps executed; negative if not converged
 };
-
-constexpr int JPW = 32;  // warps per CTA of the persistent kernel: one 1024-thread CTA per SM keeps the grid
-                         // barrier at one atomic per SM and the register budget at 64 per thread
-
-__global__ void __launch_bounds__(JPW * 32, 1) jacobi_persistent_kernel(const JacobiArgs a) {
-  __shared__ double ts[JPW][2][8][9];
-  __shared__ double psm[4][8][9];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nb = a.nb, np = nb / 2, R = nb - 1, ld = a.ld;
-  const int rb = nb * JB / 8;
-  const long long n_g = (long long)np * (np + 1) / 2;
-  const long long total = n_g + (long long)rb * np;
-  const unsigned int nblocks = gridDim.x;
-  unsigned int epoch = 0;
-  const double thr_abs2 = a.thr[0], thr_rel2 = a.thr[1];
-  // Pivot p is solved by warp 0 of CTA p (np <= gridDim.x is checked by the host); everyone else is a worker.
-  const bool pivot_warp = warp == 0 && (int)blockIdx.x < np;
-  const long long n_workers = (long long)gridDim.x * JPW - np;
-  const long long worker =
-      pivot_warp ? -1 : (long long)blockIdx.x * JPW + warp - ((int)blockIdx.x < np ? blockIdx.x + 1 : np);
-
-  // Prologue: J(0) of the first round.
-  if (pivot_warp) {
-    int bp, bq;
-    rr_pair(nb, 0, blockIdx.x, bp, bq);
-    const bool any = pivot_solve(a.Gr, a.Gi, ld, bp, bq, thr_abs2, thr_rel2, a.max_inner, psm,
-                                 a.Jbuf + (long long)blockIdx.x * 128, lane);
-    if (lane == 0) {
-      a.flags[blockIdx.x] = any ? 1 : 0;
-      if (any) atomicAdd(a.active, 1);
-    }
-  }
-  grid_barrier(a.barrier, epoch, nblocks);
-
-  int sweeps_done = 0;
-  bool converged = false;
-  for (int sweep = 0; sweep < a.max_sweeps && !converged; ++sweep) {
-    for (int r = 0; r < R; ++r) {
-      const int g = sweep * R + r;  // global round number
-      const int cur = g & 1, nxt = cur ^ 1;
-      const double* Jcur = a.Jbuf + (long long)cur * np * 128;
-      const int* fcur = a.flags + cur * np;
-      const int rho = (r + 1) % R;  // pairing of the next round
-      // ---- phase 1: priority tiles (all diagonal tiles + the tile joining the two blocks of each next pair)
-      for (long long task = (long long)blockIdx.x * JPW + warp; task < 2 * np; task += (long long)gridDim.x * JPW) {
-        int i, j;
-        if (task < np) {
-          i = j = (int)task;
-        } else {
-          int bp, bq;
-          rr_pair(nb, rho, (int)task - np, bp, bq);
-          const int sa = rr_slot(nb, r, bp), sb = rr_slot(nb, r, bq);
-          if (sa == sb) continue;  // only when nb == 2: the pivot block is the diagonal tile itself
-          i = sa < sb ? sa : sb;
-          j = sa < sb ? sb : sa;
-          // Two next-round pairs can join the same two current pairs; the tile is then updated once, by the
-          // task whose block is the first block of pair i.
-          const int xi = sa < sb ? bp : bq;
-          int ip, iq, jp, jq;
-          rr_pair(nb, r, i, ip, iq);
-          rr_pair(nb, r, j, jp, jq);
-          if (xi != ip) {
-            const int pa = rr_partner(nb, rho, ip);
-            if (pa == jp || pa == jq) continue;
-          }
-        }
-        update_tile(a.Gr, a.Gi, a.Vr, a.Vi, ld, nb, r, Jcur, fcur, true, i, j, ts[warp], lane);
-      }
-      grid_barrier(a.barrier, epoch, nblocks);
-      // ---- phase 2: next round's pivots || the rest of this round's update
-      if (pivot_warp) {
-        int bp, bq;
-        rr_pair(nb, rho, blockIdx.x, bp, bq);
-        const bool any = pivot_solve(a.Gr, a.Gi, ld, bp, bq, thr_abs2, thr_rel2, a.max_inner, psm,
-                                     a.Jbuf + ((long long)nxt * np + blockIdx.x) * 128, lane);
-        if (lane == 0) {
-          a.flags[nxt * np + blockIdx.x] = any ? 1 : 0;
-          // rotations found while preparing round g + 1 are counted in the sweep that round belongs to
-          if (any) atomicAdd(a.active + (g + 1) / R, 1);
-        }
-      } else {
-        for (long long task = worker; task < total; task += n_workers) {
-          const bool is_g = task < n_g;
-          int i, j;
-          if (is_g) {
-            upper_tile(task, np, i, j);
-            if (i == j) continue;  // diagonal tiles were done in phase 1
-            int ip, iq, jp, jq;
-            rr_pair(nb, r, i, ip, iq);
-            rr_pair(nb, r, j, jp, jq);
-            const int pa = rr_partner(nb, rho, ip), pb = rr_partner(nb, rho, iq);
-            if (pa == jp || pa == jq || pb == jp || pb == jq) continue;  // priority tile, done in phase 1
-          } else {
-            i = (int)((task - n_g) / np);
-            j = (int)((task - n_g) % np);
-          }
-          update_tile(a.Gr, a.Gi, a.Vr, a.Vi, ld, nb, r, Jcur, fcur, is_g, i, j, ts[warp], lane);
-        }
-      }
-      grid_barrier(a.barrier, epoch, nblocks);
-    }
-    sweeps_done = sweep + 1;
-    // Converged when no pivot of this sweep rotated (the counters were completed before the last barrier;
-    // the pivots prepared for the next sweep's first round are counted there and are then identities too).
-    int act;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(act) : "l"(a.active + sweep) : "memory");
-    converged = act == 0;
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) *a.sweeps_out = converged ? sweeps_done : -sweeps_done;
-}
 
 // ---------------------------------------------------------------------------------------------
 // Fused round (default): ONE kernel per round.  The CTAs first update the 2 np priority tiles that hold next

@@ -700,7 +700,7 @@ static int heev_jacobi_wide(nls_ctx* ctx, const double* A, int m, double scale, 
   return jacobi_finish(ctx, Gfinal, Vr, Vi, mp, m, lam_raw, perm, lam_out, Q_out);
 }
 
-// Hand-written parallel two-sided block Jacobi (csrc/jacobi.cuh).
+// 4-wide-block driver (csrc/jacobi.cuh): comparator and fallback of the wide solver.
 static int heev_jacobi(nls_ctx* ctx, const double* A, int m, double scale, double* lam_out, double* Q_out) {
   if (!ctx || !A || !lam_out || !Q_out || m < 1) return fail(NLS_ERR_INVALID, "bad argument to nls_heev");
   CUDA_TRY(cudaSetDevice(ctx->device));
@@ -739,21 +739,15 @@ static int heev_jacobi(nls_ctx* ctx, const double* A, int m, double scale, doubl
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   const long long tasks = (long long)np * (np + 1) / 2 + (long long)(mp / 8) * np;
   int sweep = 0, h_active = 1;
-  const char* pers = getenv("NLS_JACOBI_PERSISTENT");
-  int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jacobi_persistent_kernel, JPW * 32, 0));
-  const int coop_grid = ctx->sm_count;  // one 1024-thread CTA per SM
-  // The persistent variant is correct but measured slower than the graph of short kernels on B200 (the pivot
-  // chains share the FP64 pipe with the update's DMMAs): opt-in with NLS_JACOBI_PERSISTENT=1.
-  const bool persistent = (pers && pers[0] == '1') && occ >= 1 && np <= coop_grid && !getenv("NLS_JACOBI_DIAG");
-  const char* mode_env = getenv("NLS_JACOBI_MODE");  // "fused" (default) or "split" (two kernels per round)
-  const char* occ_env = getenv("NLS_JACOBI_OCC");  // resident CTAs per SM of the fused round kernel: 4, 5 or 6
+  const char* mode_env = getenv("NLS_JACOBI_MODE");  // "fused" or "split" (two kernels per round)
+  const char* occ_env = getenv("NLS_JACOBI_OCC");    // resident CTAs per SM of the fused round kernel: 4, 5 or 6
   const int fused_occ = occ_env && atoi(occ_env) >= 4 && atoi(occ_env) <= 6 ? atoi(occ_env) : 4;
   const int fused_grid = ctx->sm_count * fused_occ;
   // Measured on B200: fused 58 ms vs split 70 ms at m = 1025, but 21 vs 19.5 ms at m = 513 (fewer tiles per
   // round to hide the pivot behind), so small problems keep the two-kernel round unless forced.
   const bool want_fused = mode_env ? strcmp(mode_env, "fused") == 0 : np >= 96;
-  const bool fused = !persistent && want_fused && np <= fused_grid && np <= 160 && !getenv("NLS_JACOBI_DIAG");
+  const bool fused = want_fused && np <= fused_grid && np <= 160;
+  if (!ctx->jac_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->jac_stream, cudaStreamNonBlocking));
   if (fused) {
     // One kernel per round (priority tiles -> next pivots overlapped with the bulk update); one sweep
     // (nb - 1 identical launches; the round number lives on the device) is replayed as a CUDA graph.
@@ -763,12 +757,10 @@ static int heev_jacobi(nls_ctx* ctx, const double* A, int m, double scale, doubl
     ja.Gr = Gr; ja.Gi = Gi; ja.Vr = Vr; ja.Vi = Vi;
     ja.ld = mp; ja.nb = nb; ja.max_inner = ctx->jac_inner; ja.max_sweeps = max_sweeps;
     ja.thr = thr; ja.Jbuf = Jbuf; ja.flags = flags; ja.active = active;
-    ja.barrier = nullptr; ja.sweeps_out = nullptr;
     // J(0): pivots of the very first round.
     jacobi_pivot_kernel<<<(np + 3) / 4, 128, 0, ctx->stream>>>(Gr, Gi, mp, nb, 0, thr, ctx->jac_inner, Jbuf, flags, active);
     NLS_TRY(check_launch(ctx, "jacobi_pivot_kernel"));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    if (!ctx->jac_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->jac_stream, cudaStreamNonBlocking));
     if (!ctx->jac_graph || ctx->jac_graph_key != (const void*)Gr || ctx->jac_graph_nb != -(nb * 8 + fused_occ)) {
       if (ctx->jac_graph) {
         cudaGraphExecDestroy(ctx->jac_graph);
@@ -794,80 +786,38 @@ static int heev_jacobi(nls_ctx* ctx, const double* A, int m, double scale, doubl
       CUDA_TRY(cudaMemcpyAsync(&h_active, active + sweep, sizeof(int), cudaMemcpyDeviceToHost, ctx->jac_stream));
       CUDA_TRY(cudaStreamSynchronize(ctx->jac_stream));
     }
-  } else if (persistent) {
-    // One cooperative launch runs every round of every sweep (software grid barrier, pivots of round r+1
-    // overlapped with the bulk of update r); the host only reads back the sweep count.
-    CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)(2 * np + max_sweeps + 16) * 4, ctx->stream));
-    JacobiArgs ja;
-    ja.Gr = Gr; ja.Gi = Gi; ja.Vr = Vr; ja.Vi = Vi;
-    ja.ld = mp; ja.nb = nb; ja.max_inner = ctx->jac_inner; ja.max_sweeps = max_sweeps;
-    ja.thr = thr; ja.Jbuf = Jbuf; ja.flags = flags; ja.active = active;
-    ja.barrier = (unsigned int*)misc; ja.sweeps_out = misc + 1;
-    void* kargs[] = {&ja};
-    CUDA_TRY(cudaLaunchCooperativeKernel((void*)jacobi_persistent_kernel, dim3(coop_grid), dim3(JPW * 32), kargs, 0, ctx->stream));
-    ctx->launches += 1;
-    int h_sweeps = 0;
-    CUDA_TRY(cudaMemcpyAsync(&h_sweeps, misc + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    sweep = h_sweeps < 0 ? -h_sweeps : h_sweeps;
-    h_active = h_sweeps > 0 ? 0 : 1;
   } else {
-  const int upd_grid = (int)std::min<long long>((tasks + 7) / 8, (long long)ctx->sm_count * 8);
-  if (!ctx->jac_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->jac_stream, cudaStreamNonBlocking));
-  if (!ctx->jac_graph || ctx->jac_graph_key != (const void*)Gr || ctx->jac_graph_nb != nb) {
-    // Capture one sweep: reset the rotation counter, then nb-1 rounds of (pivot, update).
-    if (ctx->jac_graph) {
-      cudaGraphExecDestroy(ctx->jac_graph);
-      ctx->jac_graph = nullptr;
+    const int upd_grid = (int)std::min<long long>((tasks + 7) / 8, (long long)ctx->sm_count * 8);
+    if (!ctx->jac_graph || ctx->jac_graph_key != (const void*)Gr || ctx->jac_graph_nb != nb) {
+      // Capture one sweep: reset the rotation counter, then nb-1 rounds of (pivot, update).
+      if (ctx->jac_graph) {
+        cudaGraphExecDestroy(ctx->jac_graph);
+        ctx->jac_graph = nullptr;
+      }
+      cudaGraph_t graph = nullptr;
+      CUDA_TRY(cudaStreamBeginCapture(ctx->jac_stream, cudaStreamCaptureModeRelaxed));
+      cudaMemsetAsync(active, 0, sizeof(int), ctx->jac_stream);
+      for (int round = 0; round < nb - 1; ++round) {
+        jacobi_pivot_kernel<<<(np + 3) / 4, 128, 0, ctx->jac_stream>>>(Gr, Gi, mp, nb, round, thr, ctx->jac_inner, Jbuf,
+                                                                      flags, active);
+        jacobi_update_kernel<<<upd_grid, 256, 0, ctx->jac_stream>>>(Gr, Gi, Vr, Vi, mp, nb, round, Jbuf, flags);
+      }
+      CUDA_TRY(cudaStreamEndCapture(ctx->jac_stream, &graph));
+      cudaError_t ge = cudaGraphInstantiate(&ctx->jac_graph, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ge != cudaSuccess) return fail(NLS_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ge));
+      ctx->jac_graph_key = (const void*)Gr;
+      ctx->jac_graph_nb = nb;
     }
-    cudaGraph_t graph = nullptr;
-    CUDA_TRY(cudaStreamBeginCapture(ctx->jac_stream, cudaStreamCaptureModeRelaxed));
-    cudaMemsetAsync(active, 0, sizeof(int), ctx->jac_stream);
-    const char* diag = getenv("NLS_JACOBI_DIAG");  // timing experiments only: "pivot" / "update" runs one kernel kind
-    const bool do_pivot = !diag || strcmp(diag, "update") != 0, do_update = !diag || strcmp(diag, "pivot") != 0;
-    // Programmatic dependent launch (griddepcontrol.wait at the top of both kernels) is wired but OFF by
-    // default: on B200 it measured slower (82.8 vs 70.2 ms at m = 1025); NLS_JACOBI_PDL=1 enables it.
-    const char* pdl_env = getenv("NLS_JACOBI_PDL");
-    cudaLaunchAttribute pdl;
-    pdl.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    pdl.val.programmaticStreamSerializationAllowed = (pdl_env && pdl_env[0] == '1') ? 1 : 0;
-    cudaLaunchConfig_t cfg_p = {}, cfg_u = {};
-    cfg_p.gridDim = dim3((np + 3) / 4);
-    cfg_p.blockDim = dim3(128);
-    cfg_p.stream = ctx->jac_stream;
-    cfg_p.attrs = &pdl;
-    cfg_p.numAttrs = 1;
-    cfg_u = cfg_p;
-    cfg_u.gridDim = dim3(upd_grid);
-    cfg_u.blockDim = dim3(256);
-    const double* thr_c = thr;
-    const double* Jbuf_c = Jbuf;
-    const int* flags_c = flags;
-    const double *Gr_c = Gr, *Gi_c = Gi;
-    for (int round = 0; round < nb - 1; ++round) {
-      if (do_pivot)
-        cudaLaunchKernelEx(&cfg_p, jacobi_pivot_kernel, Gr_c, Gi_c, mp, nb, round, thr_c, ctx->jac_inner, Jbuf, flags, active);
-      if (do_update)
-        cudaLaunchKernelEx(&cfg_u, jacobi_update_kernel, Gr, Gi, Vr, Vi, mp, nb, round, Jbuf_c, flags_c);
+    for (; sweep < max_sweeps && h_active > 0; ++sweep) {
+      CUDA_TRY(cudaGraphLaunch(ctx->jac_graph, ctx->jac_stream));
+      ctx->launches += 2 * (nb - 1);
+      CUDA_TRY(cudaMemcpyAsync(&h_active, active, sizeof(int), cudaMemcpyDeviceToHost, ctx->jac_stream));
+      CUDA_TRY(cudaStreamSynchronize(ctx->jac_stream));
     }
-    CUDA_TRY(cudaStreamEndCapture(ctx->jac_stream, &graph));
-    cudaError_t ge = cudaGraphInstantiate(&ctx->jac_graph, graph, 0);
-    cudaGraphDestroy(graph);
-    if (ge != cudaSuccess) return fail(NLS_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ge));
-    ctx->jac_graph_key = (const void*)Gr;
-    ctx->jac_graph_nb = nb;
-  }
-  const int graph_sweeps = getenv("NLS_JACOBI_DIAG") ? 12 : max_sweeps;
-  for (; sweep < graph_sweeps && h_active > 0; ++sweep) {
-    CUDA_TRY(cudaGraphLaunch(ctx->jac_graph, ctx->jac_stream));
-    ctx->launches += 2 * (nb - 1);
-    CUDA_TRY(cudaMemcpyAsync(&h_active, active, sizeof(int), cudaMemcpyDeviceToHost, ctx->jac_stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->jac_stream));
-  }
   }
   ctx->eig_sweeps = sweep;
-  if (h_active > 0 && !getenv("NLS_JACOBI_DIAG"))
-    return fail(NLS_ERR_SOLVER, "Jacobi eigensolver did not converge in %d sweeps", max_sweeps);
+  if (h_active > 0) return fail(NLS_ERR_SOLVER, "Jacobi eigensolver did not converge in %d sweeps", max_sweeps);
   return jacobi_finish(ctx, Gr, Vr, Vi, mp, m, lam_raw, perm, lam_out, Q_out);
 }
 
