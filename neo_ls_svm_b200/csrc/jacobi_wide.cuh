@@ -48,7 +48,7 @@ struct WideCfg {
 struct WideArgs {
   double* G[2][2];  // [buffer][Re, Im], ping-pong by round parity
   double *Vr, *Vi;
-  int ld, nb, max_inner;
+  int ld, nb, max_inner, sm_count;
   const double* thr;  // [abs^2]
   double* Jbuf;       // [2][np][JSZ]  J of the pivots, by round parity
   double* Sbuf;       // [2][np][JSZ]  final S of the pivot solves (= the updated diagonal tiles)
@@ -599,9 +599,22 @@ __global__ void __launch_bounds__(WIDE_WARPS * 32, 2) jacobi_round_w_kernel(cons
     return;
   }
   if (diag & 2) return;
-  const long long n_workers = (long long)gridDim.x * WIDE_WARPS - np;
+  // Tile-update warps are numbered over the grid, skipping the pivot warps and (experiment, diag bits 2 and 3)
+  // the warps that would share the pivot warp's SM sub-partition: warp 4 of the pivot CTAs, and warps 0 and 4 of
+  // the CTAs that are presumably co-resident with them (blockIdx.x + sm_count).
+  const unsigned mask_p = (diag & 4) ? 0xEEu : 0xFEu, mask_q = (diag & 8) ? 0xEEu : 0xFFu;
+  const int ps = a.sm_count, gx = (int)gridDim.x, bx = (int)blockIdx.x;
+  auto clampi = [](int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); };
+  auto workers_before = [&](int b) {
+    const int q_lo = clampi(ps, np, gx), q_hi = clampi(ps + np, np, gx);
+    return (long long)__popc(mask_p) * clampi(b, 0, np) + 8LL * (clampi(b, np, q_lo) - np) +
+           (long long)__popc(mask_q) * (clampi(b, q_lo, q_hi) - q_lo) + 8LL * (clampi(b, q_hi, gx) - q_hi);
+  };
+  const unsigned my_mask = pivot_cta ? mask_p : ((bx >= ps && bx < ps + np) ? mask_q : 0xFFu);
+  if (!((my_mask >> warp) & 1u)) return;
+  const long long n_workers = workers_before(gx);
   const long long total = n_g + (long long)rb * np;
-  long long t = (long long)blockIdx.x * WIDE_WARPS + warp - (pivot_cta ? blockIdx.x + 1 : np);
+  long long t = workers_before(bx) + __popc(my_mask & ((1u << warp) - 1u));
   TileTask k = decode_tile_task(t, n_g, total, np);
   int b = 0;
   stage_tile_w<JBW>(k, k.is_g ? Sr_ : a.Vr, k.is_g ? Si_ : a.Vi, ld, pair_tab, sflags, stage, lane);

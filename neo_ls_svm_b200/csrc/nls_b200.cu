@@ -634,7 +634,7 @@ static int heev_jacobi_wide(nls_ctx* ctx, const double* A, int m, double scale, 
   for (int b = 0; b < 2; ++b)
     for (int c = 0; c < 2; ++c) wa.G[b][c] = base + (size_t)(2 * b + c) * mm;
   wa.Vr = Vr; wa.Vi = Vi;
-  wa.ld = mp; wa.nb = nb; wa.max_inner = ctx->jac_inner;
+  wa.ld = mp; wa.nb = nb; wa.max_inner = ctx->jac_inner; wa.sm_count = ctx->sm_count;
   wa.thr = thr; wa.Jbuf = Jbuf; wa.Sbuf = Sbuf; wa.flags = flags; wa.active = active; wa.state = misc + 2;
   ProfScope scope(ctx, NLS_PROF_OTHER);
   jacobi_init_kernel<<<grid_for((long long)mm), 256, 0, ctx->stream>>>(A, m, mp, scale, wa.G[0][0], wa.G[0][1], Vr, Vi);
@@ -663,9 +663,12 @@ static int heev_jacobi_wide(nls_ctx* ctx, const double* A, int m, double scale, 
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   if (!ctx->jac_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->jac_stream, cudaStreamNonBlocking));
   // Timing experiments only (results are then meaningless): bit 0 skips the pivot solves, bit 1 the tile updates.
+  // Bit 2 idles warp 4 of the pivot CTAs (it shares the pivot warp's SM sub-partition): 26.1 vs 28.1 ms at m = 1025,
+  // a wash at m = 513, 2.5 % slower at m = 2049 where the tile updates dominate; bit 3 additionally idles the
+  // presumably co-resident CTA's warps 0 and 4 and never paid off (profiles/r1d_jacobi_wide_layouts.log).
   const char* diag_env = getenv("NLS_JACOBI_DIAG");
-  const int diag = diag_env ? atoi(diag_env) & 3 : 0;
-  const int graph_code = -(1 << 24) - ((nb * 64 + JBW * 4) * 4 + diag);
+  const int diag = diag_env ? atoi(diag_env) & 15 : (np <= 100 ? 4 : 0);
+  const int graph_code = -(1 << 24) - ((nb * 64 + JBW * 4) * 16 + diag);
   if (!ctx->jac_graph || ctx->jac_graph_key != (const void*)base || ctx->jac_graph_nb != graph_code) {
     if (ctx->jac_graph) {
       cudaGraphExecDestroy(ctx->jac_graph);
@@ -686,7 +689,8 @@ static int heev_jacobi_wide(nls_ctx* ctx, const double* A, int m, double scale, 
     ctx->jac_graph_nb = graph_code;
   }
   int sweep = 0, h_active = 1, h_misc[4] = {1, 0, 0, 0};
-  for (; sweep < (diag ? 10 : max_sweeps) && (diag || (h_active > 0 && h_misc[0] > 0)); ++sweep) {
+  const bool timing_only = (diag & 3) != 0;  // bits 2 and 3 only change the warp layout: results stay valid
+  for (; sweep < (timing_only ? 10 : max_sweeps) && (timing_only || (h_active > 0 && h_misc[0] > 0)); ++sweep) {
     CUDA_TRY(cudaGraphLaunch(ctx->jac_graph, ctx->jac_stream));
     ctx->launches += nb;
     CUDA_TRY(cudaMemcpyAsync(&h_active, active + sweep, sizeof(int), cudaMemcpyDeviceToHost, ctx->jac_stream));
@@ -694,7 +698,7 @@ static int heev_jacobi_wide(nls_ctx* ctx, const double* A, int m, double scale, 
     CUDA_TRY(cudaStreamSynchronize(ctx->jac_stream));
   }
   ctx->eig_sweeps = sweep;
-  if (h_active > 0 && h_misc[0] > 0 && !diag)
+  if (h_active > 0 && h_misc[0] > 0 && !timing_only)
     return fail(NLS_ERR_SOLVER, "Jacobi eigensolver did not converge in %d sweeps", max_sweeps);
   const double* Gfinal = wa.G[(sweep * (nb - 1)) & 1][0];  // the buffer the last round wrote
   return jacobi_finish(ctx, Gfinal, Vr, Vi, mp, m, lam_raw, perm, lam_out, Q_out);
