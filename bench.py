@@ -271,6 +271,25 @@ def run_ours(args) -> None:
                                "pageable H2D, stages 1-4c, D2H, conformal split"}
         del est
 
+    # ---- size-independent correctness properties of the full-size result (outside every timed region) ----
+    def rmax(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    lev = fit.rows["loo_leverage"]
+    checks = {
+        # A is Hermitian; β̂ solves (γ*C + A) β̂ = b; per row loo_residual (1 − leverage) = residual (different kernels)
+        "gram_hermitian_rel": float((fit.A - fit.A.conj().T).abs().max() / fit.A.abs().max()),
+        "normal_equations_rel": float((fit.A @ fit.beta + (fit.gamma / fit.inv_c) * fit.beta - fit.b).abs().max() / fit.b.abs().max()),
+        "loo_identity_rel": rmax(((fit.rows["loo_residuals"] * (1.0 - lev) - fit.rows["residuals"]).abs().max()
+                                  / fit.rows["residuals"].abs().max()).item()),
+        "leverage_max": rmax(lev.max().item()),
+        # the end-to-end arm (host rows in, host results out) reproduces the device-resident arm bit for bit
+        "e2e_rows_bitwise_equal": rmax(0.0 if torch.equal(out_host["rows"], fit.rows["_stacked"].cpu()) else 1.0) == 0.0,
+    }
+
     if rank == 0:
         m = D + 1
         rows_local = r1 - r0
@@ -318,6 +337,7 @@ def run_ours(args) -> None:
             },
             "cpu_baseline": cpu,
             "fit_api": fit_api,
+            "checks": checks,
         }
         print(json.dumps(line))
     if world > 1:

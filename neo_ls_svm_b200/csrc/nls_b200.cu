@@ -87,6 +87,7 @@ struct nls_ctx {
   const void* jac_graph_key = nullptr;
   int jac_graph_nb = 0;
   int jac_inner = 1;  // cyclic sweeps per 8x8 pivot solve (partial diagonalisation is enough for block Jacobi)
+  bool jac_wide_attr = false;  // dynamic shared memory opt-in of the wide Jacobi kernels done on this device
   cudaStream_t copy_stream = nullptr;        // host -> device row groups of nls_primal_gram_h2d
   std::vector<cudaEvent_t> copy_events;      // one per row group, reused
   EncodeTiledFn encode = nullptr;
@@ -191,18 +192,18 @@ static int launch_gemm(nls_ctx* ctx, const typename Op::Params& p, dim3 grid, lo
   ProfScope scope(ctx, kind);
   if (ctx->use_tma) {
     auto kern = gemm_kernel<MODE, Op, true>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};  // function attributes are per device
+    if (!attr_set[ctx->device & 63]) {
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
-      attr_set = true;
+      attr_set[ctx->device & 63] = true;
     }
     kern<<<grid, GEMM_THREADS, T::SMEM_BYTES, ctx->stream>>>(mapA, mapB, p);
   } else {
     auto kern = gemm_kernel<MODE, Op, false>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};  // function attributes are per device
+    if (!attr_set[ctx->device & 63]) {
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
-      attr_set = true;
+      attr_set[ctx->device & 63] = true;
     }
     kern<<<grid, GEMM_THREADS, T::SMEM_BYTES, ctx->stream>>>(mapA, mapB, p);
   }
@@ -644,11 +645,10 @@ static int heev_jacobi_wide(nls_ctx* ctx, const double* A, int m, double scale, 
   jacobi_threshold_kernel<<<1, 1, 0, ctx->stream>>>(fro2, thr);
   CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)(2 * np + max_sweeps + 16) * 4, ctx->stream));
   const size_t piv_smem = (size_t)4 * C::PIV_SM * 8, round_smem = (size_t)wide_smem_doubles<JBW>() * 8;
-  static bool attr_done = false;
-  if (!attr_done) {
+  if (!ctx->jac_wide_attr) {  // per device (one context per device), not per process
     CUDA_TRY(cudaFuncSetAttribute(jacobi_pivot0_w_kernel<JBW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)piv_smem));
     CUDA_TRY(cudaFuncSetAttribute(jacobi_round_w_kernel<JBW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)round_smem));
-    attr_done = true;
+    ctx->jac_wide_attr = true;
   }
   // Two 8-warp CTAs per SM; warp 0 of the first np CTAs solves a pivot, every other warp updates tiles.
   int occ = 0;
