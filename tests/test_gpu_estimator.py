@@ -133,3 +133,38 @@ def test_large_fit_uses_device_prepass_and_matches_host_path(monkeypatch):
     assert m_dev.γ_ == m_host.γ_
     assert rel_err(m_dev.β̂_, m_host.β̂_) < 1e-6
     assert rel_err(m_dev.loo_residuals_, m_host.loo_residuals_) < 1e-6
+
+
+@pytest.mark.gpu
+def test_device_unique_matches_numpy():
+    """The device sort behind the target quantiser returns exactly np.unique's values, inverse and counts."""
+    from neo_ls_svm_b200._quantizer import MIN_SAMPLES_FOR_DEVICE_UNIQUE, sample_bins_quantized_ecdf, unique_values
+
+    rng = np.random.default_rng(5)
+    n = MIN_SAMPLES_FOR_DEVICE_UNIQUE + 12345
+    for x in (np.round(rng.standard_normal(n), 3), rng.standard_normal(n), rng.integers(-50, 50, n)):
+        v, inv, cnt = unique_values(x, return_inverse=True, return_counts=True)
+        v0, inv0, cnt0 = np.unique(x, return_inverse=True, return_counts=True)
+        assert np.array_equal(v, v0) and np.array_equal(inv, inv0) and np.array_equal(cnt, cnt0)
+        assert np.array_equal(unique_values(x), v0)
+    y = rng.standard_normal(n)
+    codes = sample_bins_quantized_ecdf(y)
+    assert codes.min() == 0 and 4 <= codes.max() + 1 <= 64 and np.all(np.diff(codes[np.argsort(y, kind="stable")]) >= 0)
+
+
+@pytest.mark.gpu
+def test_large_input_nan_is_rejected_by_the_device_scan():
+    """Above 2^24 elements the NaN/inf scan of X runs on the device copy; the error is still sklearn's."""
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((270_000, 64))
+    y = X[:, 0] + 0.1 * rng.standard_normal(len(X))
+    X[123_456, 7] = np.nan
+    with pytest.raises(ValueError, match="NaN"):
+        NeoLSSVM(primal_feature_map=OrthogonalRandomFourierFeatures(num_features=64)).fit(X, y)
+    X[123_456, 7] = 0.0
+    y[5] = np.inf
+    with pytest.raises(ValueError, match="infinity"):
+        NeoLSSVM(primal_feature_map=OrthogonalRandomFourierFeatures(num_features=64)).fit(X, y)
+    y[5] = 0.0
+    model = NeoLSSVM(primal_feature_map=OrthogonalRandomFourierFeatures(num_features=64)).fit(X, y)
+    assert model.loo_score_ > 0.5
