@@ -111,30 +111,43 @@ __device__ __forceinline__ void inner_pair(bool cross, int r, int slot, int& p, 
   }
 }
 
-// One warp: cyclic two-sided Jacobi on the P x P Hermitian block held in shared memory (Sr, Si at sm, pitch SP);
-// accumulates J (Jr, Ji, initialised here).  An inner round applies P/2 disjoint rotations in ONE stage: S is
-// updated as (P/2)^2 independent 2 x 2 blocks R_a^H S[{p_a,q_a},{p_b,q_b}] R_b (each lane owns the blocks of its
-// own column rotation b and fetches the row rotations by shuffle), J as column pairs; one barrier between the
-// reads and the writes, one after.  Returns whether anything rotated.
-template <int JBW>
+// Barrier among the NW warps that solve one pivot (named barrier 1: a CTA holds at most one multi-warp pivot).
+template <int NW>
+__device__ __forceinline__ void pivot_sync() {
+  if (NW == 1)
+    __syncwarp();
+  else
+    asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+}
+
+// NW warps (tid = 0 .. 32 NW - 1): cyclic two-sided Jacobi on the P x P Hermitian block held in shared memory (Sr,
+// Si at sm, pitch SP); accumulates J (Jr, Ji, initialised here).  An inner round applies P/2 disjoint rotations
+// in ONE stage: S is updated as (P/2)^2 independent 2 x 2 blocks R_a^H S[{p_a,q_a},{p_b,q_b}] R_b (each thread owns
+// blocks of its own column rotation b and fetches the row rotations by shuffle — every warp computes all P/2
+// rotations), J as column pairs; one barrier between the reads and the writes, one after.  With NW = 2 the two
+// warps sit on different SM sub-partitions and each does half of the FP64 and shared-memory work of a round.
+// Returns whether anything rotated.
+template <int JBW, int NW>
 __device__ __forceinline__ bool pivot_rotate_w(double* __restrict__ sm, double thr_abs2, bool cross, int max_inner,
-                                               int lane) {
+                                               int tid) {
   using C = WideCfg<JBW>;
-  constexpr int P = C::P, SP = C::SP, NROT = P / 2;
-  static_assert(NROT <= 32 && 32 % NROT == 0 && (JBW & (JBW - 1)) == 0, "one warp per pivot");
-  constexpr int LPR = 32 / NROT;   // lanes sharing a column rotation
-  constexpr int BPL = NROT / LPR;  // 2 x 2 blocks of S per lane and round
-  constexpr int RPL = P / LPR;     // rows of J per lane and round
+  constexpr int P = C::P, SP = C::SP, NROT = P / 2, T = 32 * NW;
+  static_assert(NROT <= 32 && 32 % NROT == 0 && (JBW & (JBW - 1)) == 0, "every warp holds all rotations");
+  constexpr int LPR = T / NROT;    // threads sharing a column rotation
+  constexpr int BPL = NROT / LPR;  // 2 x 2 blocks of S per thread and round
+  constexpr int RPL = P / LPR;     // rows of J per thread and round
+  static_assert(BPL >= 1 && RPL >= 1, "too many warps for this pivot size");
   double* Sr = sm;
   double* Si = sm + P * SP;
   double* Jr = sm + 2 * P * SP;
   double* Ji = sm + 3 * P * SP;
-  for (int e = lane; e < P * P; e += 32) {
+  for (int e = tid; e < P * P; e += T) {
     const int a = e / P, b = e % P;
     Jr[a * SP + b] = (a == b) ? 1.0 : 0.0;
     Ji[a * SP + b] = 0.0;
   }
-  __syncwarp();
+  pivot_sync<NW>();
+  const int lane = tid;
   const int slot = lane % NROT, sub = lane / NROT;
   const int nrounds = cross ? JBW : P - 1;
   bool any_total = false;
@@ -191,7 +204,7 @@ __device__ __forceinline__ bool pivot_rotate_w(double* __restrict__ sm, double t
         jq_r[t] = (wr * xr - wi * xi) + c * yr;
         jq_i[t] = (wr * xi + wi * xr) + c * yi;
       }
-      __syncwarp();  // every lane has read its inputs
+      pivot_sync<NW>();  // every thread has read its inputs
 #pragma unroll
       for (int t = 0; t < BPL; ++t) {
         Sr[pa[t] * SP + p] = n00r[t];
@@ -211,21 +224,21 @@ __device__ __forceinline__ bool pivot_rotate_w(double* __restrict__ sm, double t
         Jr[i * SP + q] = jq_r[t];
         Ji[i * SP + q] = jq_i[t];
       }
-      __syncwarp();
+      pivot_sync<NW>();
     }
-    if (!__any_sync(0xffffffffu, any)) break;
+    if (!__any_sync(0xffffffffu, any)) break;  // every warp sees all rotations: the decision is uniform
     any_total = true;
   }
   return any_total;
 }
 
 // Store the solver's J and final S (pitch SP in shared memory) as [2][P][P] each.
-template <int JBW>
+template <int JBW, int NW>
 __device__ __forceinline__ void pivot_store_w(const double* __restrict__ sm, double* __restrict__ Jout,
-                                              double* __restrict__ Sout, int lane) {
+                                              double* __restrict__ Sout, int tid) {
   using C = WideCfg<JBW>;
   constexpr int P = C::P, SP = C::SP;
-  for (int e = lane; e < P * P; e += 32) {
+  for (int e = tid; e < P * P; e += 32 * NW) {
     const int o = (e / P) * SP + e % P;
     Sout[e] = sm[o];
     Sout[P * P + e] = sm[P * SP + o];
@@ -253,8 +266,8 @@ __global__ void __launch_bounds__(128) jacobi_pivot0_w_kernel(const WideArgs a) 
     sm[P * SP + x * SP + y] = __ldcg(a.G[0][1] + o);
   }
   __syncwarp();
-  const bool any = pivot_rotate_w<JBW>(sm, a.thr[0], false, a.max_inner, lane);
-  pivot_store_w<JBW>(sm, a.Jbuf + (long long)pair * C::JSZ, a.Sbuf + (long long)pair * C::JSZ, lane);
+  const bool any = pivot_rotate_w<JBW, 1>(sm, a.thr[0], false, a.max_inner, lane);
+  pivot_store_w<JBW, 1>(sm, a.Jbuf + (long long)pair * C::JSZ, a.Sbuf + (long long)pair * C::JSZ, lane);
   if (lane == 0) {
     a.flags[pair] = any ? 1 : 0;
     if (any) atomicAdd(a.active, 1);
@@ -447,16 +460,18 @@ __device__ __forceinline__ void copy_diag_tile_w(const double* __restrict__ S, d
   }
 }
 
-// One warp: assemble next round's pivot block (bp, bq) in shared memory from the OLD G, the current J's and the
-// current pivots' final S (see the header), then solve it.
-template <int JBW>
+// NW warps (warps 0 .. NW - 1 of the CTA): warp 0 assembles next round's pivot block (bp, bq) in shared memory from
+// the OLD G, the current J's and the current pivots' final S (see the header); all NW warps then solve it.
+template <int JBW, int NW>
 __device__ __forceinline__ void next_pivot_w(const WideArgs& a, const double* __restrict__ Gr,
                                              const double* __restrict__ Gi, int r, int rho, int slot_next, int cur,
                                              int sweep_of_next, double* __restrict__ ts, double* __restrict__ psm,
-                                             int lane) {
+                                             int tid) {
   using C = WideCfg<JBW>;
   constexpr int P = C::P, SP = C::SP, TP = C::TP, KS = C::KS;
   const int nb = a.nb, np = nb / 2, ld = a.ld, nxt = cur ^ 1;
+  const int lane = tid & 31;
+  if (tid < 32) {
   int bp, bq;
   rr_pair(nb, rho, slot_next, bp, bq);
   const int sa = rr_slot(nb, r, bp), sb = rr_slot(nb, r, bq);
@@ -535,30 +550,32 @@ __device__ __forceinline__ void next_pivot_w(const WideArgs& a, const double* __
       Si[(JBW + 2 * fk + h) * SP + fr] = -xi[h];
     }
   }
-  __syncwarp();
+  }
+  pivot_sync<NW>();
   // The pairs inside a block are rotated in the first round of a sweep only; every other pivot annihilates its
   // 64 cross pairs.  (nb == 2: the single pivot is the whole matrix, always a full sweep.)
   const bool cross = rho != 0 && nb > 2;
-  const bool any = pivot_rotate_w<JBW>(psm, a.thr[0], cross, a.max_inner, lane);
-  pivot_store_w<JBW>(psm, a.Jbuf + ((long long)nxt * np + slot_next) * C::JSZ,
-                     a.Sbuf + ((long long)nxt * np + slot_next) * C::JSZ, lane);
-  if (lane == 0) {
+  const bool any = pivot_rotate_w<JBW, NW>(psm, a.thr[0], cross, a.max_inner, tid);
+  pivot_store_w<JBW, NW>(psm, a.Jbuf + ((long long)nxt * np + slot_next) * C::JSZ,
+                         a.Sbuf + ((long long)nxt * np + slot_next) * C::JSZ, tid);
+  if (tid == 0) {
     a.flags[nxt * np + slot_next] = any ? 1 : 0;
     if (any) atomicAdd(a.active + sweep_of_next, 1);
   }
 }
 
 // One round: G[nxt] = J^H G[cur] J (tile by tile), V <- V J in place, and the pivots of the next round.
-// Warp 0 of CTA p < np solves next round's pivot p; every other warp strides over the tile list (upper tiles of
-// G first: they cost twice a V tile).  Nothing in the kernel waits for anything else in it.
-// Layouts that keep the pivot warps away from the tile updates' DMMAs (dedicated pivot CTAs at 8 pivots per SM,
-// or 16-warp CTAs with the pivot's SM sub-partition otherwise idle) were measured and were not faster at
+// Warps 0 and 1 of CTA p < np (two SM sub-partitions) solve next round's pivot p together; every other warp strides
+// over the tile list (upper tiles of G first: they cost twice a V tile).  Nothing in the kernel waits for anything
+// else in it.  Layouts that keep the pivot warps away from the tile updates' DMMAs (dedicated pivot CTAs at 8 pivots
+// per SM, or 16-warp CTAs with the pivot's SM sub-partition otherwise idle) were measured and were not faster at
 // m = 1025: what the pivot chain gains, the tile updates lose in workers (profiles/r1_jacobi_wide_layouts.log).
 // Every tile-update warp runs a two-stage pipeline over its tasks: the source tile of task t + 1 is on its way into
 // shared memory (cp.async) while task t is in the DMMA pipe (ncu before this: long-scoreboard stalls 8.4 warps per
 // issue against 3.8 for the math pipe, DMMA pipe 42 % active).
 // Dynamic shared memory: 8 warps x 2 staging buffers (TS_WARP doubles each) + PIV_SM doubles.
 constexpr int WIDE_WARPS = 8;
+constexpr int WIDE_PIVOT_WARPS = 2;  // warps 0 and 1 of a pivot CTA (two SM sub-partitions) share one pivot solve
 template <int JBW>
 constexpr int wide_smem_doubles() {
   return WIDE_WARPS * 2 * WideCfg<JBW>::TS_WARP + WideCfg<JBW>::PIV_SM;
@@ -592,17 +609,18 @@ __global__ void __launch_bounds__(WIDE_WARPS * 32, 2) jacobi_round_w_kernel(cons
   __syncthreads();
   double* stage = dyn_sm + warp * 2 * C::TS_WARP;
   const bool pivot_cta = (int)blockIdx.x < np;
-  if (pivot_cta && warp == 0) {
+  if (pivot_cta && warp < WIDE_PIVOT_WARPS) {
     if (!(diag & 1))
-      next_pivot_w<JBW>(a, Sr_, Si_, r, rho, blockIdx.x, cur, (g + 1) / R, stage, dyn_sm + WIDE_WARPS * 2 * C::TS_WARP,
-                        lane);
+      next_pivot_w<JBW, WIDE_PIVOT_WARPS>(a, Sr_, Si_, r, rho, blockIdx.x, cur, (g + 1) / R, dyn_sm,
+                                          dyn_sm + WIDE_WARPS * 2 * C::TS_WARP, threadIdx.x);
     return;
   }
   if (diag & 2) return;
   // Tile-update warps are numbered over the grid, skipping the pivot warps and (experiment, diag bits 2 and 3)
   // the warps that would share the pivot warp's SM sub-partition: warp 4 of the pivot CTAs, and warps 0 and 4 of
   // the CTAs that are presumably co-resident with them (blockIdx.x + sm_count).
-  const unsigned mask_p = (diag & 4) ? 0xEEu : 0xFEu, mask_q = (diag & 8) ? 0xEEu : 0xFFu;
+  constexpr unsigned PIV = (1u << WIDE_PIVOT_WARPS) - 1u;  // pivot warps of a pivot CTA
+  const unsigned mask_p = 0xFFu & ~(PIV | ((diag & 4) ? PIV << 4 : 0u)), mask_q = (diag & 8) ? 0xFFu & ~(PIV | PIV << 4) : 0xFFu;
   const int ps = a.sm_count, gx = (int)gridDim.x, bx = (int)blockIdx.x;
   auto clampi = [](int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); };
   auto workers_before = [&](int b) {

@@ -663,9 +663,9 @@ static int heev_jacobi_wide(nls_ctx* ctx, const double* A, int m, double scale, 
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   if (!ctx->jac_stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->jac_stream, cudaStreamNonBlocking));
   // Timing experiments only (results are then meaningless): bit 0 skips the pivot solves, bit 1 the tile updates.
-  // Bit 2 idles warp 4 of the pivot CTAs (it shares the pivot warp's SM sub-partition): 26.1 vs 28.1 ms at m = 1025,
-  // a wash at m = 513, 2.5 % slower at m = 2049 where the tile updates dominate; bit 3 additionally idles the
-  // presumably co-resident CTA's warps 0 and 4 and never paid off (profiles/r1d_jacobi_wide_layouts.log).
+  // Bit 2 idles warps 4 and 5 of the pivot CTAs (they share the two pivot warps' SM sub-partitions): 24.4 vs 24.6 ms
+  // at m = 1025, 7.4 vs 8.0 ms at m = 513, but 190 vs 176 ms at m = 2049 where the tile updates dominate; bit 3
+  // additionally idles the presumably co-resident CTA's warps and never paid off (profiles/r1d_jacobi_*.log).
   const char* diag_env = getenv("NLS_JACOBI_DIAG");
   const int diag = diag_env ? atoi(diag_env) & 15 : (np <= 100 ? 4 : 0);
   const int graph_code = -(1 << 24) - ((nb * 64 + JBW * 4) * 16 + diag);

@@ -10,25 +10,27 @@ using namespace nls;
 constexpr int JBW = 8;
 using C = WideCfg<JBW>;
 
+template <int NW>
 __global__ void solve_kernel(const double* S_in, double* J_out, double* S_out, long long* cycles, double thr, int cross,
                              int inner, int reps) {
   extern __shared__ double sm[];
-  const int lane = threadIdx.x & 31;
+  const int tid = threadIdx.x;
   constexpr int P = C::P, SP = C::SP;
   const double* Sb = S_in + (size_t)blockIdx.x * C::JSZ;
   long long t = 0;
   for (int rep = 0; rep < reps; ++rep) {
-    for (int e = lane; e < P * P; e += 32) {
+    for (int e = tid; e < P * P; e += 32 * NW) {
       sm[(e / P) * SP + e % P] = Sb[e];
       sm[P * SP + (e / P) * SP + e % P] = Sb[P * P + e];
     }
-    __syncwarp();
+    __syncthreads();
     const long long t0 = clock64();
-    pivot_rotate_w<JBW>(sm, thr, cross != 0, inner, lane);
+    pivot_rotate_w<JBW, NW>(sm, thr, cross != 0, inner, tid);
     t += clock64() - t0;
+    __syncthreads();
   }
-  pivot_store_w<JBW>(sm, J_out + (size_t)blockIdx.x * C::JSZ, S_out + (size_t)blockIdx.x * C::JSZ, lane);
-  if (lane == 0) cycles[blockIdx.x] = t / reps;
+  pivot_store_w<JBW, NW>(sm, J_out + (size_t)blockIdx.x * C::JSZ, S_out + (size_t)blockIdx.x * C::JSZ, tid);
+  if (tid == 0) cycles[blockIdx.x] = t / reps;
 }
 
 __global__ void lat_kernel(double* out, long long* cyc, double x) {
@@ -75,9 +77,11 @@ int main() {
   double *dS, *dJ, *dSo; long long* dC;
   cudaMalloc(&dS, S.size() * 8); cudaMalloc(&dJ, S.size() * 8); cudaMalloc(&dSo, S.size() * 8); cudaMalloc(&dC, nblk * 8);
   cudaMemcpy(dS, S.data(), S.size() * 8, cudaMemcpyHostToDevice);
+  for (int nw = 1; nw <= 2; ++nw)
   for (int cross = 0; cross < 2; ++cross)
     for (int inner = 1; inner <= 8; inner *= 8) {
-      solve_kernel<<<nblk, 32, C::PIV_SM * 8>>>(dS, dJ, dSo, dC, 1e-30, cross, inner, 20);
+      if (nw == 1) solve_kernel<1><<<nblk, 32, C::PIV_SM * 8>>>(dS, dJ, dSo, dC, 1e-30, cross, inner, 20);
+      else solve_kernel<2><<<nblk, 64, C::PIV_SM * 8>>>(dS, dJ, dSo, dC, 1e-30, cross, inner, 20);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(e)); return 1; }
       std::vector<double> J(S.size()), So(S.size()); std::vector<long long> cyc(nblk);
@@ -102,7 +106,7 @@ int main() {
           }
         cmax = cyc[b] > cmax ? cyc[b] : cmax;
       }
-      printf("cross=%d inner=%d : cycles/solve %lld  |J^H J - I| %.2e  |J^H S J - S_final| %.2e  max offdiag %.2e\n", cross,
+      printf("warps=%d cross=%d inner=%d : cycles/solve %lld  |J^H J - I| %.2e  |J^H S J - S_final| %.2e  max offdiag %.2e\n", nw, cross,
              inner, cmax, uni, res, off);
     }
   return 0;
