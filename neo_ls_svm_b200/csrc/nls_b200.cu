@@ -95,7 +95,7 @@ struct nls_ctx {
   // scratch (grow-only, zero-filled when (re)allocated)
   DevBuf xc, wt, psi, psiT, pu, bt, rt, small, part, gram_ws, border, rowtmp, solver_ws, solver_mat;
   // dual path (state kept between nls_dual_sweep and nls_dual_finalize)
-  DevBuf jac_mat, jac_small, bs_part, bs_keys;
+  DevBuf jac_mat, jac_small, bs_part, bs_keys, dotpart;
   DevBuf d_xpad, d_xq, d_norm, d_fm, d_sq, d_sqt, d_g1, d_ab, d_ra, d_vec, d_ng, d_kq, d_btp;
   int dual_n = 0;
   // profiling
@@ -245,7 +245,8 @@ static int prep_weights(nls_ctx* ctx, const MapGeom& g, const double* W) {
 
 // Feature map of `rows` rows starting at X into `out` with the given layout.
 static int feature_chunk(nls_ctx* ctx, const MapGeom& g, const double* X, const double* shift, int rows, int layout,
-                         double* out, long long ld, int plane_stride, const double* row_scale) {
+                         double* out, long long ld, int plane_stride, const double* row_scale,
+                         const RowDots* dots = nullptr) {
   center_rows_kernel<<<grid_for((long long)rows * g.dpad), 256, 0, ctx->stream>>>(X, shift, rows, g.d, g.dpad,
                                                                                  (double*)ctx->xc.p);
   NLS_TRY(check_launch(ctx, "center_rows_kernel"));
@@ -260,8 +261,22 @@ static int feature_chunk(nls_ctx* ctx, const MapGeom& g, const double* X, const 
   p.out = out;
   p.ld = ld;
   p.plane_stride = plane_stride;
+  if (dots) {
+    p.dots = *dots;
+  } else {
+    p.dots = RowDots{};
+    p.dots.count = 0;
+  }
   dim3 grid((g.D + BN - 1) / BN, (rows + BM - 1) / BM);
   return launch_gemm<MODE_REAL, OpFeatureMap>(ctx, p, grid, rows, g.D, NLS_PROF_FEATURE_MAP, "feature_map");
+}
+
+// Partials buffer of the fused row dot products: [feature tiles][2][chunk rows].
+static int rowdots_buffer(nls_ctx* ctx, const MapGeom& g, double** out) {
+  const size_t tiles = (size_t)(g.D + BN - 1) / BN;
+  NLS_TRY(ensure(ctx, ctx->dotpart, tiles * 2 * (size_t)ctx->chunk_rows * 8));
+  *out = (double*)ctx->dotpart.p;
+  return NLS_OK;
 }
 
 // Number of leading projection columns computed by 64-wide GEMM tiles.  When only a few columns spill into
@@ -345,7 +360,7 @@ extern "C" int nls_ctx_destroy(nls_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->xc, &ctx->wt, &ctx->psi, &ctx->psiT, &ctx->pu, &ctx->bt, &ctx->rt, &ctx->small,
                     &ctx->part, &ctx->gram_ws, &ctx->border, &ctx->rowtmp, &ctx->solver_ws, &ctx->solver_mat,
-                    &ctx->jac_mat, &ctx->jac_small, &ctx->bs_part, &ctx->bs_keys, &ctx->d_xpad, &ctx->d_xq, &ctx->d_norm, &ctx->d_fm, &ctx->d_sq, &ctx->d_sqt, &ctx->d_g1,
+                    &ctx->jac_mat, &ctx->jac_small, &ctx->bs_part, &ctx->bs_keys, &ctx->dotpart, &ctx->d_xpad, &ctx->d_xq, &ctx->d_norm, &ctx->d_fm, &ctx->d_sq, &ctx->d_sqt, &ctx->d_g1,
                     &ctx->d_ab, &ctx->d_ra, &ctx->d_vec, &ctx->d_ng, &ctx->d_kq, &ctx->d_btp};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
@@ -929,7 +944,21 @@ extern "C" int nls_primal_loo_sweep(nls_ctx* ctx, const double* X, const double*
   for (int64_t i0 = 0; i0 < n; i0 += cap) {
     const int rows = (int)std::min<int64_t>(cap, n - i0);
     const int mtiles = (rows + BM - 1) / BM;
-    NLS_TRY(feature_chunk(ctx, g, X + i0 * d, shift, rows, FM_PLANAR, (double*)ctx->psi.p, 2LL * g.Dp, g.Dp, nullptr));
+    // One spill column (m = D + 1, D a multiple of 64): its Re T / Im T are row dot products fused into the feature-map
+    // epilogue, so the chunk is not read a second time by a GEMV tail.
+    const int full_cols = tail_split(g.m);  // columns handled by 64-wide tiles
+    const bool fused_spill = g.m - full_cols == 1;
+    RowDots dots{};
+    if (fused_spill) {
+      const double* qr = bs.bt + (size_t)full_cols * g.Dp;
+      const double* qi = bs.bt + (size_t)(g.Np + full_cols) * g.Dp;
+      dots.x[0] = qr; dots.y[0] = qi; dots.ysign[0] = 1.0;   // Re((c - i s)(a + i b)) = c a + s b
+      dots.x[1] = qi; dots.y[1] = qr; dots.ysign[1] = -1.0;  // Im                     = c b - s a
+      dots.stride = 1; dots.count = 2; dots.ld = cap;
+      NLS_TRY(rowdots_buffer(ctx, g, &dots.out));
+    }
+    NLS_TRY(feature_chunk(ctx, g, X + i0 * d, shift, rows, FM_PLANAR, (double*)ctx->psi.p, 2LL * g.Dp, g.Dp, nullptr,
+                          fused_spill ? &dots : nullptr));
     OpProject::Params pp;
     pp.A = psi_operand(ctx, g, rows);
     pp.B = basis_operand(g, bs.bt);
@@ -943,11 +972,16 @@ extern "C" int nls_primal_loo_sweep(nls_ctx* ctx, const double* X, const double*
     pp.P = P;
     pp.U = U;
     pp.ld = g.ldp;
-    const int full_cols = tail_split(g.m);  // columns handled by 64-wide tiles; the rest by the GEMV tail
     pp.m = full_cols;
     NLS_TRY((launch_gemm<MODE_COMPLEX, OpProject>(ctx, pp, dim3((full_cols + BN - 1) / BN, mtiles), rows, 2 * g.Np,
                                                    NLS_PROF_PROJECT, "project")));
-    if (full_cols < g.m) {
+    if (fused_spill) {
+      ProfScope scope(ctx, NLS_PROF_PROJECT);
+      project_spill_kernel<<<(rows + 255) / 256, 256, 0, ctx->stream>>>(dots.out, (g.D + BN - 1) / BN, cap, rows, full_cols,
+                                                                       bs.bias_r, bs.bias_i, bs.v_r, bs.v_i, inv_c, P, U,
+                                                                       g.ldp);
+      NLS_TRY(check_launch(ctx, "project_spill_kernel"));
+    } else if (full_cols < g.m) {
       ProfScope scope(ctx, NLS_PROF_PROJECT);
       project_tail_kernel<<<(rows * 32 + 255) / 256, 256, 0, ctx->stream>>>(
           (const double*)ctx->psi.p, 2LL * g.Dp, g.Dp, rows, D, bs.bt, g.Dp, g.Np, full_cols, g.m, bs.bias_r, bs.bias_i, 0,
@@ -1032,14 +1066,30 @@ extern "C" int nls_primal_finalize(nls_ctx* ctx, const double* X, const double* 
   double* sigma2_tmp = (double*)ctx->rowtmp.p;
   double* num = sigma2_tmp + cap;
   double* fit = num + cap;
+  // With the sigma^2 stash the only thing this pass needs from phi is Re(phi beta) for the two coefficient vectors:
+  // they are accumulated in the feature-map epilogue and the chunk is neither written nor read back.
+  RowDots dots{};
+  if (sigma2_in) {
+    dots.x[0] = beta_eig; dots.y[0] = beta_eig + 1; dots.ysign[0] = 1.0;
+    dots.x[1] = beta;     dots.y[1] = beta + 1;     dots.ysign[1] = 1.0;
+    dots.stride = 2; dots.count = 2; dots.ld = cap;
+    NLS_TRY(rowdots_buffer(ctx, g, &dots.out));
+  }
   for (int64_t i0 = 0; i0 < n; i0 += cap) {
     const int rows = (int)std::min<int64_t>(cap, n - i0);
-    NLS_TRY(feature_chunk(ctx, g, X + i0 * d, shift, rows, FM_PLANAR, (double*)ctx->psi.p, 2LL * g.Dp, g.Dp, nullptr));
     const double* sigma2 = sigma2_in ? sigma2_in + i0 : sigma2_tmp;
-    if (!sigma2_in) NLS_TRY(variance_chunk(ctx, g, bs, rows, sigma2_tmp));
-    gemv_pair_kernel<<<(rows * 32 + 255) / 256, 256, 0, ctx->stream>>>((const double*)ctx->psi.p, 2LL * g.Dp, g.Dp,
-                                                                      rows, D, beta_eig, beta, num, fit);
-    NLS_TRY(check_launch(ctx, "gemv_pair_kernel"));
+    if (sigma2_in) {
+      NLS_TRY(feature_chunk(ctx, g, X + i0 * d, shift, rows, FM_NONE, nullptr, 0, 0, nullptr, &dots));
+      rowdots_reduce_kernel<<<(rows + 255) / 256, 256, 0, ctx->stream>>>(dots.out, (g.D + BN - 1) / BN, cap, rows,
+                                                                        beta_eig + 2 * D, beta + 2 * D, num, fit);
+      NLS_TRY(check_launch(ctx, "rowdots_reduce_kernel"));
+    } else {
+      NLS_TRY(feature_chunk(ctx, g, X + i0 * d, shift, rows, FM_PLANAR, (double*)ctx->psi.p, 2LL * g.Dp, g.Dp, nullptr));
+      NLS_TRY(variance_chunk(ctx, g, bs, rows, sigma2_tmp));
+      gemv_pair_kernel<<<(rows * 32 + 255) / 256, 256, 0, ctx->stream>>>((const double*)ctx->psi.p, 2LL * g.Dp, g.Dp,
+                                                                        rows, D, beta_eig, beta, num, fit);
+      NLS_TRY(check_launch(ctx, "gemv_pair_kernel"));
+    }
     finalize_rows_kernel<<<(rows + 255) / 256, 256, 0, ctx->stream>>>(rows, y + i0, s + i0, sigma2, num, fit,
                                                                      is_classifier, loo_res_out + i0,
                                                                      yhat_loo_out + i0, leverage_out + i0,
@@ -1066,14 +1116,22 @@ extern "C" int nls_primal_predict(nls_ctx* ctx, const double* X, int64_t n, int 
   NLS_TRY(ensure(ctx, ctx->psi, (size_t)cap * 2 * g.Dp * 8));
   NLS_TRY(ensure(ctx, ctx->rowtmp, (size_t)3 * cap * 8));
   double* sigma2 = (double*)ctx->rowtmp.p;
+  // yhat = Re(phi beta) rides in the feature-map epilogue; without sigma_out the chunk is not even written.
+  RowDots dots{};
+  if (yhat_out) {
+    dots.x[0] = beta; dots.y[0] = beta + 1; dots.ysign[0] = 1.0;
+    dots.x[1] = beta; dots.y[1] = beta + 1; dots.ysign[1] = 1.0;
+    dots.stride = 2; dots.count = 1; dots.ld = cap;
+    NLS_TRY(rowdots_buffer(ctx, g, &dots.out));
+  }
   for (int64_t i0 = 0; i0 < n; i0 += cap) {
     const int rows = (int)std::min<int64_t>(cap, n - i0);
-    NLS_TRY(feature_chunk(ctx, g, X + i0 * d, shift, rows, FM_PLANAR, (double*)ctx->psi.p, 2LL * g.Dp, g.Dp, nullptr));
+    NLS_TRY(feature_chunk(ctx, g, X + i0 * d, shift, rows, sigma_out ? FM_PLANAR : FM_NONE, (double*)ctx->psi.p,
+                          2LL * g.Dp, g.Dp, nullptr, yhat_out ? &dots : nullptr));
     if (yhat_out) {
-      gemv_pair_kernel<<<(rows * 32 + 255) / 256, 256, 0, ctx->stream>>>((const double*)ctx->psi.p, 2LL * g.Dp, g.Dp,
-                                                                        rows, D, beta, nullptr, yhat_out + i0,
-                                                                        nullptr);
-      NLS_TRY(check_launch(ctx, "gemv_pair_kernel"));
+      rowdots_reduce_kernel<<<(rows + 255) / 256, 256, 0, ctx->stream>>>(dots.out, (g.D + BN - 1) / BN, cap, rows,
+                                                                        beta + 2 * D, nullptr, yhat_out + i0, nullptr);
+      NLS_TRY(check_launch(ctx, "rowdots_reduce_kernel"));
     }
     if (sigma_out) {
       NLS_TRY(variance_chunk(ctx, g, bs, rows, sigma2, b_upper));

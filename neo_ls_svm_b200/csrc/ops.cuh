@@ -82,7 +82,24 @@ __device__ __forceinline__ void loo_reduce(Acc& acc, const Tile& t, int n_rows, 
 // Stage 1: z = Xc . W^T-tile, epilogue (cos z, sin z)/sqrt(D) in one of three layouts.
 //   reference: _affine_feature_map.py:81-89 (z) and _feature_maps.py:201-202 (exp(-1j z)/sqrt(D)).
 // =============================================================================================
-enum { FM_PLANAR = 0, FM_TRANSPOSED = 1, FM_COMPLEX = 2 };
+enum { FM_PLANAR = 0, FM_TRANSPOSED = 1, FM_COMPLEX = 2, FM_NONE = 3 };
+
+// Optional fused row dot products of the feature-map epilogue: for up to two coefficient vectors q,
+//     dot_q[row] = sum_l ( c_l x_q[l * stride] + ysign_q s_l y_q[l * stride] )        (c, s = cos, sin / sqrt(D))
+// accumulated over the CTA tile's 64 features and written as one partial per feature tile,
+//     out[(feature_tile * 2 + q) * ld + row],
+// to be summed over the feature tiles in a fixed order by the consumer.  With (x, y) = (Re b, Im b), ysign = +1 this
+// is Re(phi b) (_neo_ls_svm.py:664); with (Re q, Im q, +1) and (Im q, Re q, -1) it is Re and Im of phi q.  It replaces
+// GEMV kernels that re-read the 16 D bytes per row of the feature chunk from HBM.
+struct RowDots {
+  const double* x[2];
+  const double* y[2];
+  double ysign[2];
+  int stride;
+  int count;      // 0 (off), 1 or 2
+  double* out;
+  long long ld;
+};
 
 struct OpFeatureMap {
   struct Params {
@@ -94,6 +111,7 @@ struct OpFeatureMap {
     double* out;
     long long ld;             // FM_PLANAR: row pitch (>= 2*Dp); FM_TRANSPOSED: pitch of a feature row
     int plane_stride;         // FM_PLANAR: column offset of the sin plane; FM_TRANSPOSED: row offset
+    RowDots dots;             // fused row dot products (count = 0: none); FM_NONE stores nothing else
   };
   static __device__ __forceinline__ Tile tile(const Params& p) {
     Tile t;
@@ -105,7 +123,30 @@ struct OpFeatureMap {
     return t;
   }
   static __device__ __forceinline__ void epilogue(const Params& p, const Tile& t, Acc& acc, int warp_m, int warp_n,
-                                                  int lane, uint8_t*) {
+                                                  int lane, uint8_t* scratch) {
+    const int ndots = p.dots.count;
+    double dsum[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dsum[i][0] = dsum[i][1] = 0.0;
+    // Coefficients of the fused dot products for the tile's 64 columns, staged once in shared memory as
+    // {x0, ysign0 y0, x1, ysign1 y1} per column (registers would push the kernel past 128 per thread and with that
+    // from two resident CTAs per SM to one: measured 94 -> 142 ms per fit for the three feature-map passes).
+    double4* coef = reinterpret_cast<double4*>(scratch);  // [BN]
+    if (ndots) {
+      const int tid = threadIdx.x;
+      if (tid < BN) {
+        const int col = t.n0 + tid;
+        const bool in = col < p.D;
+        const long long l = (long long)col * p.dots.stride;
+        double4 q;
+        q.x = in ? p.dots.x[0][l] : 0.0;
+        q.y = in ? p.dots.ysign[0] * p.dots.y[0][l] : 0.0;
+        q.z = (in && ndots > 1) ? p.dots.x[1][l] : 0.0;
+        q.w = (in && ndots > 1) ? p.dots.ysign[1] * p.dots.y[1][l] : 0.0;
+        coef[tid] = q;
+      }
+      __syncthreads();
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int row = t.m0 + acc_row(warp_m, i, lane);
@@ -121,7 +162,17 @@ struct OpFeatureMap {
           c[e] *= w;
           s[e] *= w;
         }
-        if (p.layout == FM_PLANAR) {
+        if (ndots) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const double4 q = coef[acc_col(warp_n, j, lane) + e];
+            dsum[i][0] += c[e] * q.x + s[e] * q.y;
+            dsum[i][1] += c[e] * q.z + s[e] * q.w;
+          }
+        }
+        if (p.layout == FM_NONE) {
+          // dot products only: the chunk itself is not needed by any later kernel
+        } else if (p.layout == FM_PLANAR) {
           double* o = p.out + (long long)row * p.ld + col;
           if (col + 1 < p.D) {
             *reinterpret_cast<double2*>(o) = make_double2(c[0], c[1]);
@@ -151,6 +202,33 @@ struct OpFeatureMap {
             last[1] = 0.0;
           }
         }
+      }
+    }
+    if (ndots) {  // uniform over the grid
+      // Row sums over the tile's 64 features in a fixed order: the 4 lanes of a row (butterfly), then the two
+      // column warps through shared memory.
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          dsum[i][q] += __shfl_xor_sync(0xffffffffu, dsum[i][q], 1);
+          dsum[i][q] += __shfl_xor_sync(0xffffffffu, dsum[i][q], 2);
+        }
+      double* red = reinterpret_cast<double*>(scratch) + 4 * BN;  // [2 warp_n][2 q][BM rows], after the coefficients
+      if ((lane & 3) == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = acc_row(warp_m, i, lane);
+          red[(warp_n * 2 + 0) * BM + r] = dsum[i][0];
+          red[(warp_n * 2 + 1) * BM + r] = dsum[i][1];
+        }
+      }
+      __syncthreads();
+      const int tid = threadIdx.x;
+      if (tid < ndots * BM) {
+        const int q = tid / BM, r = tid % BM, row = t.m0 + r;
+        if (row < p.n_rows)
+          p.dots.out[((long long)blockIdx.x * 2 + q) * p.dots.ld + row] = red[(0 * 2 + q) * BM + r] + red[(1 * 2 + q) * BM + r];
       }
     }
   }

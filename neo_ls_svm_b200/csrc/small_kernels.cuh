@@ -279,6 +279,41 @@ __global__ void project_tail_kernel(const double* __restrict__ psi, long long ld
   if (mode == 1 && lane == 0) part[warp] = acc;
 }
 
+// Sums the per-feature-tile partials of the fused row dot products (ops.cuh, RowDots) in tile order and adds the
+// constant feature's coefficient:  y_q[row] = sum_t part[(t * 2 + q) * ld + row] + bias_q.
+__global__ void rowdots_reduce_kernel(const double* __restrict__ part, int n_tiles, long long ld, int rows,
+                                      const double* __restrict__ bias1, const double* __restrict__ bias2,
+                                      double* __restrict__ y1, double* __restrict__ y2) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  double a1 = 0.0, a2 = 0.0;
+  for (int t = 0; t < n_tiles; ++t) {
+    a1 += part[((long long)t * 2 + 0) * ld + row];
+    if (y2) a2 += part[((long long)t * 2 + 1) * ld + row];
+  }
+  y1[row] = a1 + (bias1 ? bias1[0] : 0.0);
+  if (y2) y2[row] = a2 + (bias2 ? bias2[0] : 0.0);
+}
+
+// One spill column k of the projection T = phi B from the fused row dot products (Re T, Im T partials):
+//   P[row, k] = Re(T v_k), U[row, k] = |T|^2 inv_c      (stage 4a; replaces project_tail_kernel's re-read of the chunk)
+__global__ void project_spill_kernel(const double* __restrict__ part, int n_tiles, long long ld, int rows, int k,
+                                     const double* __restrict__ bias_r, const double* __restrict__ bias_i,
+                                     const double* __restrict__ v_r, const double* __restrict__ v_i, double inv_c,
+                                     double* __restrict__ P, double* __restrict__ U, long long ldp) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  double tr = 0.0, ti = 0.0;
+  for (int t = 0; t < n_tiles; ++t) {
+    tr += part[((long long)t * 2 + 0) * ld + row];
+    ti += part[((long long)t * 2 + 1) * ld + row];
+  }
+  tr += bias_r[k];
+  ti += bias_i[k];
+  P[(long long)row * ldp + k] = tr * v_r[k] - ti * v_i[k];
+  U[(long long)row * ldp + k] = (tr * tr + ti * ti) * inv_c;
+}
+
 // Per-row outputs at the selected gamma.  _neo_ls_svm.py:149-155, :167-169, :179-187.
 __global__ void finalize_rows_kernel(int rows, const double* __restrict__ y, const double* __restrict__ s,
                                      const double* __restrict__ sigma2, const double* __restrict__ num,
