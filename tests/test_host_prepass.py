@@ -122,3 +122,18 @@ def test_bin_layout_tiles_cover_each_bin_once():
         covered = np.concatenate([np.arange(r0, r1) for (bb, r0, r1, _) in tiles[t0:t1]])
         assert np.all(tiles[t0:t1, 0] == b) and np.all(tiles[t0:t1, 2] - tiles[t0:t1, 1] <= TILE_ROWS)
         np.testing.assert_array_equal(np.sort(perm[covered]), rows[b])
+
+
+def test_sample_bins_shortcut_equals_the_generic_quantiser():
+    """`sample_bins_quantized_ecdf` takes the distinct values/counts of the dense rank codes from a bincount
+    instead of sorting a second time; the bins must be those of the generic Quantizer (reference :246-253)."""
+    from neo_ls_svm_b200._quantizer import Quantizer, sample_bins_quantized_ecdf, unique_values
+
+    rng = np.random.default_rng(11)
+    for y in (rng.standard_normal(5000), np.round(rng.standard_normal(5000), 1), rng.exponential(2.0, 3000)):
+        distinct, codes = np.unique(y, return_inverse=True)
+        v, inv, cnt = unique_values(y, return_inverse=True, return_counts=True)  # small: the NumPy path
+        assert np.array_equal(v, distinct) and np.array_equal(inv, codes) and cnt.sum() == len(y)
+        expect = codes if len(distinct) <= np.ceil(np.sqrt(len(codes))) else \
+            Quantizer(dtype=np.intp).fit_transform(codes[:, np.newaxis]).ravel()
+        assert np.array_equal(sample_bins_quantized_ecdf(y), expect)
