@@ -84,7 +84,8 @@ struct nls_ctx {
   int eig_sweeps = 0;  // sweeps used by the last Jacobi solve
   cudaStream_t jac_stream = nullptr;  // side stream (graph capture is not allowed on the legacy default stream)
   cudaGraphExec_t jac_graph = nullptr;
-  const void* jac_graph_key = nullptr;
+  const void* jac_graph_key = nullptr;   // the captured graph bakes in the pointers of both Jacobi buffers:
+  const void* jac_graph_key2 = nullptr;  // jac_mat (key) and jac_small (key2); either one moving invalidates it
   int jac_graph_nb = 0;
   int jac_inner = 1;  // cyclic sweeps per 8x8 pivot solve (partial diagonalisation is enough for block Jacobi)
   bool jac_wide_attr = false;  // dynamic shared memory opt-in of the wide Jacobi kernels done on this device
@@ -684,7 +685,7 @@ static int heev_jacobi_wide(nls_ctx* ctx, const double* A, int m, double scale, 
   const char* diag_env = getenv("NLS_JACOBI_DIAG");
   const int diag = diag_env ? atoi(diag_env) & 15 : (np <= 100 ? 4 : 0);
   const int graph_code = -(1 << 24) - ((nb * 64 + JBW * 4) * 16 + diag);
-  if (!ctx->jac_graph || ctx->jac_graph_key != (const void*)base || ctx->jac_graph_nb != graph_code) {
+  if (!ctx->jac_graph || ctx->jac_graph_key != (const void*)base || ctx->jac_graph_key2 != (const void*)ctx->jac_small.p || ctx->jac_graph_nb != graph_code) {
     if (ctx->jac_graph) {
       cudaGraphExecDestroy(ctx->jac_graph);
       ctx->jac_graph = nullptr;
@@ -701,6 +702,7 @@ static int heev_jacobi_wide(nls_ctx* ctx, const double* A, int m, double scale, 
     cudaGraphDestroy(graph);
     if (ge != cudaSuccess) return fail(NLS_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ge));
     ctx->jac_graph_key = (const void*)base;
+    ctx->jac_graph_key2 = (const void*)ctx->jac_small.p;
     ctx->jac_graph_nb = graph_code;
   }
   int sweep = 0, h_active = 1, h_misc[4] = {1, 0, 0, 0};
@@ -780,7 +782,7 @@ static int heev_jacobi(nls_ctx* ctx, const double* A, int m, double scale, doubl
     jacobi_pivot_kernel<<<(np + 3) / 4, 128, 0, ctx->stream>>>(Gr, Gi, mp, nb, 0, thr, ctx->jac_inner, Jbuf, flags, active);
     NLS_TRY(check_launch(ctx, "jacobi_pivot_kernel"));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    if (!ctx->jac_graph || ctx->jac_graph_key != (const void*)Gr || ctx->jac_graph_nb != -(nb * 8 + fused_occ)) {
+    if (!ctx->jac_graph || ctx->jac_graph_key != (const void*)Gr || ctx->jac_graph_key2 != (const void*)ctx->jac_small.p || ctx->jac_graph_nb != -(nb * 8 + fused_occ)) {
       if (ctx->jac_graph) {
         cudaGraphExecDestroy(ctx->jac_graph);
         ctx->jac_graph = nullptr;
@@ -797,6 +799,7 @@ static int heev_jacobi(nls_ctx* ctx, const double* A, int m, double scale, doubl
       cudaGraphDestroy(graph);
       if (ge != cudaSuccess) return fail(NLS_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ge));
       ctx->jac_graph_key = (const void*)Gr;
+      ctx->jac_graph_key2 = (const void*)ctx->jac_small.p;
       ctx->jac_graph_nb = -(nb * 8 + fused_occ);  // negative: fused-round graph
     }
     for (; sweep < max_sweeps && h_active > 0; ++sweep) {
@@ -807,7 +810,7 @@ static int heev_jacobi(nls_ctx* ctx, const double* A, int m, double scale, doubl
     }
   } else {
     const int upd_grid = (int)std::min<long long>((tasks + 7) / 8, (long long)ctx->sm_count * 8);
-    if (!ctx->jac_graph || ctx->jac_graph_key != (const void*)Gr || ctx->jac_graph_nb != nb) {
+    if (!ctx->jac_graph || ctx->jac_graph_key != (const void*)Gr || ctx->jac_graph_key2 != (const void*)ctx->jac_small.p || ctx->jac_graph_nb != nb) {
       // Capture one sweep: reset the rotation counter, then nb-1 rounds of (pivot, update).
       if (ctx->jac_graph) {
         cudaGraphExecDestroy(ctx->jac_graph);
@@ -826,6 +829,7 @@ static int heev_jacobi(nls_ctx* ctx, const double* A, int m, double scale, doubl
       cudaGraphDestroy(graph);
       if (ge != cudaSuccess) return fail(NLS_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ge));
       ctx->jac_graph_key = (const void*)Gr;
+      ctx->jac_graph_key2 = (const void*)ctx->jac_small.p;
       ctx->jac_graph_nb = nb;
     }
     for (; sweep < max_sweeps && h_active > 0; ++sweep) {
