@@ -51,3 +51,16 @@ def test_product_package_never_imports_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_integration_stub_signatures_match_the_binding():
+    """The ctypes stub shown in INTEGRATION.md has the argument count of the real binding for every entry point."""
+    integ = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    binding = open(os.path.join(ROOT, "neo_ls_svm_b200", "_lib.py")).read()
+    found = re.findall(r"lib\.(nls_\w+)\.argtypes = \[([^\]]*)\]", integ)
+    assert len(found) >= 8
+    for name, args in found:
+        m = re.search(r'"%s": \(\[([^\]]*)\]' % name, binding)
+        assert m, f"{name} is not bound in _lib.py"
+        count = lambda text: len([a for a in text.split(",") if a.strip()])  # noqa: E731
+        assert count(args) == count(m.group(1)), name
