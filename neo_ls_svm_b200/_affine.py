@@ -225,6 +225,18 @@ class AffineNormalizer(AffineFeatureMap):
         return self
 
 
+def _weighted_draw(rng, p, size):
+    """`rng.choice(len(p), size=size, p=p)` of a legacy RandomState, without its validation passes over p.
+
+    Same algorithm (inverse-CDF lookup of `size` uniforms, numpy/random/mtrand.pyx) and therefore the same
+    indices and the same generator state afterwards; p is a probability vector built a line earlier from
+    validated sample weights, so re-checking it costs three more passes over up to n elements per call.
+    """
+    cdf = np.cumsum(p)
+    cdf /= cdf[-1]
+    return np.searchsorted(cdf, rng.random_sample(size), side="right")
+
+
 def pairwise_distances(X, Y):
     """Squared Euclidean distances between the rows of X and Y."""
     return np.sum(X * X, axis=1, keepdims=True) - 2 * X @ Y.T + np.sum(Y * Y, axis=1, keepdims=True).T
@@ -290,22 +302,23 @@ class AffineSeparator(AffineNormalizer):
             return ((X[idx, :] - shift) / scale).astype(X.dtype)
 
         sizes = np.array([len(r) for r in rows])
+        sw_by_bin = [sw[r] for r in rows]  # gathered once; every bin's complement concatenates six of them
         directions, inside_edges, outside_edges = [], [], []
         for i in range(n_bins):
             own_rows = rows[i]
             p_own = np.ravel(s_bins[i])
-            seeds = normalised(own_rows[rng.choice(len(own_rows), size=E, p=p_own)])
+            seeds = normalised(own_rows[_weighted_draw(rng, p_own, E)])
             # Sample the complement of bin i ("vstack of the other bins", :150-156) through row indices.
             others = [j for j in range(n_bins) if j != i]
-            w_rest = np.hstack([sw[rows[j]] for j in others])
-            pick = rng.choice(len(w_rest), size=wide, p=np.ravel(w_rest) / np.sum(w_rest))
+            w_rest = np.hstack([sw_by_bin[j] for j in others])
+            pick = _weighted_draw(rng, np.ravel(w_rest) / np.sum(w_rest), wide)
             offsets = np.concatenate([[0], np.cumsum(sizes[others])])
             which = np.searchsorted(offsets, pick, side="right") - 1
             rest_rows = np.array([rows[others[b]][k - offsets[b]] for b, k in zip(which, pick)])
             rest_sample = normalised(rest_rows)
             # Points of the complement closest to bin i, then points of bin i closest to those.
             outside = nearest_neighbours(seeds, rest_sample)
-            own_sample = normalised(own_rows[rng.choice(len(own_rows), size=wide, p=p_own)])
+            own_sample = normalised(own_rows[_weighted_draw(rng, p_own, wide)])
             inside = nearest_neighbours(outside, own_sample)
             outside_edges.append(outside)
             inside_edges.append(inside)

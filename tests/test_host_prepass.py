@@ -137,3 +137,17 @@ def test_sample_bins_shortcut_equals_the_generic_quantiser():
         expect = codes if len(distinct) <= np.ceil(np.sqrt(len(codes))) else \
             Quantizer(dtype=np.intp).fit_transform(codes[:, np.newaxis]).ravel()
         assert np.array_equal(sample_bins_quantized_ecdf(y), expect)
+
+
+def test_weighted_draw_is_randomstate_choice():
+    """The validation-free inverse-CDF draw returns RandomState.choice's indices and leaves the same state."""
+    from neo_ls_svm_b200._affine import _weighted_draw
+
+    for trial in range(4):
+        n = 50_000 + 17 * trial
+        w = np.random.default_rng(trial).random(n) + (trial % 2)
+        p = w / w.sum()
+        r1, r2 = np.random.RandomState(42 + trial), np.random.RandomState(42 + trial)
+        a = r1.choice(n, size=1536, p=p)
+        b = _weighted_draw(r2, p, 1536)
+        assert np.array_equal(a, b) and r1.random_sample() == r2.random_sample()
