@@ -472,84 +472,84 @@ __device__ __forceinline__ void next_pivot_w(const WideArgs& a, const double* __
   const int nb = a.nb, np = nb / 2, ld = a.ld, nxt = cur ^ 1;
   const int lane = tid & 31;
   if (tid < 32) {
-  int bp, bq;
-  rr_pair(nb, rho, slot_next, bp, bq);
-  const int sa = rr_slot(nb, r, bp), sb = rr_slot(nb, r, bq);
-  int xa, ya, xb, yb;
-  rr_pair(nb, r, sa, xa, ya);
-  rr_pair(nb, r, sb, xb, yb);
-  const int oa = xa == bp ? 0 : JBW, ob = xb == bq ? 0 : JBW;  // local offsets of bp in pair sa, of bq in pair sb
-  const double* Sa = a.Sbuf + ((long long)cur * np + sa) * C::JSZ;
-  const double* Sb = a.Sbuf + ((long long)cur * np + sb) * C::JSZ;
-  double* Sr = psm;
-  double* Si = psm + P * SP;
-  // Same-pair entries (both diagonal blocks; everything when sa == sb, i.e. nb == 2): from the final S.
-  for (int e = lane; e < P * P; e += 32) {
-    const int x = e / P, y = e % P;
-    const bool x1 = x >= JBW, y1 = y >= JBW;
-    if (sa != sb && x1 != y1) continue;
-    const double* S = x1 ? Sb : Sa;
-    const int lx = (x1 ? ob : oa) + (x & (JBW - 1)), ly = (y1 ? ob : oa) + (y & (JBW - 1));
-    Sr[x * SP + y] = __ldcg(S + lx * P + ly);
-    Si[x * SP + y] = __ldcg(S + P * P + lx * P + ly);
-  }
-  if (sa != sb) {
-    // Cross block X = J_a[:, oa..]^H  G[I_a, I_b]  J_b[:, ob..]  (JBW x JBW; JBW == 8: one DMMA tile).
-    static_assert(JBW == 8, "cross-block assembly is written for 8-wide blocks");
-    const int fr = lane >> 2, fk = lane & 3;
-    const double* Ja = a.Jbuf + ((long long)cur * np + sa) * C::JSZ;
-    const double* Jb = a.Jbuf + ((long long)cur * np + sb) * C::JSZ;
-    double mr[2][KS], mi[2][KS], br[KS], bi[KS], cr[KS], ci[KS];
+    int bp, bq;
+    rr_pair(nb, rho, slot_next, bp, bq);
+    const int sa = rr_slot(nb, r, bp), sb = rr_slot(nb, r, bq);
+    int xa, ya, xb, yb;
+    rr_pair(nb, r, sa, xa, ya);
+    rr_pair(nb, r, sb, xb, yb);
+    const int oa = xa == bp ? 0 : JBW, ob = xb == bq ? 0 : JBW;  // local offsets of bp in pair sa, of bq in pair sb
+    const double* Sa = a.Sbuf + ((long long)cur * np + sa) * C::JSZ;
+    const double* Sb = a.Sbuf + ((long long)cur * np + sb) * C::JSZ;
+    double* Sr = psm;
+    double* Si = psm + P * SP;
+    // Same-pair entries (both diagonal blocks; everything when sa == sb, i.e. nb == 2): from the final S.
+    for (int e = lane; e < P * P; e += 32) {
+      const int x = e / P, y = e % P;
+      const bool x1 = x >= JBW, y1 = y >= JBW;
+      if (sa != sb && x1 != y1) continue;
+      const double* S = x1 ? Sb : Sa;
+      const int lx = (x1 ? ob : oa) + (x & (JBW - 1)), ly = (y1 ? ob : oa) + (y & (JBW - 1));
+      Sr[x * SP + y] = __ldcg(S + lx * P + ly);
+      Si[x * SP + y] = __ldcg(S + P * P + lx * P + ly);
+    }
+    if (sa != sb) {
+      // Cross block X = J_a[:, oa..]^H  G[I_a, I_b]  J_b[:, ob..]  (JBW x JBW; JBW == 8: one DMMA tile).
+      static_assert(JBW == 8, "cross-block assembly is written for 8-wide blocks");
+      const int fr = lane >> 2, fk = lane & 3;
+      const double* Ja = a.Jbuf + ((long long)cur * np + sa) * C::JSZ;
+      const double* Jb = a.Jbuf + ((long long)cur * np + sb) * C::JSZ;
+      double mr[2][KS], mi[2][KS], br[KS], bi[KS], cr[KS], ci[KS];
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-      const int col = pair_index_w<JBW>(xb, yb, 4 * ks + fk);
+      for (int ks = 0; ks < KS; ++ks) {
+        const int col = pair_index_w<JBW>(xb, yb, 4 * ks + fk);
+#pragma unroll
+        for (int rs = 0; rs < 2; ++rs) {
+          const long long o = (long long)pair_index_w<JBW>(xa, ya, rs * 8 + fr) * ld + col;
+          mr[rs][ks] = __ldcg(Gr + o);
+          mi[rs][ks] = __ldcg(Gi + o);
+        }
+        br[ks] = __ldcg(Jb + (4 * ks + fk) * P + ob + fr);
+        bi[ks] = __ldcg(Jb + P * P + (4 * ks + fk) * P + ob + fr);
+        cr[ks] = __ldcg(Ja + (4 * ks + fk) * P + oa + fr);
+        ci[ks] = __ldcg(Ja + P * P + (4 * ks + fk) * P + oa + fr);
+      }
+      double tr[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, ti[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int rs = 0; rs < 2; ++rs) {
+          dmma(tr[rs][0], tr[rs][1], mr[rs][ks], br[ks]);
+          dmma(tr[rs][0], tr[rs][1], -mi[rs][ks], bi[ks]);
+          dmma(ti[rs][0], ti[rs][1], mr[rs][ks], bi[ks]);
+          dmma(ti[rs][0], ti[rs][1], mi[rs][ks], br[ks]);
+        }
+      double* Tr = ts;
+      double* Ti = ts + P * TP;
+      __syncwarp();
 #pragma unroll
       for (int rs = 0; rs < 2; ++rs) {
-        const long long o = (long long)pair_index_w<JBW>(xa, ya, rs * 8 + fr) * ld + col;
-        mr[rs][ks] = __ldcg(Gr + o);
-        mi[rs][ks] = __ldcg(Gi + o);
+        *reinterpret_cast<double2*>(Tr + (rs * 8 + fr) * TP + 2 * fk) = make_double2(tr[rs][0], tr[rs][1]);
+        *reinterpret_cast<double2*>(Ti + (rs * 8 + fr) * TP + 2 * fk) = make_double2(ti[rs][0], ti[rs][1]);
       }
-      br[ks] = __ldcg(Jb + (4 * ks + fk) * P + ob + fr);
-      bi[ks] = __ldcg(Jb + P * P + (4 * ks + fk) * P + ob + fr);
-      cr[ks] = __ldcg(Ja + (4 * ks + fk) * P + oa + fr);
-      ci[ks] = __ldcg(Ja + P * P + (4 * ks + fk) * P + oa + fr);
-    }
-    double tr[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, ti[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+      __syncwarp();
+      double xr[2] = {0.0, 0.0}, xi[2] = {0.0, 0.0};
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-      for (int rs = 0; rs < 2; ++rs) {
-        dmma(tr[rs][0], tr[rs][1], mr[rs][ks], br[ks]);
-        dmma(tr[rs][0], tr[rs][1], -mi[rs][ks], bi[ks]);
-        dmma(ti[rs][0], ti[rs][1], mr[rs][ks], bi[ks]);
-        dmma(ti[rs][0], ti[rs][1], mi[rs][ks], br[ks]);
+      for (int ks = 0; ks < KS; ++ks) {
+        const double tbr = Tr[(4 * ks + fk) * TP + fr], tbi = Ti[(4 * ks + fk) * TP + fr];
+        dmma(xr[0], xr[1], cr[ks], tbr);
+        dmma(xr[0], xr[1], ci[ks], tbi);
+        dmma(xi[0], xi[1], cr[ks], tbi);
+        dmma(xi[0], xi[1], -ci[ks], tbr);
       }
-    double* Tr = ts;
-    double* Ti = ts + P * TP;
-    __syncwarp();
 #pragma unroll
-    for (int rs = 0; rs < 2; ++rs) {
-      *reinterpret_cast<double2*>(Tr + (rs * 8 + fr) * TP + 2 * fk) = make_double2(tr[rs][0], tr[rs][1]);
-      *reinterpret_cast<double2*>(Ti + (rs * 8 + fr) * TP + 2 * fk) = make_double2(ti[rs][0], ti[rs][1]);
+      for (int h = 0; h < 2; ++h) {  // X[fr][2 fk + h] and its conjugate transpose
+        Sr[fr * SP + JBW + 2 * fk + h] = xr[h];
+        Si[fr * SP + JBW + 2 * fk + h] = xi[h];
+        Sr[(JBW + 2 * fk + h) * SP + fr] = xr[h];
+        Si[(JBW + 2 * fk + h) * SP + fr] = -xi[h];
+      }
     }
-    __syncwarp();
-    double xr[2] = {0.0, 0.0}, xi[2] = {0.0, 0.0};
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-      const double tbr = Tr[(4 * ks + fk) * TP + fr], tbi = Ti[(4 * ks + fk) * TP + fr];
-      dmma(xr[0], xr[1], cr[ks], tbr);
-      dmma(xr[0], xr[1], ci[ks], tbi);
-      dmma(xi[0], xi[1], cr[ks], tbi);
-      dmma(xi[0], xi[1], -ci[ks], tbr);
-    }
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {  // X[fr][2 fk + h] and its conjugate transpose
-      Sr[fr * SP + JBW + 2 * fk + h] = xr[h];
-      Si[fr * SP + JBW + 2 * fk + h] = xi[h];
-      Sr[(JBW + 2 * fk + h) * SP + fr] = xr[h];
-      Si[(JBW + 2 * fk + h) * SP + fr] = -xi[h];
-    }
-  }
   }
   pivot_sync<NW>();
   // The pairs inside a block are rotated in the first round of a sweep only; every other pivot annihilates its
