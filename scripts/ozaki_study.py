@@ -28,15 +28,18 @@ from neo_ls_svm_b200.datasets import load_case  # noqa: E402
 from oracle import neo_oracle as orc  # noqa: E402
 
 
+RADIX = float(os.environ.get("OZAKI_RADIX", "128"))  # 128: signed 7-bit digits; 256: 8-bit digits (first signed, rest unsigned on hardware)
+
+
 def slices(X: np.ndarray, s: int):
-    """Digit planes of the rows of X: X ≈ scale[:, None] * Σ_p planes[p] * 128^-(p+1), |digits| ≤ 128."""
+    """Digit planes of the rows of X: X ≈ scale[:, None] * Σ_p planes[p] * RADIX^-(p+1), |digits| ≤ RADIX / 2."""
     amax = np.max(np.abs(X), axis=1)
     e = np.where(amax > 0, np.ceil(np.log2(np.where(amax > 0, amax, 1.0))) + 1, 0.0)  # |x| / 2^e ≤ 1/2
     scale = np.exp2(e)
     r = X / scale[:, None]
     planes = []
     for _ in range(s):
-        r = r * 128.0
+        r = r * RADIX
         q = np.rint(r)
         planes.append(q)
         r = r - q
@@ -54,7 +57,7 @@ def ozaki_mm(A: np.ndarray, B: np.ndarray, s: int) -> np.ndarray:
         acc = np.zeros_like(C)
         for p in range(t + 1):
             acc += Ap[p] @ Bp[t - p].T  # exact: integer-valued float64, |sum| < 2^53
-        C += acc * 128.0 ** -(t + 2)
+        C += acc * RADIX ** -(t + 2)
     return C * sa[:, None] * sb[None, :]
 
 
@@ -110,6 +113,7 @@ def rel(a, b):
 
 def main():
     cases = sys.argv[1:] or ["c1", "c3_small", "clf_small"]
+    print(f"digit radix {int(RADIX)}")
     for name in cases:
         with np.load(os.path.join(ROOT, "tests", "golden", f"{name}.npz")) as z:
             g = {k: z[k] for k in z.files}
@@ -124,7 +128,7 @@ def main():
               f"(golden {int(g['opt'])}), FP64 vs golden β̂ {rel(ref['beta'], g['beta']):.1e}, "
               f"best-vs-second LOO error gap {(margin[1] - margin[0]) / margin[0]:.1e}")
         print("   slices  int-GEMMs  γ index   A rel      λ rel      β̂ rel     LOO-curve rel  LOO-resid rel")
-        for s in (4, 5, 6, 7, 8, 9):
+        for s in ((4, 5, 6, 7, 8, 9) if RADIX == 128 else (4, 5, 6, 7)):
             out = fit(*args, s)
             print(f"   {s:6d}  {s * (s + 1) // 2:9d}  {out['opt']:7d}   {rel(out['A'], ref['A']):.1e}    {rel(out['lam'], ref['lam']):.1e}    "
                   f"{rel(out['beta'], ref['beta']):.1e}    {rel(out['loo_errors'], ref['loo_errors']):.1e}        "
