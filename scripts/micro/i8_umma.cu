@@ -23,7 +23,7 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return d;
 }
 
-template <int N>
+template <int N, bool B_UNSIGNED>
 __global__ void __launch_bounds__(128) i8_kernel(const int8_t* __restrict__ A, const int8_t* __restrict__ B,
                                                  int32_t* __restrict__ C, int K, int reps, long long* cyc) {
   extern __shared__ uint8_t smem_raw[];
@@ -33,9 +33,9 @@ __global__ void __launch_bounds__(128) i8_kernel(const int8_t* __restrict__ A, c
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_holder;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr uint32_t COLS = N < 32 ? 32 : N;  // power of two >= 32
+  constexpr uint32_t COLS = N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : N <= 256 ? 256 : 512;  // power of two >= 32
   // instruction descriptor: D = S32, A = B = signed 8 bit, both K-major, N, M
-  constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | ((B_UNSIGNED ? 0u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(COLS));
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(128) i8_kernel(const int8_t* __restrict__ A, c
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(COLS));
 }
 
-template <int N>
+template <int N, bool B_UNSIGNED>
 static int run(int K, int reps) {
   std::vector<int8_t> A((size_t)M * K), B((size_t)N * K);
   srand(7 + N);
@@ -138,8 +138,8 @@ static int run(int K, int reps) {
   cudaMemcpy(dB, B.data(), B.size(), cudaMemcpyHostToDevice);
   cudaMemset(dC, 0xff, (size_t)M * N * 4);
   const size_t smem = 1024 + (size_t)(M + N) * KB;
-  cudaFuncSetAttribute(i8_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  i8_kernel<N><<<1, 128, smem>>>(dA, dB, dC, K, reps, dcyc);
+  cudaFuncSetAttribute(i8_kernel<N, B_UNSIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  i8_kernel<N, B_UNSIGNED><<<1, 128, smem>>>(dA, dB, dC, K, reps, dcyc);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     printf("N=%d: CUDA error: %s\n", N, cudaGetErrorString(e));
@@ -153,13 +153,14 @@ static int run(int K, int reps) {
   for (int i = 0; i < M; ++i)
     for (int j = 0; j < N; ++j) {
       int32_t ref = 0;
-      for (int k = 0; k < K; ++k) ref += (int32_t)A[(size_t)i * K + k] * (int32_t)B[(size_t)j * K + k];
+      for (int k = 0; k < K; ++k)
+        ref += (int32_t)A[(size_t)i * K + k] * (B_UNSIGNED ? (int32_t)(uint8_t)B[(size_t)j * K + k] : (int32_t)B[(size_t)j * K + k]);
       if (ref != C[(size_t)i * N + j]) {
         if (first < 0) first = (long long)i * N + j;
         ++bad;
       }
     }
-  printf("N=%d K=%d: %lld of %d entries differ from the host INT32 product", N, K, bad, M * N);
+  printf("N=%d K=%d B %s: %lld of %d entries differ from the host INT32 product", N, K, B_UNSIGNED ? "unsigned" : "signed", bad, M * N);
   if (bad) printf(" (first at row %lld col %lld: got %d)", first / N, first % N, C[first]);
   const double ops = 2.0 * M * N * KB * (double)reps;
   printf("; %d x 4 MMAs in %lld cycles = %.0f INT8 op/cycle/SM\n", reps, cyc, cyc > 0 ? ops / (double)cyc : 0.0);
@@ -168,7 +169,8 @@ static int run(int K, int reps) {
 
 int main() {
   int rc = 0;
-  rc |= run<64>(256, 2000);
-  rc |= run<256>(256, 2000);
+  rc |= run<64, false>(256, 2000);
+  rc |= run<256, false>(256, 2000);
+  rc |= run<80, true>(256, 2000);  // radix-256 planes: signed x unsigned digits, N = 80 (6 accumulators fit TMEM)
   return rc;
 }
