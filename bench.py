@@ -40,7 +40,7 @@ sys.path.insert(0, ROOT)
 METRIC = "NeoLSSVM primal fit rows/s"
 N_ROWS, N_FEATURES, N_INFORMATIVE, NUM_RFF, N_GAMMAS = 4_000_000, 64, 32, 1024, 1024
 PREPASS_ROWS = 100_000
-CPU_SAMPLE_ROWS = 16_384
+CPU_SAMPLE_ROWS = 100_000  # the reference CPU path is timed on the first 100,000 rows
 
 
 def flops_per_row(d: int, D: int, G: int) -> float:
@@ -108,49 +108,127 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_rows_per_s(shift, W, rows: int, steps: int, warmup: int) -> tuple[float, int]:
-    """Time the CPU port of the reference algorithm (transform + _optimize_β̂_γ) on `rows` rows."""
-    from threadpoolctl import threadpool_info
+def _load_datasets_module():
+    """neo_ls_svm_b200/datasets.py loaded as a stand-alone module (NumPy only): the reference arm must not import
+    the product package, let alone its CUDA library."""
+    import importlib.util
 
-    from neo_ls_svm_b200.datasets import fast_regression_rows
+    spec = importlib.util.spec_from_file_location("_nls_bench_datasets", os.path.join(ROOT, "neo_ls_svm_b200", "datasets.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def bench_map(d: int, D: int):
+    """(shift, W) shared by both arms: the REFERENCE's OrthogonalRandomFourierFeatures(1024) fitted on the first
+    100,000 rows of the bench dataset (tests/golden/bench_c3_map.npz, written by `oracle/gen_golden.py bench_map`)."""
+    with np.load(os.path.join(ROOT, "tests", "golden", "bench_c3_map.npz")) as z:
+        shift, W = z["shift"], z["W"]
+    assert shift.shape == (d,) and W.shape == (d, D), "the committed map is for the C3 shape"
+    return np.ascontiguousarray(shift), np.ascontiguousarray(W)
+
+
+def _import_reference():
+    """The unmodified reference package, if this machine has it (`baseline/_ref` or /root/reference/src)."""
+    os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/nls_numba_cache")
+    sys.dont_write_bytecode = True
+    for cand in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference/src"):
+        if os.path.isdir(os.path.join(cand, "neo_ls_svm")):
+            sys.path.insert(0, cand)
+            try:
+                import neo_ls_svm  # noqa: F401
+
+                return cand
+            except Exception:  # noqa: BLE001
+                sys.path.remove(cand)
+    return None
+
+
+def make_cpu_step(rows: int):
+    """One pass of the reference's CPU hot path (feature-map transform + `_optimize_β̂_γ`) over the first `rows` rows
+    of the C3 dataset, given the fitted map.  Returns (step, kind, detail): the unmodified reference when it is
+    importable on this machine, else the oracle port (the reference is pure Python and cannot travel)."""
+    ds = _load_datasets_module()
+    X, y = ds.fast_regression_rows(N_ROWS, N_FEATURES, N_INFORMATIVE, row_begin=0, row_end=rows)
+    s = np.ones(rows)
+    shift, W = bench_map(N_FEATURES, NUM_RFF)
+    where = _import_reference()
+    if where is not None:
+        from neo_ls_svm import NeoLSSVM
+        from neo_ls_svm._feature_maps import OrthogonalRandomFourierFeatures
+
+        fm = OrthogonalRandomFourierFeatures(num_features=NUM_RFF).fit(X[:2048], y[:2048], s[:2048])  # untimed; map overwritten
+        aff = fm.affine_feature_map
+        aff.shift_, aff.scale_, aff.A_ = shift.reshape(1, -1).copy(), np.ones((1, N_FEATURES)), W.copy()
+        model = NeoLSSVM(primal_feature_map=fm, dual=False)
+        model._estimator_type = "regressor"
+
+        def step():
+            phi = fm.transform(X)  # _neo_ls_svm.py:386
+            C = fm.complexity_matrix.astype(phi.dtype)  # :401
+            return model._optimize_β̂_γ(φ=phi, y=y, s=s, C=C)  # :402
+
+        return step, "reference", f"unmodified neo_ls_svm from {where}"
     from oracle import neo_oracle as orc
 
-    X, y = fast_regression_rows(N_ROWS, N_FEATURES, N_INFORMATIVE, row_begin=0, row_end=rows)
-    s = np.ones(rows)
-
-    def once():
+    def step():
         phi = orc.fourier_map((X - shift[None, :]) @ W)  # _affine_feature_map.py:88 + _feature_maps.py:197-203
         return orc.primal_fit_materialised(phi, y, s, classifier=False)
 
+    return step, "port", "oracle/neo_oracle.py (NumPy/SciPy restatement of the reference, operation for operation)"
+
+
+def cpu_reference_rows_per_s(rows: int, steps: int, warmup: int):
+    """Time `steps` passes after `warmup` untimed ones -> (rows/s, BLAS threads, kind, detail)."""
+    from threadpoolctl import threadpool_info
+
+    step, kind, detail = make_cpu_step(rows)
     for _ in range(warmup):
-        once()
+        step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        once()
+        step()
     dt = time.perf_counter() - t0
     threads = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
-    return rows * steps / dt, threads
+    return rows * steps / dt, threads, kind, detail
+
+
+def _all_host_threads() -> None:
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm is a CPU measurement and gets every host
+    core at every N, so the interpreter is re-executed once with the thread caps lifted (before NumPy loads)."""
+    want = str(os.cpu_count() or 1)
+    if os.environ.get("NLS_REF_THREADS_SET") == "1":
+        return
+    env = dict(os.environ)
+    env["NLS_REF_THREADS_SET"] = "1"
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMBA_NUM_THREADS"):
+        env[var] = want
+    os.execve(sys.executable, [sys.executable] + sys.argv, env)
 
 
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    shift, W = fit_feature_map(N_FEATURES, NUM_RFF, min(PREPASS_ROWS, 50_000))
-    rows = CPU_SAMPLE_ROWS
+    _all_host_threads()
+    rows = args.cpu_rows
+    warmup = min(args.warmup, 1)
     t0 = time.perf_counter()
-    value, threads = cpu_reference_rows_per_s(shift, W, rows, args.steps, min(args.warmup, 1))
+    value, threads, kind, detail = cpu_reference_rows_per_s(rows, args.steps, warmup)
     ms_per_step = 1e3 * rows / value
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"C3 primal fit n=4M d={N_FEATURES} m={NUM_RFF} G={N_GAMMAS} (reference CPU algorithm, "
-                               f"bounded sample of {rows} rows per step; cost is linear in n)"},
-        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": "port",
-                         "sample": f"first {rows} rows of the C3 dataset, transform + _optimize_β̂_γ, NumPy/SciPy/OpenBLAS"},
+                               f"bounded sample of {rows} rows per step as BASELINE.md §3 prescribes; cost is linear in n)",
+                   "feature_map": "tests/golden/bench_c3_map.npz (the map both arms use)"},
+        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": kind,
+                         "sample": f"first {rows} rows of the C3 dataset, feature-map transform + _optimize_β̂_γ; {detail}",
+                         "host_cpus": os.cpu_count()},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+        "native_imported": sorted(m for m in sys.modules if m.startswith("neo_ls_svm_b200")),
     }
     print(json.dumps(line))
 
@@ -171,7 +249,7 @@ def run_ours(args) -> None:
         dist.init_process_group("nccl", device_id=dev)
     n, d, D = args.rows, N_FEATURES, NUM_RFF
     r0, r1 = rank * n // world, (rank + 1) * n // world
-    shift, W = fit_feature_map(d, D, min(PREPASS_ROWS, n))
+    shift, W = bench_map(d, D)  # the reference's own fitted map, shared with the reference arm
     X, y = fast_regression_rows(n, d, N_INFORMATIVE, row_begin=r0, row_end=r1)
     s = np.full(r1 - r0, 1.0 / n)  # uniform weights normalised by the global sum (:110)
     # Pinned host copies for the end-to-end measurement.
@@ -213,14 +291,17 @@ def run_ours(args) -> None:
     peak_tflops = max(peak_burst, peak_sustained)
     sampler = ClockSampler(local_rank)
     launches0 = ctx.launch_count()
-    ctx.profile(True)
     if rank == 0:
         sampler.start()
-    ms_total = timed(lambda: solve(Xd, yd, sd), args.steps)
+    ms_total = timed(lambda: solve(Xd, yd, sd), args.steps)  # per-launch event profiling is OFF in the timed region
     clocks = sampler.stop() if rank == 0 else {}
+    launches = torch.tensor([ctx.launch_count() - launches0], dtype=torch.float64, device=dev)
+    # Per-kernel device times for the roofline: a separate pass over the same K steps with CUDA events around every
+    # GEMM launch (they cost ~1% of a step, which is why they are kept out of `value`).
+    ctx.profile(True)
+    timed(lambda: solve(Xd, yd, sd), args.steps)
     prof = ctx.profile_read()
     ctx.profile(False)
-    launches = torch.tensor([ctx.launch_count() - launches0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(launches)
     value = n * args.steps / (ms_total * 1e-3)
@@ -300,10 +381,10 @@ def run_ours(args) -> None:
         kernel_share = {k: v["ms"] for k, v in prof.items()}
         cpu = None
         if world == 1:
-            v, threads = cpu_reference_rows_per_s(shift, W, CPU_SAMPLE_ROWS, 1, 1)
-            cpu = {"value": v, "unit": "rows/s", "cores": threads, "kind": "port",
-                   "sample": f"first {CPU_SAMPLE_ROWS} rows of the same dataset, reference algorithm (transform + "
-                             f"_optimize_β̂_γ) restated in NumPy/SciPy, 1 timed pass after 1 warm-up"}
+            v, threads, kind, detail = cpu_reference_rows_per_s(args.cpu_rows, 1, 1)
+            cpu = {"value": v, "unit": "rows/s", "cores": threads, "kind": kind, "host_cpus": os.cpu_count(),
+                   "sample": f"first {args.cpu_rows} rows of the same dataset, feature-map transform + _optimize_β̂_γ, "
+                             f"1 timed pass after 1 warm-up; {detail}"}
         line = {
             "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -313,7 +394,8 @@ def run_ours(args) -> None:
                 "rows_per_gpu": rows_local, "chunk_rows": int(os.environ.get("NLS_CHUNK_ROWS", 32768)),
                 "cache": "inputs larger than L2 (X shard %.0f MB; every chunk's feature/projection buffers "
                          "stream through HBM)" % x_shard_mb,
-                "feature_map": f"OrthogonalRandomFourierFeatures({D}) fitted on the first {min(PREPASS_ROWS, n)} rows (host pre-pass, untimed)",
+                "feature_map": f"OrthogonalRandomFourierFeatures({D}) fitted by the reference on the first {PREPASS_ROWS} rows "
+                               "(tests/golden/bench_c3_map.npz; both arms use it)",
                 "selected_gamma_index": fit.opt,
                 "eigensolver": args.eig, "jacobi_sweeps": ctx.last_eig_sweeps(),
             },
@@ -351,6 +433,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--rows", type=int, default=N_ROWS, help="total training rows (default: config C3)")
+    ap.add_argument("--cpu-rows", type=int, default=CPU_SAMPLE_ROWS,
+                    help="rows per step of the CPU reference measurement (BASELINE.md §3: 100,000)")
     ap.add_argument("--skip-api", action="store_true", help="skip the public-API NeoLSSVM.fit timing (N=1 arm)")
     ap.add_argument("--eig", choices=["auto", "jacobi", "cusolver"], default="auto",
                     help="stage-3 eigensolver: hand-written block Jacobi (auto for m<=1100) or the cuSOLVER comparator")

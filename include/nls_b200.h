@@ -45,6 +45,8 @@ const char* nls_last_error(void);
 /* Create / destroy a context bound to `device`, enqueueing on `stream` (a cudaStream_t, may be 0). */
 int nls_ctx_create(int device, void* stream, nls_ctx** out);
 int nls_ctx_destroy(nls_ctx* ctx);
+/* Enqueue on another stream from now on (the old stream is drained first: the scratch buffers are shared). */
+int nls_ctx_set_stream(nls_ctx* ctx, void* stream);
 /* Rows per internal chunk (default 32768); affects scratch size only, never results' meaning. */
 int nls_ctx_set_chunk_rows(nls_ctx* ctx, int64_t rows);
 /* Kernels of this library launched through `ctx` so far (for bench.py's gpu_launches). */
@@ -217,11 +219,14 @@ int nls_dual_predict(nls_ctx* ctx, const double* Xq, int64_t nq, const double* X
  * weight first exceeds half the bin's weight: v*, predecessor value (NaN if none), successor value
  * (NaN if none), weight strictly below v*, weight of the ties at v*, number of ties, weight of the
  * first tie; and wtot_out[nbins][d] = total weight.  The host evaluates the reference's two linear
- * interpolations from these.  nls_bin_mad: spread_out[bin][col] = sum_i w_i |x_i,col - centre[bin][col]|.
+ * interpolations from these.  thresh (nbins, may be NULL): crossing threshold of every bin in place of half its
+ * total weight; with unit weights and thresh[b] = r + 0.5, v* is the order statistic of rank r (0-based), which is
+ * how the host reproduces the reference's interpolation bit for bit for uniformly weighted bins.
+ * nls_bin_mad: spread_out[bin][col] = sum_i w_i |x_i,col - centre[bin][col]|.
  * ------------------------------------------------------------------------------------------- */
 int nls_bin_median_stats(nls_ctx* ctx, const double* X, int64_t n, int d, const int64_t* perm,
                          const double* w, const int* tiles, int ntiles, const int* bin_tiles,
-                         int nbins, double* stats_out, double* wtot_out);
+                         int nbins, const double* thresh, double* stats_out, double* wtot_out);
 int nls_bin_mad(nls_ctx* ctx, const double* X, int64_t n, int d, const int64_t* perm, const double* w,
                 const int* tiles, int ntiles, const int* bin_tiles, int nbins, const double* centre,
                 double* spread_out);

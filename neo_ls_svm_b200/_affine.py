@@ -232,7 +232,7 @@ def _weighted_draw(rng, p, size):
     indices and the same generator state afterwards; p is a probability vector built a line earlier from
     validated sample weights, so re-checking it costs three more passes over up to n elements per call.
     """
-    cdf = np.cumsum(p)
+    cdf = np.cumsum(np.asarray(p, dtype=np.float64))  # `choice` casts p to float64 before the running sum
     cdf /= cdf[-1]
     return np.searchsorted(cdf, rng.random_sample(size), side="right")
 

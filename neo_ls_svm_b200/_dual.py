@@ -96,7 +96,11 @@ def predict(model, X: np.ndarray, want_decision: bool, want_std: bool):
     if "shift" not in st:
         shift, W = model.dual_feature_map_.device_weights(model.n_features_in_)
         st["shift"], st["W"] = torch.from_numpy(shift).to(dev), torch.from_numpy(W).to(dev)
-    Xq = ctx.affine_map(torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).to(dev), st["shift"], st["W"])  # :473, :668
+    Xraw = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).to(dev)
+    Xq = ctx.affine_map(Xraw, st["shift"], st["W"])  # :473, :668
+    aff = model.dual_feature_map_
+    if aff.append_features and getattr(aff, "A_", aff.A) is not None:
+        Xq = torch.cat([Xraw, Xq], dim=1).contiguous()  # transform() hstacks [X | Z] (_affine_feature_map.py:90-91)
     return ctx.dual_predict(
         Xq, st["Xt"], alpha=st["alpha"] if want_decision else None, alpha_sum=st["alpha_sum"],
         Bt=st["Bt"] if want_std else None, w=st["w"] if want_std else None, want_std=want_std,

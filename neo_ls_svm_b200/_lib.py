@@ -32,6 +32,7 @@ def _signatures(lib: C.CDLL) -> None:
         "nls_last_error": ([], C.c_char_p),
         "nls_ctx_create": ([i, p, C.POINTER(p)], i),
         "nls_ctx_destroy": ([p], i),
+        "nls_ctx_set_stream": ([p, p], i),
         "nls_ctx_set_chunk_rows": ([p, i64], i),
         "nls_ctx_launch_count": ([p], i64),
         "nls_ctx_profile": ([p, i], i),
@@ -52,7 +53,7 @@ def _signatures(lib: C.CDLL) -> None:
         "nls_dual_sweep": ([p, p, i, i, p, p, p, p, i, i, p, p, p], i),
         "nls_dual_finalize": ([p, i, p, p, d, p, p, p, p, p, p, p], i),
         "nls_dual_predict": ([p, p, i64, p, i, i, p, d, p, p, p, p], i),
-        "nls_bin_median_stats": ([p, p, i64, i, p, p, p, i, p, i, p, p], i),
+        "nls_bin_median_stats": ([p, p, i64, i, p, p, p, i, p, i, p, p, p], i),
         "nls_bin_mad": ([p, p, i64, i, p, p, p, i, p, i, p, p], i),
         "nls_bench_dmma_peak": ([p, i, C.POINTER(d)], i),
     }
@@ -129,6 +130,16 @@ class Context:
             pass
 
     # -- bookkeeping ---------------------------------------------------------------------------
+    def bind_current_stream(self) -> None:
+        """Enqueue on torch's CURRENT stream of this device from now on (the tensors handed to the library are
+        produced and consumed on that stream).  Called by `context()` on every lookup."""
+        import torch
+
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        if stream != self.stream:
+            check(self.lib.nls_ctx_set_stream(self.handle, C.c_void_p(stream)))
+            self.stream = stream
+
     def set_chunk_rows(self, rows: int) -> None:
         check(self.lib.nls_ctx_set_chunk_rows(self.handle, rows))
 
@@ -238,6 +249,15 @@ class Context:
         check(self.lib.nls_cholesky_solve(self.handle, ptr(A), m, float(diag_shift), ptr(b), ptr(U), ptr(beta)))
         return U, beta
 
+    def triangular_inverse(self, U):
+        """U⁻¹ of the upper-triangular factor U (anything below the diagonal of U is ignored): the basis B of
+        predict_std, (γC + A)⁻¹ = U⁻¹ U⁻ᴴ (_neo_ls_svm.py:467-469, :473-475)."""
+        import torch
+
+        m = U.shape[0]
+        eye = torch.eye(m, dtype=U.dtype, device=U.device)
+        return torch.linalg.solve_triangular(torch.triu(U), eye, upper=True).contiguous()
+
     def primal_loo_sweep(self, X, y, s, shift, W, Q, lam, v, inv_c: float, gammas, classifier: bool, stash=None):
         """Per-γ error sums (3×G); `stash` (n×G float64, optional) receives σ²ᵢ(γ_g) for every row."""
         import torch
@@ -331,6 +351,8 @@ class Context:
 
         nq, p_ = Xq.shape
         n = Xt.shape[0]
+        if Xt.shape[1] != p_:
+            raise ValueError(f"query rows have {p_} transformed features, the training rows {Xt.shape[1]}")
         yhat = torch.empty((nq,), dtype=torch.float64, device=Xq.device) if alpha is not None else None
         sigma = torch.empty((nq,), dtype=torch.float64, device=Xq.device) if want_std else None
         check(self.lib.nls_dual_predict(
@@ -339,7 +361,7 @@ class Context:
 
 
     # -- supervised affine pre-pass ------------------------------------------------------------
-    def bin_median_stats(self, X, perm, w, tiles, bin_tiles):
+    def bin_median_stats(self, X, perm, w, tiles, bin_tiles, thresh=None):
         import torch
 
         n, d = X.shape
@@ -347,7 +369,7 @@ class Context:
         stats = torch.empty((7, nbins, d), dtype=torch.float64, device=X.device)
         wtot = torch.empty((nbins, d), dtype=torch.float64, device=X.device)
         check(self.lib.nls_bin_median_stats(
-            self.handle, ptr(X), n, d, ptr(perm), ptr(w), ptr(tiles), ntiles, ptr(bin_tiles), nbins, ptr(stats), ptr(wtot)))
+            self.handle, ptr(X), n, d, ptr(perm), ptr(w), ptr(tiles), ntiles, ptr(bin_tiles), nbins, ptr(thresh), ptr(stats), ptr(wtot)))
         return stats, wtot
 
     def bin_mad(self, X, perm, w, tiles, bin_tiles, centre):
@@ -371,4 +393,5 @@ def context(device: int | None = None) -> Context:
     dev = torch.cuda.current_device() if (device is None and torch.cuda.is_available()) else device
     if dev not in _contexts:
         _contexts[dev] = Context(dev)
+    _contexts[dev].bind_current_stream()
     return _contexts[dev]

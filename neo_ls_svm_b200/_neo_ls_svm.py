@@ -120,6 +120,7 @@ class NeoLSSVM(BaseEstimator):
         from . import _primal
 
         ctx, torch, dev = self._gpu()
+        self._check_primal_feature_map(self.primal_feature_map_)
         shift, W = self.primal_feature_map_.device_weights(X.shape[1])
         dt = X.dtype
         s64 = np.asarray(s, dtype=np.float64)
@@ -147,6 +148,25 @@ class NeoLSSVM(BaseEstimator):
         self.loo_std_ = rows["loo_std"].astype(dt)
         self.__dict__[_DEVICE_STATE] = {"kind": "primal", "shift": shd, "W": Wd, "beta": fit.beta, "U": fit.U}
         return fit.beta.cpu().numpy().astype(cdt), self.γs_[fit.opt]
+
+    @staticmethod
+    def _check_primal_feature_map(fm) -> None:
+        """The device solver computes φ = [exp(-i (x - shift) W)/√D | 1] itself and regularises with C = c·I
+        (the reference's `eigh(A / c)` branch, :119-121).  A user-supplied map with another `transform` or a
+        non-constant / non-diagonal complexity matrix (the reference's generalised `eigh(A, C)` + LU branch,
+        :122-124) would be solved as something it is not, so it is refused instead."""
+        from ._feature_maps import RandomFourierFeatures
+
+        if not isinstance(fm, RandomFourierFeatures) or type(fm).transform is not RandomFourierFeatures.transform:
+            raise NotImplementedError(
+                "the B200 primal solver supports RandomFourierFeatures / OrthogonalRandomFourierFeatures maps "
+                f"(and subclasses that keep their transform); got {type(fm).__name__}")
+        C = np.asarray(fm.complexity_matrix)
+        c = np.diag(C) if C.ndim == 2 else C  # noqa: PLR2004
+        if (C.ndim == 2 and np.any(C != np.diag(c))) or np.any(c != c[0]) or not np.isfinite(c[0]) or c[0] <= 0:  # noqa: PLR2004
+            raise NotImplementedError(
+                "the B200 primal solver supports a constant diagonal complexity matrix only (every feature map the "
+                "reference ships has one, _feature_maps.py:129-135)")
 
     def _optimize_α̂_γ(self, X, y, s, ρ: float = 1.0):
         """GPU counterpart of the reference's `_optimize_α̂_γ` (:191-325) for ρ = 1."""

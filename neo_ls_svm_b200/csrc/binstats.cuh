@@ -86,10 +86,12 @@ __global__ void __launch_bounds__(256) bs_count_kernel(const double* __restrict_
 }
 
 // One thread per (bin, col): F = sum of the bin's tile partials (fixed order), then one bisection step
-// towards the smallest key v with F(v) > half[bin].  iter < 0: initialise (F is the bin's total weight).
+// towards the smallest key v with F(v) > threshold[bin] (0.5 * total weight when `thresh` is null).
+// iter < 0: initialise (F is the bin's total weight).
 __global__ void bs_step_kernel(const double* __restrict__ partial, const int2* __restrict__ bin_tiles, int nbins, int d,
-                               int iter, double* __restrict__ wtot, unsigned long long* __restrict__ lo,
-                               unsigned long long* __restrict__ hi, unsigned long long* __restrict__ mid) {
+                               int iter, const double* __restrict__ thresh, double* __restrict__ wtot,
+                               unsigned long long* __restrict__ lo, unsigned long long* __restrict__ hi,
+                               unsigned long long* __restrict__ mid) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nbins * d) return;
   const int b = e / d, col = e % d;
@@ -100,7 +102,8 @@ __global__ void bs_step_kernel(const double* __restrict__ partial, const int2* _
     lo[e] = 0ull;
     hi[e] = ~0ull;
   } else {
-    if (F > 0.5 * wtot[e]) hi[e] = mid[e]; else lo[e] = mid[e] + 1ull;
+    const double cut = thresh ? thresh[b] : 0.5 * wtot[e];
+    if (F > cut) hi[e] = mid[e]; else lo[e] = mid[e] + 1ull;
   }
   mid[e] = lo[e] + ((hi[e] - lo[e]) >> 1);
 }

@@ -378,6 +378,15 @@ extern "C" int nls_ctx_destroy(nls_ctx* ctx) {
   return NLS_OK;
 }
 
+extern "C" int nls_ctx_set_stream(nls_ctx* ctx, void* stream) {
+  if (!ctx) return fail(NLS_ERR_INVALID, "ctx is null");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // scratch buffers are shared: drain the old stream first
+  ctx->stream = (cudaStream_t)stream;
+  if (ctx->solver) cusolverDnSetStream(ctx->solver, ctx->stream);
+  return NLS_OK;
+}
+
 extern "C" int nls_ctx_set_chunk_rows(nls_ctx* ctx, int64_t rows) {
   if (!ctx || rows < 128) return fail(NLS_ERR_INVALID, "chunk rows must be >= 128");
   ctx->chunk_rows = round_up(rows, 128);
@@ -1152,7 +1161,7 @@ extern "C" int nls_quantile_epilogue(nls_ctx* ctx, const double* yhat, const dou
                                      const double* iso_y, int n_iso, double* out) {
   if (!ctx || !yhat || !sigma || !beta_abs || !beta_rel || !bias_abs || !bias_rel || !out)
     return fail(NLS_ERR_INVALID, "null pointer");
-  if (Q < 1 || Q > MAX_QUANTILES) return fail(NLS_ERR_INVALID, "Q must be in [1, %d]", MAX_QUANTILES);
+  if (Q < 1) return fail(NLS_ERR_INVALID, "Q must be positive");
   if (!is_regressor && (!iso_x || !iso_y || n_iso < 1)) return fail(NLS_ERR_INVALID, "classifier needs isotonic thresholds");
   if (n < 1) return NLS_OK;
   CUDA_TRY(cudaSetDevice(ctx->device));
@@ -1449,7 +1458,7 @@ extern "C" int nls_dual_predict(nls_ctx* ctx, const double* Xq, int64_t nq, cons
 // ---------------------------------------------------------------------------------------------
 extern "C" int nls_bin_median_stats(nls_ctx* ctx, const double* X, int64_t n, int d, const int64_t* perm,
                                     const double* w, const int* tiles, int ntiles, const int* bin_tiles, int nbins,
-                                    double* stats_out, double* wtot_out) {
+                                    const double* thresh, double* stats_out, double* wtot_out) {
   if (!ctx || !X || !perm || !w || !tiles || !bin_tiles || !stats_out || !wtot_out)
     return fail(NLS_ERR_INVALID, "null pointer");
   if (n < 1 || d < 1 || ntiles < 1 || nbins < 1) return fail(NLS_ERR_INVALID, "bad shape");
@@ -1476,12 +1485,12 @@ extern "C" int nls_bin_median_stats(nls_ctx* ctx, const double* X, int64_t n, in
   // Total weight per (bin, column): every key is <= the all-ones key.
   CUDA_TRY(cudaMemsetAsync(mid, 0xff, (size_t)nd * 8, ctx->stream));
   count();
-  bs_step_kernel<<<sgrid, 256, 0, ctx->stream>>>(partial, bt, nbins, d, -1, wtot_out, lo, hi, mid);
+  bs_step_kernel<<<sgrid, 256, 0, ctx->stream>>>(partial, bt, nbins, d, -1, thresh, wtot_out, lo, hi, mid);
   ctx->launches += 2;
   // 64 bisection steps on the 64-bit key: afterwards lo == hi == key of the crossing value v*.
   for (int it = 0; it < 64; ++it) {
     count();
-    bs_step_kernel<<<sgrid, 256, 0, ctx->stream>>>(partial, bt, nbins, d, it, wtot_out, lo, hi, mid);
+    bs_step_kernel<<<sgrid, 256, 0, ctx->stream>>>(partial, bt, nbins, d, it, thresh, wtot_out, lo, hi, mid);
     ctx->launches += 2;
   }
   bs_stats_kernel<<<grid, 256, 0, ctx->stream>>>(X, d, (const long long*)perm, w, tl, lo, partial);

@@ -425,7 +425,8 @@ __global__ void conj_vec_kernel(double* __restrict__ z, int m) {
 }
 
 // Conformal quantile epilogue, one thread per row.  _neo_ls_svm.py:566-600.
-constexpr int MAX_QUANTILES = 32;
+// Any number of quantiles: the two candidate offsets of a quantile are recomputed where they are needed (a handful of
+// flops) instead of being held in per-thread arrays, so there is no compile-time cap on Q.
 __global__ void quantile_epilogue_kernel(const double* __restrict__ yhat, const double* __restrict__ sigma, long long n,
                                          const double* __restrict__ beta_abs, const double* __restrict__ beta_rel,
                                          const double* __restrict__ bias_abs, const double* __restrict__ bias_rel,
@@ -434,59 +435,53 @@ __global__ void quantile_epilogue_kernel(const double* __restrict__ yhat, const 
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double yh = yhat[i], sg = sigma[i], ay = fabs(yh);
-  double da[MAX_QUANTILES], dr[MAX_QUANTILES];
-  for (int q = 0; q < Q; ++q) {
-    double a, r;
-    if (is_regressor) {  // features [sigma, |yhat|, 1]
-      a = (sg * beta_abs[q] + ay * beta_abs[Q + q]) + beta_abs[2 * Q + q];
-      r = (sg * beta_rel[q] + ay * beta_rel[Q + q]) + beta_rel[2 * Q + q];
-    } else {  // features [sigma, 1]
-      a = sg * beta_abs[q] + beta_abs[Q + q];
-      r = sg * beta_rel[q] + beta_rel[Q + q];
-    }
-    da[q] = a + bias_abs[q];
-    dr[q] = ay * (r + bias_rel[q]);
-  }
+  auto d_abs = [&](int q) {
+    const double a = is_regressor ? (sg * beta_abs[q] + ay * beta_abs[Q + q]) + beta_abs[2 * Q + q]   // [sigma, |yhat|, 1]
+                                  : sg * beta_abs[q] + beta_abs[Q + q];                               // [sigma, 1]
+    return a + bias_abs[q];
+  };
+  auto d_rel = [&](int q) {
+    const double r = is_regressor ? (sg * beta_rel[q] + ay * beta_rel[Q + q]) + beta_rel[2 * Q + q]
+                                  : sg * beta_rel[q] + beta_rel[Q + q];
+    return ay * (r + bias_rel[q]);
+  };
   // Dispersion = population standard deviation over the quantile axis (np.std), :586.
   double ma = 0.0, mr = 0.0;
   for (int q = 0; q < Q; ++q) {
-    ma += da[q];
-    mr += dr[q];
+    ma += d_abs(q);
+    mr += d_rel(q);
   }
   ma /= Q;
   mr /= Q;
   double va = 0.0, vr = 0.0;
   for (int q = 0; q < Q; ++q) {
-    va += (da[q] - ma) * (da[q] - ma);
-    vr += (dr[q] - mr) * (dr[q] - mr);
+    const double a = d_abs(q), r = d_rel(q);
+    va += (a - ma) * (a - ma);
+    vr += (r - mr) * (r - mr);
   }
   const bool pick_rel = sqrt(vr / Q) < sqrt(va / Q);  // argmin: first (absolute) wins ties
   if (is_regressor) {
-    for (int q = 0; q < Q; ++q) out[i * Q + q] = yh + (pick_rel ? dr[q] : da[q]);
+    for (int q = 0; q < Q; ++q) out[i * Q + q] = yh + (pick_rel ? d_rel(q) : d_abs(q));
     return;
   }
   // Classifier: isotonic calibration per quantile (clip + linear interpolation), then [1 - p_rev | p].
-  double pq[MAX_QUANTILES];
-  for (int q = 0; q < Q; ++q) {
-    double t = yh + (pick_rel ? dr[q] : da[q]);
+  auto calibrated = [&](int q) {
+    double t = yh + (pick_rel ? d_rel(q) : d_abs(q));
     t = fmin(fmax(t, iso_x[0]), iso_x[n_iso - 1]);
-    if (n_iso == 1) {
-      pq[q] = iso_y[0];
-      continue;
-    }
+    if (n_iso == 1) return iso_y[0];
     int lo = 0, hi = n_iso;  // first index with iso_x[idx] >= t (searchsorted side='left')
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
       if (iso_x[mid] < t) lo = mid + 1; else hi = mid;
     }
-    int up = lo < 1 ? 1 : (lo > n_iso - 1 ? n_iso - 1 : lo);
+    const int up = lo < 1 ? 1 : (lo > n_iso - 1 ? n_iso - 1 : lo);
     const int dn = up - 1;
     const double slope = (iso_y[up] - iso_y[dn]) / (iso_x[up] - iso_x[dn]);
-    pq[q] = slope * (t - iso_x[dn]) + iso_y[dn];
-  }
+    return slope * (t - iso_x[dn]) + iso_y[dn];
+  };
   for (int q = 0; q < Q; ++q) {
-    out[(i * Q + q) * 2] = 1.0 - pq[Q - 1 - q];
-    out[(i * Q + q) * 2 + 1] = pq[q];
+    out[(i * Q + q) * 2] = 1.0 - calibrated(Q - 1 - q);
+    out[(i * Q + q) * 2 + 1] = calibrated(q);
   }
 }
 

@@ -75,7 +75,19 @@ CASES = {
     "c3_small": ("regression", dict(n=5000, d=64, n_informative=32), dict(num_features=1024, dual=False)),
     "dual_reg": ("regression", dict(n=600, d=6, n_informative=4), dict(dual=True)),
     "dual_clf": ("churn", dict(n=500, d=10, n_informative=5), dict(dual=True)),
+    # Full-size C2: the largest configuration the reference itself can run here (32 s).  Its fixture
+    # stores the n-vectors on the 4096 rows of `golden_row_subset` only, which keeps the .npz small.
+    "c2_full": ("churn", dict(n=100_000, d=70, n_informative=20), dict()),
 }
+
+GOLDEN_ROW_SUBSET = 4096
+
+
+def golden_row_subset(n: int) -> np.ndarray:
+    """Rows on which large fixtures keep their per-row vectors (all rows when n is small)."""
+    if n <= 20_000:
+        return np.arange(n)
+    return np.linspace(0, n - 1, GOLDEN_ROW_SUBSET).astype(np.int64)
 
 
 def load_case(name: str, n_test: int = 400):

@@ -23,7 +23,7 @@ sys.path.insert(0, "/root/reference/src")
 
 import numpy as np  # noqa: E402
 
-from neo_ls_svm_b200.datasets import CASES, load_case  # noqa: E402
+from neo_ls_svm_b200.datasets import CASES, golden_row_subset, load_case  # noqa: E402
 
 
 def run_case(name: str) -> dict:
@@ -37,7 +37,9 @@ def run_case(name: str) -> dict:
     if "dual" in est:
         kwargs["dual"] = est["dual"]
     model = NeoLSSVM(**kwargs).fit(X, y, sample_weight=sw)
+    rows = golden_row_subset(len(y))  # per-row vectors of large cases are stored on a fixed row subset
     out: dict = {
+        "rows": rows,
         "x_checksum": np.array([X.sum(), np.abs(X).sum(), float(np.asarray(y, dtype=np.float64).sum())]),
         "classifier": np.array(model._estimator_type == "classifier"),
         "dual": np.array(bool(model.dual_)),
@@ -45,12 +47,12 @@ def run_case(name: str) -> dict:
         "gammas": model.γs_,
         "loo_errors": model.loo_errors_γs_,
         "opt": np.array(int(np.argmin(np.abs(model.γs_ - model.γ_)))),
-        "loo_residuals": model.loo_residuals_,
-        "loo_yhat": model.loo_ŷ_,
+        "loo_residuals": model.loo_residuals_[rows],
+        "loo_yhat": model.loo_ŷ_[rows],
         "loo_error": np.array(model.loo_error_),
         "loo_score": np.array(model.loo_score_),
-        "residuals": model.residuals_,
-        "loo_std": model.loo_std_,
+        "residuals": model.residuals_[rows],
+        "loo_std": model.loo_std_[rows],
     }
     # Digest of the Cholesky factor U (gamma*C + A = U^H U): its diagonal and U @ probe.
     U = np.triu(model.L_[0])
@@ -62,13 +64,14 @@ def run_case(name: str) -> dict:
         aff = fm.affine_feature_map
         out.update(
             shift=aff.shift_, scale=aff.scale_, A_map=aff.A_,
-            beta=model.β̂_, loo_leverage=model.loo_leverage_,
+            beta=model.β̂_, loo_leverage=model.loo_leverage_[rows],
         )
         # The feature map itself on a few rows (a1 + a2).
         out["phi_head"] = fm.transform(X[:16])
     else:
         aff = model.dual_feature_map_
         out.update(shift=aff.shift_, scale=aff.scale_, A_map=aff.A_, Xt_train=model.X_, alpha=model.α̂_)
+        assert len(rows) == len(y), "dual fixtures keep every row"
     # Predictions on held-out rows.
     out["decision"] = model.decision_function(Xt)
     out["std"] = model.predict_std(Xt)
@@ -92,9 +95,30 @@ def run_case(name: str) -> dict:
     return {k: np.asarray(v) for k, v in out.items()}
 
 
+def bench_map() -> dict:
+    """(shift, W) of the C3 benchmark: the reference's OrthogonalRandomFourierFeatures(1024) fitted on the first
+    100,000 rows of the bench dataset, so that bench.py's two arms share one map and the reference arm never has to
+    import the product package."""
+    from neo_ls_svm._feature_maps import OrthogonalRandomFourierFeatures
+
+    from neo_ls_svm_b200.datasets import fast_regression_rows
+
+    X, y = fast_regression_rows(4_000_000, 64, 32, row_begin=0, row_end=100_000)
+    fm = OrthogonalRandomFourierFeatures(num_features=1024).fit(X, y, np.ones(len(y)))
+    aff = fm.affine_feature_map
+    W = aff.A_ / np.reshape(aff.scale_, (-1, 1))
+    return {"shift": np.ravel(aff.shift_), "W": np.ascontiguousarray(W), "rows": np.array(100_000),
+            "x_checksum": np.array([X.sum(), np.abs(X).sum(), y.sum()])}
+
+
 def main() -> None:
     names = sys.argv[1:] or list(CASES)
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    if "bench_map" in names:
+        names.remove("bench_map")
+        path = os.path.join(ROOT, "tests", "golden", "bench_c3_map.npz")
+        np.savez_compressed(path, **bench_map())
+        print("bench_map ->", path, f"{os.path.getsize(path) / 1e6:.2f} MB")
     for name in names:
         arrays = run_case(name)
         path = os.path.join(ROOT, "tests", "golden", f"{name}.npz")

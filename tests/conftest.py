@@ -39,3 +39,14 @@ def rel_err(a, b) -> float:
     a, b = np.asarray(a), np.asarray(b)
     den = float(np.max(np.abs(b))) or 1.0
     return float(np.max(np.abs(a - b))) / den
+
+
+def assert_elementwise(a, ref, rtol: float = 1e-9, atol_scale: float = 1e-12) -> None:
+    """Every entry: |a - ref| <= rtol |ref| + atol_scale max|ref| (rel_err alone leaves small entries unconstrained)."""
+    a, ref = np.asarray(a), np.asarray(ref)
+    bound = rtol * np.abs(ref) + atol_scale * (float(np.max(np.abs(ref))) or 1.0)
+    excess = np.abs(a - ref) - bound
+    worst = int(np.argmax(excess))
+    assert excess.flat[worst] <= 0, (
+        f"entry {worst}: got {a.flat[worst]!r}, reference {ref.flat[worst]!r}, |Δ| = {abs(a.flat[worst] - ref.flat[worst]):.3e} "
+        f"> bound {bound.flat[worst]:.3e}")

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import rel_err  # noqa: E402
+from conftest import assert_elementwise, rel_err  # noqa: E402
 from neo_ls_svm_b200.datasets import load_case, make_regression_rows
 
 pytestmark = pytest.mark.gpu
@@ -57,6 +57,8 @@ def test_primal_fit_matches_reference(name, chunk, stash, golden, gpu):
     assert rel_err(fit.beta.cpu().numpy(), g["beta"]) < TOL_FIT
     assert rel_err(fit.beta_eig.cpu().numpy(), g["beta"]) < TOL_FIT
     assert rel_err(fit.rows["loo_residuals"].cpu().numpy(), g["loo_residuals"]) < TOL_FIT
+    assert_elementwise(fit.rows["loo_residuals"].cpu().numpy(), g["loo_residuals"])
+    assert_elementwise(fit.loo_errors, g["loo_errors"])
     assert rel_err(fit.rows["loo_leverage"].cpu().numpy(), g["loo_leverage"]) < TOL_FIT
     assert rel_err(fit.rows["residuals"].cpu().numpy(), g["residuals"]) < TOL_FIT
     assert rel_err(fit.rows["loo_std"].cpu().numpy(), g["loo_std"]) < TOL_FIT
@@ -122,6 +124,7 @@ def test_ragged_shapes_match_oracle(n, d, D, gpu):
     assert rel_err(fit.loo_errors, ref["loo_errors"]) < TOL_FIT
     assert rel_err(fit.beta.cpu().numpy(), ref["beta"]) < TOL_FIT
     assert rel_err(fit.rows["loo_residuals"].cpu().numpy(), ref["loo_residuals"]) < TOL_FIT
+    assert_elementwise(fit.rows["loo_residuals"].cpu().numpy(), ref["loo_residuals"])
     assert rel_err(fit.rows["loo_std"].cpu().numpy(), ref["loo_std"]) < TOL_FIT
 
 

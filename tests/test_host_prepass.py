@@ -151,3 +151,31 @@ def test_weighted_draw_is_randomstate_choice():
         a = r1.choice(n, size=1536, p=p)
         b = _weighted_draw(r2, p, 1536)
         assert np.array_equal(a, b) and r1.random_sample() == r2.random_sample()
+    # float32 weights (float32 X): `choice` accumulates the CDF in float64, and so must the replica
+    n = 200_000
+    w32 = (np.random.default_rng(9).random(n) + 0.5).astype(np.float32)
+    p32 = w32 / np.sum(w32)
+    assert p32.dtype == np.float32
+    r1, r2 = np.random.RandomState(7), np.random.RandomState(7)
+    a = r1.choice(n, size=1536, p=p32)
+    b = _weighted_draw(r2, p32, 1536)
+    assert np.array_equal(a, b) and r1.random_sample() == r2.random_sample()
+
+
+def test_uniform_rank_plan_reproduces_the_reference_median():
+    """Uniformly weighted bins (every fit without sample_weight): the ranks and abscissae of `uniform_rank_plan`
+    reproduce `weighted_quantile(a, w, 0.5)` from order statistics alone — what the device pre-pass relies on —
+    including the bin sizes where the sequential cumulative sum crosses 0.5 by one ulp (n = 26, 28, ...)."""
+    from neo_ls_svm_b200._binstats import median_from_ranks, uniform_rank_plan
+    from neo_ls_svm_b200._weighted_quantile import weighted_quantile
+
+    rng = np.random.default_rng(0)
+    for n_b in list(range(1, 70)) + [100, 101, 1000, 1001, 4096, 65_536, 100_003]:
+        w = 1.0 / n_b if n_b % 3 else 1.0 / int(rng.integers(n_b, 5 * n_b + 1))
+        a = rng.standard_normal((n_b, 3))
+        a[:, 1] = np.round(a[:, 1], 1)  # ties
+        ref = weighted_quantile(a, np.full((n_b, 1), w), 0.5, axis=0)[0]
+        srt = np.sort(a, axis=0)
+        got = median_from_ranks(lambda r: srt[r], n_b, uniform_rank_plan(w, n_b))
+        # same ranks, same formula; the reference's numba kernel may contract the last multiply-add
+        assert np.max(np.abs(got - ref)) <= 4 * np.finfo(float).eps * max(1.0, np.max(np.abs(ref))), n_b
