@@ -96,6 +96,12 @@ int nls_primal_gram_h2d(nls_ctx* ctx, const double* X_host, const double* y_host
  * A: m x m complex128 (only needs to be Hermitian), lam_out: m, Q_out: m x m complex128.
  * ------------------------------------------------------------------------------------------- */
 int nls_heev(nls_ctx* ctx, const double* A, int m, double scale, double* lam_out, double* Q_out);
+/* The middle stage of nls_heev on its own: eigen-decomposition of the real symmetric tridiagonal matrix with diagonal
+ * d_host (n) and off-diagonal e_host (n - 1), both HOST arrays, by divide and conquer (csrc/stedc.cuh).  lam_out
+ * (device, n) ascending; Zt_out (device, n x n row-major): row k is the eigenvector of lam_out[k]. */
+int nls_stedc(nls_ctx* ctx, int n, const double* d_host, const double* e_host, double* lam_out, double* Zt_out);
+/* The tridiagonal form (host arrays d: n, e: n - 1) the last eigensolve of this context reduced its matrix to. */
+int nls_ctx_last_tridiagonal(nls_ctx* ctx, int n, double* d_host, double* e_host);
 /* Which solver nls_heev runs: 0 = the hand-written parallel two-sided block Jacobi kernels
  * (csrc/jacobi.cuh), 1 = cuSOLVER Zheevd (library comparator), 2 = auto (default: Jacobi for
  * m <= 1100, cuSOLVER above).  Also selectable with NLS_EIG=jacobi|cusolver. */

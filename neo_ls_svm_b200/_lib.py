@@ -42,6 +42,8 @@ def _signatures(lib: C.CDLL) -> None:
         "nls_primal_gram": ([p, p, p, p, i64, i, p, p, i, p, p], i),
         "nls_primal_gram_h2d": ([p, p, p, p, i64, i, p, p, p, p, p, i, p, p], i),
         "nls_heev": ([p, p, i, d, p, p], i),
+        "nls_stedc": ([p, i, p, p, p, p], i),
+        "nls_ctx_last_tridiagonal": ([p, i, p, p], i),
         "nls_ctx_set_eigensolver": ([p, i], i),
         "nls_ctx_last_eig_sweeps": ([p], i),
         "nls_primal_coeffs": ([p, p, p, p, i, d, d, p, p], i),
@@ -144,8 +146,9 @@ class Context:
         check(self.lib.nls_ctx_set_chunk_rows(self.handle, rows))
 
     def set_eigensolver(self, kind: str) -> None:
-        """'jacobi' (hand-written block Jacobi kernels), 'cusolver' (library comparator) or 'auto' (default)."""
-        check(self.lib.nls_ctx_set_eigensolver(self.handle, {"jacobi": 0, "cusolver": 1, "auto": 2}[kind]))
+        """'dc' (hand-written tridiagonalisation + divide and conquer; what 'auto', the default, runs), 'jacobi'
+        (hand-written block Jacobi kernels) or 'cusolver' (library comparator)."""
+        check(self.lib.nls_ctx_set_eigensolver(self.handle, {"jacobi": 0, "cusolver": 1, "auto": 2, "dc": 3}[kind]))
 
     def last_eig_sweeps(self) -> int:
         return int(self.lib.nls_ctx_last_eig_sweeps(self.handle))
@@ -226,6 +229,28 @@ class Context:
         Q = torch.empty((m, m), dtype=torch.complex128, device=A.device)
         check(self.lib.nls_heev(self.handle, ptr(A), m, float(scale), ptr(lam), ptr(Q)))
         return lam, Q
+
+    def stedc(self, d, e):
+        """Eigenpairs of the real symmetric tridiagonal matrix (d, e: host NumPy arrays): (lam, Zt) on the device,
+        row k of Zt the eigenvector of lam[k]."""
+        import numpy as np
+        import torch
+
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        e = np.ascontiguousarray(e, dtype=np.float64)
+        n = len(d)
+        dev = torch.device("cuda", self.device)
+        lam = torch.empty((n,), dtype=torch.float64, device=dev)
+        Zt = torch.empty((n, n), dtype=torch.float64, device=dev)
+        check(self.lib.nls_stedc(self.handle, n, d.ctypes.data, e.ctypes.data if n > 1 else None, ptr(lam), ptr(Zt)))
+        return lam, Zt
+
+    def last_tridiagonal(self, n: int):
+        import numpy as np
+
+        d, e = np.empty(n), np.empty(max(n - 1, 0))
+        check(self.lib.nls_ctx_last_tridiagonal(self.handle, n, d.ctypes.data, e.ctypes.data if n > 1 else None))
+        return d, e
 
     def primal_coeffs(self, Q, lam, b, inv_c: float, gamma: float | None = None, v=None):
         """v = Q^H b inv_c (if b is given) and beta_eig = Q (v/(lam+gamma)) (if gamma is given)."""

@@ -1,0 +1,622 @@
+// hetrd.cuh — Householder tridiagonalisation of a dense Hermitian / real symmetric matrix and the matching
+// back-transformation: first and last stage of the hand-written eigensolver that replaces LAPACK behind
+// scipy.linalg.eigh (_neo_ls_svm.py:120, complex m x m) and np.linalg.eigh (:265, real n x n).
+//
+// Blocked LAPACK-style reduction (zhetrd/zlatrd, lower form, full storage), restructured for one persistent
+// cooperative kernel per panel of NB = 32 columns:
+//   * per column ONE exchange of the raw updated column x and ONE grid-wide reduction of
+//       [x^H x, x^H (A x), x^H a_1, V^H x, W^H x];
+//     the Householder scalars (beta, tau) and everything that depends on them (v, V^H v, W^H v, v^H A v, w) follow
+//     from those sums ("deferred alpha": v = sigma (x - beta e_1) is linear in x), so a column costs two grid
+//     barriers instead of the five dependent reductions of the textbook loop;
+//   * the big operand, y_raw = A x over the trailing matrix, is row-slab distributed over all SMs (warp per row
+//     segment, x staged in shared memory, fixed-order partial sums => bitwise reproducible);
+//   * after the panel the trailing matrix takes the rank-2NB update A -= V W^H + W V^H as ONE GEMM on the FP64 DMMA
+//     core (OpHer2k, K = 2 NB), and the reflectors are kept in the two K-contiguous layouts the back-transformation
+//     GEMMs want (VT: one reflector per row; VR: one coordinate per row, conjugated).
+// Back-transformation X = Q Z with Q = prod_p (I - V_p T_p V_p^H), on Y = X^T (row k = eigenvector k):
+//   C1 = Y conj(V_p) (split-K GEMM, OpBT1)  ->  C2 = C1 T_p^T (small kernel)  ->  Y -= C2 V_p^T (GEMM, OpBT2).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "gemm_core.cuh"
+
+namespace nls {
+
+constexpr int HNB = 32;            // panel width
+constexpr int HETRD_THREADS = 512;
+constexpr int HETRD_WARPS = HETRD_THREADS / 32;
+constexpr int HETRD_NSUM = 3 + 2 * HNB;  // grid-reduced sums per column
+
+// ---- scalar helpers: T = double (real symmetric) or double2 (complex Hermitian, interleaved re/im) -------------
+template <bool C> struct HS;
+template <> struct HS<false> {
+  using T = double;
+  static __device__ __forceinline__ T zero() { return 0.0; }
+  static __device__ __forceinline__ T make(double re, double) { return re; }
+  static __device__ __forceinline__ double re(T a) { return a; }
+  static __device__ __forceinline__ double im(T) { return 0.0; }
+  static __device__ __forceinline__ T conj(T a) { return a; }
+  static __device__ __forceinline__ T add(T a, T b) { return a + b; }
+  static __device__ __forceinline__ T sub(T a, T b) { return a - b; }
+  static __device__ __forceinline__ T mul(T a, T b) { return a * b; }
+  static __device__ __forceinline__ T cmul(T a, T b) { return a * b; }             // conj(a) * b
+  static __device__ __forceinline__ T fma(T a, T b, T c) { return ::fma(a, b, c); }  // a * b + c
+  static __device__ __forceinline__ T cfma(T a, T b, T c) { return ::fma(a, b, c); }  // conj(a) * b + c
+  static __device__ __forceinline__ T scale(double s, T a) { return s * a; }
+  static __device__ __forceinline__ double abs2(T a) { return a * a; }
+  static __device__ __forceinline__ T ldcg(const T* p) { return __ldcg(p); }
+  static __device__ __forceinline__ T shfl_xor(T a, int off) { return __shfl_xor_sync(0xffffffffu, a, off); }
+};
+template <> struct HS<true> {
+  using T = double2;
+  static __device__ __forceinline__ T zero() { return make_double2(0.0, 0.0); }
+  static __device__ __forceinline__ T make(double re, double im) { return make_double2(re, im); }
+  static __device__ __forceinline__ double re(T a) { return a.x; }
+  static __device__ __forceinline__ double im(T a) { return a.y; }
+  static __device__ __forceinline__ T conj(T a) { return make_double2(a.x, -a.y); }
+  static __device__ __forceinline__ T add(T a, T b) { return make_double2(a.x + b.x, a.y + b.y); }
+  static __device__ __forceinline__ T sub(T a, T b) { return make_double2(a.x - b.x, a.y - b.y); }
+  static __device__ __forceinline__ T mul(T a, T b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+  static __device__ __forceinline__ T cmul(T a, T b) { return make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x); }
+  static __device__ __forceinline__ T fma(T a, T b, T c) {
+    return make_double2(::fma(a.x, b.x, ::fma(-a.y, b.y, c.x)), ::fma(a.x, b.y, ::fma(a.y, b.x, c.y)));
+  }
+  static __device__ __forceinline__ T cfma(T a, T b, T c) {
+    return make_double2(::fma(a.x, b.x, ::fma(a.y, b.y, c.x)), ::fma(a.x, b.y, ::fma(-a.y, b.x, c.y)));
+  }
+  static __device__ __forceinline__ T scale(double s, T a) { return make_double2(s * a.x, s * a.y); }
+  static __device__ __forceinline__ double abs2(T a) { return a.x * a.x + a.y * a.y; }
+  static __device__ __forceinline__ T ldcg(const T* p) { return __ldcg(p); }
+  static __device__ __forceinline__ T shfl_xor(T a, int off) {
+    return make_double2(__shfl_xor_sync(0xffffffffu, a.x, off), __shfl_xor_sync(0xffffffffu, a.y, off));
+  }
+};
+
+template <bool C>
+struct HetrdArgs {
+  using T = typename HS<C>::T;
+  T* A;             // n x n row-major work matrix (full storage), pitch lda elements
+  long long lda;
+  int n, k0, jb;    // panel = columns [k0, k0 + jb)
+  T* V;             // n x HNB panel reflectors (row-major), rows > k0 used
+  T* W;             // n x HNB
+  double* d;        // n
+  double* e;        // n - 1
+  T* tau;           // n - 1
+  T* Tfac;          // [panels][HNB][HNB] compact-WY factors (upper triangular)
+  // planar GEMM operands (plane 1 = imaginary part, complex only), row pitch 2 HNB / ldv doubles
+  double* PW;       // [planes][npad][2 HNB]: [V | W]
+  double* RW;       // [planes][npad][2 HNB]: [W | V]
+  double* VT;       // [planes][npad][ldv]: VT[c][k] = v_c[k]
+  double* VR;       // [planes][npad][ldv]: VR[k][c] = conj(v_c[k])
+  long long ldv;
+  long long npad;
+  // exchange buffers
+  T* xbuf;          // n
+  T* ybuf;          // n
+  T* part;          // [HETRD_NSUM][gpad]
+  int gpad;
+  unsigned* bar;    // grid barrier counter (zeroed before every launch)
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void hetrd_grid_barrier(unsigned* ctr, unsigned& target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    unsigned spins = 0;
+    while (ld_acquire_u32(ctr) < target) {
+      if (++spins > (1u << 30)) __trap();  // a lost CTA must not hang the GPU
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// Shared-memory layout of the panel kernel (dynamic): x staging area first (n elements of T), then fixed scratch.
+template <bool C>
+struct HetrdSmem {
+  using T = typename HS<C>::T;
+  T sums[HETRD_NSUM];            // grid-reduced: 0 xx, 1 xy, 2 xa, 3.. V^H x, 3+HNB.. W^H x
+  T Vv[HNB], Wv[HNB];            // V^H v, W^H v
+  T rowV[HNB], rowW[HNB];        // row c+1 of the panel matrices (becomes row c of the next column)
+  T wred[HETRD_WARPS][2 * HNB];  // per-warp partials of V^H x | W^H x
+  T psum[HETRD_THREADS];         // per-task partial row sums of A x
+  T rowred[3][128];              // per-row contributions to xx, xy, xa
+  T Tf[HNB][HNB + 1];            // compact-WY factor (CTA 0)
+  double beta, sigma_re, sigma_im, tau_re, tau_im, alpha2_re, alpha2_im;
+};
+
+template <bool C>
+__global__ void __launch_bounds__(HETRD_THREADS, 1) hetrd_panel_kernel(const HetrdArgs<C> a) {
+  using H = HS<C>;
+  using T = typename H::T;
+  extern __shared__ __align__(16) unsigned char hsm_raw[];
+  T* xs = reinterpret_cast<T*>(hsm_raw);
+  HetrdSmem<C>& sm = *reinterpret_cast<HetrdSmem<C>*>(hsm_raw + (((size_t)a.n * sizeof(T)) + 15) / 16 * 16);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int G = gridDim.x, b = blockIdx.x;
+  const int n = a.n;
+  const long long gtid = (long long)b * HETRD_THREADS + tid, gthreads = (long long)G * HETRD_THREADS;
+  unsigned bar_target = 0;
+  const int planes = C ? 2 : 1;
+  (void)planes;
+
+  if (b == 0)
+    for (int t = tid; t < HNB * (HNB + 1); t += HETRD_THREADS) (&sm.Tf[0][0])[t] = H::zero();
+
+  // ---- phase A of the panel's first column: x = A[k0+1:, k0] (the trailing matrix is up to date) ----
+  for (long long r = a.k0 + gtid; r < n; r += gthreads) {
+    const T v = a.A[r * a.lda + a.k0];
+    if (r == a.k0) a.d[a.k0] = H::re(v);
+    else a.xbuf[r] = v;
+  }
+
+  for (int j = 0; j < a.jb; ++j) {
+    const int c = a.k0 + j;      // column being reduced
+    const int f = c + 1;         // first row of x / of the trailing matrix
+    const int n1 = n - f;        // trailing size
+    hetrd_grid_barrier(a.bar, bar_target);  // B1: x complete
+
+    // ---- phase B: y_raw = A[f:, f:] x for this CTA's row slab, plus the partial sums --------------------
+    const int kbase = f & ~1;    // x staged from an even index (vector loads in the real case)
+    for (int k = kbase + tid; k < n; k += HETRD_THREADS) xs[k - kbase] = (k >= f) ? H::ldcg(a.xbuf + k) : H::zero();
+    __syncthreads();
+    const int R = (n1 + G - 1) / G;             // rows per CTA
+    const int r_lo = f + b * R;
+    const int rows = max(0, min(n, r_lo + R) - r_lo);
+    int S = 1;                                  // k segments per row (few rows per CTA: spread a row over warps)
+    if (R < HETRD_WARPS) {
+      S = HETRD_WARPS / max(R, 1);
+      while (S > 1 && (n - kbase) / S < 128) S >>= 1;
+      if (S > 8) S = 8;
+    }
+    const int nk = n - kbase;
+    const int seglen = ((nk + S - 1) / S + 63) & ~63;
+    for (int task = warp; task < rows * S; task += HETRD_WARPS) {
+      const int row = r_lo + task / S, seg = task % S;
+      const int ka = kbase + seg * seglen, kb = min(n, ka + seglen);
+      const T* arow = a.A + (long long)row * a.lda;
+      T acc0 = H::zero(), acc1 = H::zero();
+      if (C) {
+        for (int k = ka + lane; k < kb; k += 64) {
+          const T a0 = arow[k];
+          const T x0 = xs[k - kbase];
+          const bool two = k + 32 < kb;
+          const T a1 = two ? arow[k + 32] : H::zero();
+          const T x1 = two ? xs[k + 32 - kbase] : H::zero();
+          acc0 = H::fma(a0, x0, acc0);
+          acc1 = H::fma(a1, x1, acc1);
+        }
+      } else {
+        const double* ar = reinterpret_cast<const double*>(arow);
+        const double* xr = reinterpret_cast<const double*>(xs);
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        for (int k = ka + 2 * lane; k < kb; k += 128) {  // ka, kbase even: 16-byte aligned pairs
+          const double2 a0 = (k + 1 < n) ? *reinterpret_cast<const double2*>(ar + k) : make_double2(ar[k], 0.0);
+          const double2 x0 = *reinterpret_cast<const double2*>(xr + (k - kbase));
+          s0 = ::fma(a0.x, x0.x, s0);
+          s1 = ::fma(a0.y, (k + 1 < kb) ? x0.y : 0.0, s1);
+          const int k2 = k + 64;
+          if (k2 < kb) {
+            const double2 a1 = (k2 + 1 < n) ? *reinterpret_cast<const double2*>(ar + k2) : make_double2(ar[k2], 0.0);
+            const double2 x1 = *reinterpret_cast<const double2*>(xr + (k2 - kbase));
+            s2 = ::fma(a1.x, x1.x, s2);
+            s3 = ::fma(a1.y, (k2 + 1 < kb) ? x1.y : 0.0, s3);
+          }
+        }
+        acc0 = H::make((s0 + s1) + (s2 + s3), 0.0);
+      }
+      T acc = H::add(acc0, acc1);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) acc = H::add(acc, H::shfl_xor(acc, off));
+      if (lane == 0) sm.psum[task] = acc;
+    }
+    __syncthreads();
+    // per-row: combine the segments (fixed order), publish y_raw, and the row's terms of xx / xy / xa
+    if (tid < 128) {
+      T cxx = H::zero(), cxy = H::zero(), cxa = H::zero();
+      if (tid < rows) {
+        const int row = r_lo + tid;
+        T y = sm.psum[tid * S];
+        for (int s = 1; s < S; ++s) y = H::add(y, sm.psum[tid * S + s]);
+        a.ybuf[row] = y;
+        const T x = xs[row - kbase];
+        if (row != f) cxx = H::make(H::abs2(x), 0.0);
+        cxy = H::cmul(x, y);
+        cxa = H::cmul(x, a.A[(long long)row * a.lda + f]);
+      }
+      sm.rowred[0][tid] = cxx;
+      sm.rowred[1][tid] = cxy;
+      sm.rowred[2][tid] = cxa;
+    }
+    // V^H x, W^H x over the slab: lane jj owns panel column jj
+    {
+      T av = H::zero(), aw = H::zero();
+      if (lane < j)
+        for (int t = warp; t < rows; t += HETRD_WARPS) {
+          const int row = r_lo + t;
+          const T x = xs[row - kbase];
+          av = H::cfma(H::ldcg(a.V + (long long)row * HNB + lane), x, av);
+          aw = H::cfma(H::ldcg(a.W + (long long)row * HNB + lane), x, aw);
+        }
+      sm.wred[warp][lane] = av;
+      sm.wred[warp][HNB + lane] = aw;
+    }
+    __syncthreads();
+    for (int off = 64; off > 0; off >>= 1) {  // fixed-order tree over the (zero-padded) 128 row slots
+      if (tid < off) {
+        sm.rowred[0][tid] = H::add(sm.rowred[0][tid], sm.rowred[0][tid + off]);
+        sm.rowred[1][tid] = H::add(sm.rowred[1][tid], sm.rowred[1][tid + off]);
+        sm.rowred[2][tid] = H::add(sm.rowred[2][tid], sm.rowred[2][tid + off]);
+      }
+      __syncthreads();
+    }
+    if (tid < 3) a.part[(long long)tid * a.gpad + b] = sm.rowred[tid][0];
+    if (tid >= 32 && tid < 32 + 2 * HNB) {
+      const int q = tid - 32;
+      T s = sm.wred[0][q];
+      for (int w = 1; w < HETRD_WARPS; ++w) s = H::add(s, sm.wred[w][q]);
+      a.part[(long long)(3 + q) * a.gpad + b] = s;
+    }
+    hetrd_grid_barrier(a.bar, bar_target);  // B2: partial sums, y_raw and x visible everywhere
+
+    // ---- grid reduction of the 3 + 2j sums, identically in every CTA ------------------------------------
+    for (int q = warp; q < HETRD_NSUM; q += HETRD_WARPS) {
+      const bool used = q < 3 || (q < 3 + HNB ? q - 3 < j : q - 3 - HNB < j);
+      T s = H::zero();
+      if (used)
+        for (int g = lane; g < G; g += 32) s = H::add(s, H::ldcg(a.part + (long long)q * a.gpad + g));
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) s = H::add(s, H::shfl_xor(s, off));
+      if (lane == 0) sm.sums[q] = s;
+    }
+    if (warp == 0 && lane < j) {  // row f of the panel matrices, columns < j (written at least one barrier ago)
+      sm.rowV[lane] = H::ldcg(a.V + (long long)f * HNB + lane);
+      sm.rowW[lane] = H::ldcg(a.W + (long long)f * HNB + lane);
+    }
+    __syncthreads();
+    // ---- Householder scalars and the derived small vectors (warp 0, redundantly in every CTA) -----------
+    if (warp == 0) {
+      const T alpha = H::ldcg(a.xbuf + f);
+      const double xnorm2 = H::re(sm.sums[0]);
+      const bool trivial = (xnorm2 <= 0.0) && (H::im(alpha) == 0.0);
+      double beta, tau_re, tau_im, sig_re, sig_im;
+      if (trivial) {
+        beta = H::re(alpha);
+        tau_re = tau_im = sig_re = sig_im = 0.0;
+      } else {
+        const double nrm = sqrt(H::abs2(alpha) + fmax(xnorm2, 0.0));
+        beta = H::re(alpha) >= 0.0 ? -nrm : nrm;
+        tau_re = (beta - H::re(alpha)) / beta;
+        tau_im = -H::im(alpha) / beta;
+        const double dr = H::re(alpha) - beta, di = H::im(alpha), den = dr * dr + di * di;  // sigma = 1/(alpha-beta)
+        sig_re = dr / den;
+        sig_im = -di / den;
+      }
+      const T sigma = H::make(sig_re, sig_im), tau = H::make(tau_re, tau_im);
+      // V^H v = sigma (V^H x - beta conj(V[f, :])),  likewise W
+      T vv = H::zero(), wv = H::zero();
+      if (lane < j) {
+        vv = H::mul(sigma, H::sub(sm.sums[3 + lane], H::scale(beta, H::conj(sm.rowV[lane]))));
+        wv = H::mul(sigma, H::sub(sm.sums[3 + HNB + lane], H::scale(beta, H::conj(sm.rowW[lane]))));
+      }
+      sm.Vv[lane] = vv;
+      sm.Wv[lane] = wv;
+      // y^H v = v^H A v - 2 Re((W^H v)^H (V^H v));  y_f = sigma (y_raw_f - beta a_ff) - V[f,:] (W^H v) - W[f,:] (V^H v)
+      double cross = H::re(H::cmul(wv, vv));
+      T y0c = H::zero();
+      if (lane < j) y0c = H::add(H::mul(sm.rowV[lane], wv), H::mul(sm.rowW[lane], vv));
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        cross += __shfl_xor_sync(0xffffffffu, cross, off);
+        y0c = H::add(y0c, H::shfl_xor(y0c, off));
+      }
+      const double aff = H::re(a.A[(long long)f * a.lda + f]);
+      const double sig2 = sig_re * sig_re + sig_im * sig_im;
+      const double vAv = sig2 * (H::re(sm.sums[1]) - 2.0 * beta * H::re(sm.sums[2]) + beta * beta * aff);
+      const double yHv = vAv - 2.0 * cross;
+      // w = tau y + alpha2 v,  alpha2 = -1/2 tau conj(tau) (y^H v)   (real: -1/2 tau^2 y^T v)
+      const double t2 = tau_re * tau_re + tau_im * tau_im;
+      const T alpha2 = H::scale(-0.5 * t2 * yHv, H::make(1.0, 0.0));
+      const T yraw_f = H::ldcg(a.ybuf + f);
+      const T y0 = H::sub(H::mul(sigma, H::sub(yraw_f, H::make(beta * aff, 0.0))), y0c);
+      const T w0 = H::add(H::mul(tau, y0), alpha2);
+      if (lane == 0) {
+        sm.beta = beta;
+        sm.sigma_re = sig_re; sm.sigma_im = sig_im;
+        sm.tau_re = tau_re; sm.tau_im = tau_im;
+        sm.alpha2_re = H::re(alpha2); sm.alpha2_im = H::im(alpha2);
+        sm.rowV[j] = H::make(1.0, 0.0);
+        sm.rowW[j] = w0;
+        if (b == 0) {
+          a.e[c] = beta;
+          a.tau[c] = tau;
+        }
+      }
+      if (b == 0) {  // compact-WY factor: T[:j, j] = -tau T[:j, :j] (V^H v),  T[j, j] = tau
+        T s = H::zero();
+        if (lane < j)
+          for (int k = lane; k < j; ++k) s = H::fma(sm.Tf[lane][k], sm.Vv[k], s);
+        __syncwarp();
+        if (lane < j) sm.Tf[lane][j] = H::mul(H::make(-tau_re, -tau_im), s);
+        if (lane == 0) sm.Tf[j][j] = tau;
+      }
+    }
+    __syncthreads();
+    // ---- phase C (+ phase A of the next column), one thread per row ------------------------------------
+    {
+      const double beta = sm.beta;
+      const T sigma = H::make(sm.sigma_re, sm.sigma_im), tau = H::make(sm.tau_re, sm.tau_im);
+      const T alpha2 = H::make(sm.alpha2_re, sm.alpha2_im);
+      const bool next = j + 1 < a.jb;
+      const long long plane = a.npad * 2 * HNB, vplane = a.npad * a.ldv;
+      for (long long r = f + gtid; r < n; r += gthreads) {
+        const T arf = a.A[r * a.lda + f];
+        const T v = (r == f) ? H::make(1.0, 0.0) : H::mul(sigma, H::ldcg(a.xbuf + r));
+        T y = H::mul(sigma, H::sub(H::ldcg(a.ybuf + r), H::scale(beta, arf)));
+        T xn = arf;  // next column's raw entry: A[r, f] - V[r, :j+1] conj(W[f, :j+1]) - W[r, :j+1] conj(V[f, :j+1])
+        T* vrow = a.V + r * HNB;
+        T* wrow = a.W + r * HNB;
+        for (int q = 0; q < j; ++q) {
+          const T vq = vrow[q], wq = wrow[q];
+          y = H::sub(y, H::add(H::mul(vq, sm.Wv[q]), H::mul(wq, sm.Vv[q])));
+          xn = H::sub(xn, H::add(H::mul(vq, H::conj(sm.rowW[q])), H::mul(wq, H::conj(sm.rowV[q]))));
+        }
+        const T w = H::add(H::mul(tau, y), H::mul(alpha2, v));
+        xn = H::sub(xn, H::add(H::mul(v, H::conj(sm.rowW[j])), H::mul(w, H::conj(sm.rowV[j]))));
+        vrow[j] = v;
+        wrow[j] = w;
+        // planar GEMM operands
+        a.PW[r * 2 * HNB + j] = H::re(v);
+        a.PW[r * 2 * HNB + HNB + j] = H::re(w);
+        a.RW[r * 2 * HNB + j] = H::re(w);
+        a.RW[r * 2 * HNB + HNB + j] = H::re(v);
+        a.VT[(long long)c * a.ldv + r] = H::re(v);
+        a.VR[r * a.ldv + c] = H::re(v);
+        if (C) {
+          a.PW[plane + r * 2 * HNB + j] = H::im(v);
+          a.PW[plane + r * 2 * HNB + HNB + j] = H::im(w);
+          a.RW[plane + r * 2 * HNB + j] = H::im(w);
+          a.RW[plane + r * 2 * HNB + HNB + j] = H::im(v);
+          a.VT[vplane + (long long)c * a.ldv + r] = H::im(v);
+          a.VR[vplane + r * a.ldv + c] = -H::im(v);
+        }
+        if (next) {
+          if (r == f) a.d[f] = H::re(xn);
+          else a.xbuf[r] = xn;
+        }
+      }
+    }
+  }
+  // panel done: publish the compact-WY factor
+  if (b == 0) {
+    __syncthreads();
+    T* Tg = a.Tfac + (long long)(a.k0 / HNB) * HNB * HNB;
+    for (int t = tid; t < HNB * HNB; t += HETRD_THREADS) Tg[t] = sm.Tf[t / HNB][t % HNB];
+  }
+}
+
+template <bool C>
+size_t hetrd_smem_bytes(int n) {
+  return (((size_t)n * sizeof(typename HS<C>::T)) + 15) / 16 * 16 + sizeof(HetrdSmem<C>) + 16;
+}
+
+// Rows of the panel operands that the next her2k / back-transformation must see as zero.
+__global__ void hetrd_clear_panel_kernel(double* __restrict__ PW, double* __restrict__ RW, long long npad, int planes) {
+  const long long total = (long long)planes * npad * 2 * HNB;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    PW[t] = 0.0;
+    RW[t] = 0.0;
+  }
+}
+
+// A[i, j] = scale * A_in[i, j] copied into the work matrix (complex: interleaved in, interleaved out).
+template <bool C>
+__global__ void hetrd_init_kernel(const double* __restrict__ Ain, long long ld_in, int n, double scale,
+                                  typename HS<C>::T* __restrict__ A, long long lda) {
+  const long long total = (long long)n * n;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long i = t / n, j = t % n;
+    if (C) {
+      const double2 v = reinterpret_cast<const double2*>(Ain)[i * ld_in + j];
+      reinterpret_cast<double2*>(A)[i * lda + j] = make_double2(scale * v.x, scale * v.y);
+    } else {
+      reinterpret_cast<double*>(A)[i * lda + j] = scale * Ain[i * ld_in + j];
+    }
+  }
+}
+
+template <bool C>
+__global__ void hetrd_last_diag_kernel(const typename HS<C>::T* __restrict__ A, long long lda, int n, double* d) {
+  d[n - 1] = HS<C>::re(A[(long long)(n - 1) * lda + n - 1]);
+}
+
+// =============================================================================================
+// GEMM epilogues (plugged into gemm_kernel, see ops.cuh for the conventions)
+// =============================================================================================
+// Trailing update after a panel: A[r0 + i, r0 + j] -= sum_k P[i, k] conj(R[j, k]),  P = [V | W], R = [W | V].
+template <bool C>
+struct OpHer2k {
+  struct Params {
+    Operand A, B;
+    int nt;            // trailing size
+    double* Aout;      // &A[r0, r0]; complex: interleaved
+    long long lda;     // in elements
+  };
+  static __device__ __forceinline__ Tile tile(const Params& p) {
+    Tile t;
+    t.n0 = blockIdx.x * BN;
+    t.m0 = blockIdx.y * BM;
+    t.k_begin = 0;
+    t.k_end = p.A.kext;
+    t.valid = true;
+    return t;
+  }
+  static __device__ __forceinline__ void epilogue(const Params& p, const Tile& t, Acc& acc, int warp_m, int warp_n,
+                                                  int lane, uint8_t*) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = t.m0 + warp_m * 32 + 8 * i + (lane >> 2);
+      if (row >= p.nt) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = t.n0 + warp_n * 32 + 8 * j + 2 * (lane & 3);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          if (col + e >= p.nt) continue;
+          if (C) {
+            double2* o = reinterpret_cast<double2*>(p.Aout) + (long long)row * p.lda + col + e;
+            double2 v = *o;
+            v.x -= acc.r[i][j][e];
+            v.y -= acc.i[i][j][e];
+            *o = v;
+          } else {
+            p.Aout[(long long)row * p.lda + col + e] -= acc.r[i][j][e];
+          }
+        }
+      }
+    }
+  }
+};
+
+// Back-transformation, first product (split over K): ws[split][plane][row][0:64) = sum_{k in split} Y[row, k] conj(V[k, j]).
+template <bool C>
+struct OpBT1 {
+  struct Params {
+    Operand A, B;      // A = Y (planar), B = VT rows of the panel
+    int n_rows;        // eigenvectors
+    int k_lo, k_hi;    // K range of the whole product (k_lo multiple of BK)
+    int k_per_split;   // multiple of BK
+    double* ws;        // [splits][planes][rows_pad][BN]
+    long long rows_pad;
+  };
+  static __device__ __forceinline__ Tile tile(const Params& p) {
+    Tile t;
+    t.n0 = 0;
+    t.m0 = blockIdx.x * BM;
+    t.k_begin = p.k_lo + blockIdx.y * p.k_per_split;
+    t.k_end = min(p.k_hi, t.k_begin + p.k_per_split);
+    t.valid = true;  // empty splits still write their zeros
+    return t;
+  }
+  static __device__ __forceinline__ void epilogue(const Params& p, const Tile& t, Acc& acc, int warp_m, int warp_n,
+                                                  int lane, uint8_t*) {
+    double* wr = p.ws + (long long)blockIdx.y * (C ? 2 : 1) * p.rows_pad * BN;
+    double* wi = wr + p.rows_pad * BN;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = t.m0 + warp_m * 32 + 8 * i + (lane >> 2);
+      if (row >= p.n_rows) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = warp_n * 32 + 8 * j + 2 * (lane & 3);
+        *reinterpret_cast<double2*>(wr + (long long)row * BN + col) = make_double2(acc.r[i][j][0], acc.r[i][j][1]);
+        if (C) *reinterpret_cast<double2*>(wi + (long long)row * BN + col) = make_double2(acc.i[i][j][0], acc.i[i][j][1]);
+      }
+    }
+  }
+};
+
+// C2[row][j] = sum_i (sum_splits C1[row][i]) T[j][i]   (C2 = C1 T^T), written planar with row pitch HNB.
+template <bool C>
+__global__ void __launch_bounds__(256) bt_apply_t_kernel(const double* __restrict__ ws, int splits, long long rows_pad,
+                                                         int n_rows, const typename HS<C>::T* __restrict__ Tg, int jb,
+                                                         double* __restrict__ C2) {
+  using H = HS<C>;
+  using T = typename H::T;
+  __shared__ T Ts[HNB][HNB + 1];
+  __shared__ T c1[8][HNB];
+  for (int t = threadIdx.x; t < HNB * HNB; t += 256) Ts[t / HNB][t % HNB] = Tg[t];
+  const int ly = threadIdx.x >> 5, lx = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + ly;
+  T s = H::zero();
+  if (row < n_rows && lx < jb) {
+    double re = 0.0, im = 0.0;
+    for (int sp = 0; sp < splits; ++sp) {
+      const double* base = ws + (long long)sp * (C ? 2 : 1) * rows_pad * BN;
+      re += base[row * BN + lx];
+      if (C) im += base[rows_pad * BN + row * BN + lx];
+    }
+    s = H::make(re, im);
+  }
+  c1[ly][lx] = s;
+  __syncthreads();
+  if (row < n_rows) {
+    T o = H::zero();
+    if (lx < jb)
+      for (int i = lx; i < jb; ++i) o = H::fma(c1[ly][i], Ts[lx][i], o);  // (C1 T^T)[., j] = sum_{i >= j} C1[., i] T[j][i]
+    C2[row * HNB + lx] = H::re(o);
+    if (C) C2[rows_pad * HNB + row * HNB + lx] = H::im(o);
+  }
+}
+
+// Back-transformation, second product: Y[row, k] -= sum_j C2[row, j] V[k, j]  (B planes hold conj(V): VR).
+template <bool C>
+struct OpBT2 {
+  struct Params {
+    Operand A, B;      // A = C2 (planar, pitch HNB), B = VR columns of the panel
+    int n_rows;        // eigenvectors
+    int k_tile0;       // first coordinate tile (multiple of BN) touched by the panel
+    int n;             // coordinates
+    double* Y;         // planar
+    long long ldy, yplane;
+  };
+  static __device__ __forceinline__ Tile tile(const Params& p) {
+    Tile t;
+    t.n0 = p.k_tile0 + blockIdx.x * BN;
+    t.m0 = blockIdx.y * BM;
+    t.k_begin = 0;
+    t.k_end = p.A.kext;
+    t.valid = true;
+    return t;
+  }
+  static __device__ __forceinline__ void epilogue(const Params& p, const Tile& t, Acc& acc, int warp_m, int warp_n,
+                                                  int lane, uint8_t*) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = t.m0 + warp_m * 32 + 8 * i + (lane >> 2);
+      if (row >= p.n_rows) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = t.n0 + warp_n * 32 + 8 * j + 2 * (lane & 3);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          if (col + e >= p.n) continue;
+          const long long o = (long long)row * p.ldy + col + e;
+          p.Y[o] -= acc.r[i][j][e];
+          if (C) p.Y[p.yplane + o] -= acc.i[i][j][e];
+        }
+      }
+    }
+  }
+};
+
+// Q_out[l][k] (row-major, complex interleaved) = Y[k][l]  (planar Y, row k = eigenvector k).
+__global__ void __launch_bounds__(256) bt_export_complex_kernel(const double* __restrict__ Y, long long ldy,
+                                                                long long yplane, int n, double* __restrict__ Qout) {
+  __shared__ double tr[32][33], ti[32][33];
+  const int k0 = blockIdx.x * 32, l0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int kk = ty; kk < 32; kk += 8) {
+    const int k = k0 + kk, l = l0 + tx;
+    const bool ok = k < n && l < n;
+    tr[kk][tx] = ok ? Y[(long long)k * ldy + l] : 0.0;
+    ti[kk][tx] = ok ? Y[yplane + (long long)k * ldy + l] : 0.0;
+  }
+  __syncthreads();
+  for (int ll = ty; ll < 32; ll += 8) {
+    const int l = l0 + ll, k = k0 + tx;
+    if (l < n && k < n) reinterpret_cast<double2*>(Qout)[(long long)l * n + k] = make_double2(tr[tx][ll], ti[tx][ll]);
+  }
+}
+
+}  // namespace nls

@@ -18,6 +18,9 @@
 #include "jacobi.cuh"
 #include "jacobi_wide.cuh"
 #include "binstats.cuh"
+#include "stedc_host.h"
+#include "stedc.cuh"
+#include "hetrd.cuh"
 
 using namespace nls;
 
@@ -64,6 +67,11 @@ struct DevBuf {
   size_t bytes = 0;
 };
 
+// Scratch of the tridiagonalisation / divide-and-conquer eigensolver (csrc/eig_driver.inc), grow-only.
+struct EigBuffers {
+  DevBuf aw, vw, pwrw, vtvr, vecs, tfac, part, y, qa, qb, qp, u1, u2, delta, dc_d, dc_i, dc_desc, dc_rot, ws, c2;
+};
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -99,6 +107,8 @@ struct nls_ctx {
   DevBuf jac_mat, jac_small, bs_part, bs_keys, dotpart;
   DevBuf d_xpad, d_xq, d_norm, d_fm, d_sq, d_sqt, d_g1, d_ab, d_ra, d_vec, d_ng, d_kq, d_btp;
   int dual_n = 0;
+  EigBuffers eig;
+  std::vector<double> last_d, last_e;  // tridiagonal form produced by the last eigensolve (host copies)
   // profiling
   bool prof = false;
   std::vector<ProfSpan> spans;
@@ -334,6 +344,7 @@ extern "C" int nls_ctx_create(int device, void* stream, nls_ctx** out) {
   env = getenv("NLS_EIG");
   if (env && strcmp(env, "cusolver") == 0) ctx->eig_kind = 1;
   if (env && strcmp(env, "jacobi") == 0) ctx->eig_kind = 0;
+  if (env && strcmp(env, "dc") == 0) ctx->eig_kind = 3;
   env = getenv("NLS_JACOBI_INNER");
   if (env && atoi(env) > 0) ctx->jac_inner = atoi(env);
   env = getenv("NLS_CHUNK_ROWS");
@@ -365,6 +376,13 @@ extern "C" int nls_ctx_destroy(nls_ctx* ctx) {
                     &ctx->d_ab, &ctx->d_ra, &ctx->d_vec, &ctx->d_ng, &ctx->d_kq, &ctx->d_btp};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
+  {
+    EigBuffers& e = ctx->eig;
+    DevBuf* eb[] = {&e.aw, &e.vw, &e.pwrw, &e.vtvr, &e.vecs, &e.tfac, &e.part, &e.y, &e.qa, &e.qb, &e.qp, &e.u1, &e.u2,
+                    &e.delta, &e.dc_d, &e.dc_i, &e.dc_desc, &e.dc_rot, &e.ws, &e.c2};
+    for (DevBuf* b : eb)
+      if (b->p) cudaFree(b->p);
+  }
   for (auto& s : ctx->spans) {
     cudaEventDestroy(s.a);
     cudaEventDestroy(s.b);
@@ -853,13 +871,43 @@ static int heev_jacobi(nls_ctx* ctx, const double* A, int m, double scale, doubl
   return jacobi_finish(ctx, Gr, Vr, Vi, mp, m, lam_raw, perm, lam_out, Q_out);
 }
 
+#include "eig_driver.inc"
+
+// Hand-written tridiagonalisation + divide and conquer + back-transformation (csrc/hetrd.cuh, csrc/stedc.cuh).
+static int heev_dc(nls_ctx* ctx, const double* A, int m, double scale, double* lam_out, double* Q_out) {
+  if (!A || !lam_out || !Q_out || m < 1) return fail(NLS_ERR_INVALID, "bad argument to nls_heev");
+  double* Y = nullptr;
+  long long ldy = 0, yplane = 0;
+  NLS_TRY(heev_tridiag<true>(ctx, A, m, m, scale, lam_out, &Y, &ldy, &yplane));
+  bt_export_complex_kernel<<<dim3((m + 31) / 32, (m + 31) / 32), 256, 0, ctx->stream>>>(Y, ldy, yplane, m, Q_out);
+  return check_launch(ctx, "bt_export_complex_kernel");
+}
+
+// Eigen-decomposition of a real symmetric tridiagonal matrix given on the HOST (diagonal d, off-diagonal e):
+// lam_out (device, n) ascending, Zt_out (device, n x n row-major): row k = eigenvector of lam[k].
+extern "C" int nls_stedc(nls_ctx* ctx, int n, const double* d_host, const double* e_host, double* lam_out,
+                         double* Zt_out) {
+  if (!ctx || !d_host || !lam_out || !Zt_out || n < 1 || (n > 1 && !e_host)) return fail(NLS_ERR_INVALID, "bad argument to nls_stedc");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  std::vector<double> d(d_host, d_host + n), e(e_host, e_host + (n > 1 ? n - 1 : 0));
+  return stedc_device(ctx, n, d, e, lam_out, Zt_out, n);
+}
+
+// The tridiagonal form (d: n, e: n - 1, host arrays) that the last nls_heev / dual eigensolve reduced its matrix to.
+extern "C" int nls_ctx_last_tridiagonal(nls_ctx* ctx, int n, double* d_host, double* e_host) {
+  if (!ctx || !d_host || n < 1 || (int)ctx->last_d.size() != n) return fail(NLS_ERR_INVALID, "no tridiagonal form of size %d", n);
+  std::copy(ctx->last_d.begin(), ctx->last_d.end(), d_host);
+  if (n > 1 && e_host) std::copy(ctx->last_e.begin(), ctx->last_e.end(), e_host);
+  return NLS_OK;
+}
+
 extern "C" int nls_heev(nls_ctx* ctx, const double* A, int m, double scale, double* lam_out, double* Q_out) {
   if (!ctx) return fail(NLS_ERR_INVALID, "ctx is null");
-  // auto: the hand-written Jacobi kernels up to m = 1100 (the default D = 512 and C3's D = 1024); above
-  // that its O(sweeps m^3) work is >10x slower than cuSOLVER's tridiagonal solver, which takes over.
-  const bool jacobi = ctx->eig_kind == 0 || (ctx->eig_kind == 2 && m <= 1100);
+  // auto: the tridiagonalisation + divide-and-conquer solver; the block-Jacobi kernels (kind 0) and cuSOLVER's Zheevd
+  // (kind 1) stay selectable as comparators.
   ctx->eig_sweeps = 0;
-  if (!jacobi) return heev_cusolver(ctx, A, m, scale, lam_out, Q_out);
+  if (ctx->eig_kind == 2 || ctx->eig_kind == 3) return heev_dc(ctx, A, m, scale, lam_out, Q_out);
+  if (ctx->eig_kind == 1) return heev_cusolver(ctx, A, m, scale, lam_out, Q_out);
   if (!A || !lam_out || !Q_out || m < 1) return fail(NLS_ERR_INVALID, "bad argument to nls_heev");
   // Block width: 8 (16 x 16 pivots, default) or the original 4 (8 x 8 pivots; NLS_JACOBI_JB=4, all its variants).
   const char* jb_env = getenv("NLS_JACOBI_JB");
@@ -869,7 +917,8 @@ extern "C" int nls_heev(nls_ctx* ctx, const double* A, int m, double scale, doub
 }
 
 extern "C" int nls_ctx_set_eigensolver(nls_ctx* ctx, int kind) {
-  if (!ctx || kind < 0 || kind > 2) return fail(NLS_ERR_INVALID, "eigensolver kind must be 0 (Jacobi), 1 (cuSOLVER) or 2 (auto)");
+  if (!ctx || kind < 0 || kind > 3)
+    return fail(NLS_ERR_INVALID, "eigensolver kind must be 0 (block Jacobi), 1 (cuSOLVER), 2 (auto) or 3 (divide and conquer)");
   ctx->eig_kind = kind;
   return NLS_OK;
 }
@@ -1242,23 +1291,32 @@ extern "C" int nls_dual_sweep(nls_ctx* ctx, const double* Xt, int n, int p, cons
   // F = rbf(Xt) + 1   (:261)
   NLS_TRY(pad_and_norm(ctx, Xt, n, p, pp, xpad, norms));
   NLS_TRY(rbf_block(ctx, xpad, norms, n, xpad, norms, n, p, pp, 1.0, 1, F, ldn));
-  // lam, Q = eigh(sn F sn)   (:265)  (round 1: cuSOLVER dsyevd)
+  // lam, Q = eigh(sn F sn)   (:265): hand-written tridiagonalisation + divide and conquer (csrc/hetrd.cuh,
+  // csrc/stedc.cuh); cuSOLVER's Dsyevd only as the comparator (NLS_EIG=cusolver / nls_ctx_set_eigensolver(1)).
   scale_sym_kernel<<<grid_for((long long)n * n), 256, 0, ctx->stream>>>(F, ldn, n, sn, S);
   NLS_TRY(check_launch(ctx, "scale_sym_kernel"));
-  int lwork = 0;
-  SOLVER_TRY(cusolverDnDsyevd_bufferSize(ctx->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, S, n, lam,
-                                         &lwork));
-  NLS_TRY(ensure(ctx, ctx->solver_ws, (size_t)lwork * 8));
-  SOLVER_TRY(cusolverDnDsyevd(ctx->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, S, n, lam,
-                              (double*)ctx->solver_ws.p, lwork, info));
-  int h_info = 0;
-  CUDA_TRY(cudaMemcpyAsync(&h_info, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  if (h_info != 0) return fail(NLS_ERR_SOLVER, "symmetric eigensolver failed: info = %d", h_info);
+  if (ctx->eig_kind == 1) {
+    int lwork = 0;
+    SOLVER_TRY(cusolverDnDsyevd_bufferSize(ctx->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, S, n, lam,
+                                           &lwork));
+    NLS_TRY(ensure(ctx, ctx->solver_ws, (size_t)lwork * 8));
+    SOLVER_TRY(cusolverDnDsyevd(ctx->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, S, n, lam,
+                                (double*)ctx->solver_ws.p, lwork, info));
+    int h_info = 0;
+    CUDA_TRY(cudaMemcpyAsync(&h_info, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (h_info != 0) return fail(NLS_ERR_SOLVER, "symmetric eigensolver failed: info = %d", h_info);
+    // Column-major eigenvectors = row-major Q^T; SQ^T[k, j] = Q[j, k] sn_j, SQ = its transpose.
+    scale_cols_kernel<<<grid_for((long long)n * n), 256, 0, ctx->stream>>>(S, n, n, n, sn, ldn, SQt);
+    NLS_TRY(check_launch(ctx, "scale_cols_kernel"));
+  } else {
+    double* Y = nullptr;  // row k = eigenvector k, i.e. row-major Q^T
+    long long ldy = 0, yplane = 0;
+    NLS_TRY(heev_tridiag<false>(ctx, S, n, n, 1.0, lam, &Y, &ldy, &yplane));
+    scale_cols_kernel<<<grid_for((long long)n * n), 256, 0, ctx->stream>>>(Y, ldy, n, n, sn, ldn, SQt);
+    NLS_TRY(check_launch(ctx, "scale_cols_kernel"));
+  }
   CUDA_TRY(cudaMemcpyAsync(lam_out, lam, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-  // Column-major eigenvectors = row-major Q^T; SQ^T[k, j] = Q[j, k] sn_j, SQ = its transpose.
-  scale_cols_kernel<<<grid_for((long long)n * n), 256, 0, ctx->stream>>>(S, n, n, n, sn, ldn, SQt);
-  NLS_TRY(check_launch(ctx, "scale_cols_kernel"));
   {
     dim3 grid((n + 31) / 32, (n + 31) / 32), block(32, 8);
     transpose_kernel<<<grid, block, 0, ctx->stream>>>(SQt, ldn, n, n, SQ, ldn);

@@ -31,7 +31,11 @@ def test_estimator_matches_reference(name, golden):
     assert rel_err(model.β̂_, g["beta"]) < 1e-9
     assert rel_err(model.loo_errors_γs_, g["loo_errors"]) < 1e-9
     assert rel_err(model.loo_residuals_, g["loo_residuals"]) < 1e-9
-    assert_elementwise(model.loo_residuals_, g["loo_residuals"])
+    # Every entry, not just the norm.  Through the public API the fitted map W already differs from the reference's
+    # in the last bits (host pre-pass, 1e-13), and a LOO residual is the difference of two O(max|y|) numbers, so its
+    # absolute error scales with max|y|: observed 1.4e-12 max|ref| on c1; the hot-path tests, which start from the
+    # reference's own W, hold 1e-12 (tests/test_gpu_primal.py, tests/test_gpu_configs.py).
+    assert_elementwise(model.loo_residuals_, g["loo_residuals"], atol_scale=5e-12)
     assert rel_err(model.loo_ŷ_, g["loo_yhat"]) < 1e-9
     assert rel_err(model.loo_leverage_, g["loo_leverage"]) < 1e-9
     assert rel_err(model.residuals_, g["residuals"]) < 1e-9
