@@ -27,6 +27,7 @@ constexpr int HNB = 32;            // panel width
 constexpr int HETRD_THREADS = 512;
 constexpr int HETRD_WARPS = HETRD_THREADS / 32;
 constexpr int HETRD_NSUM = 3 + 2 * HNB;  // grid-reduced sums per column
+constexpr int HETRD_SPAN = 512;          // elements of one unrolled hemv step per warp (real: 32 lanes x 2 x 8)
 
 // ---- scalar helpers: T = double (real symmetric) or double2 (complex Hermitian, interleaved re/im) -------------
 template <bool C> struct HS;
@@ -98,6 +99,7 @@ struct HetrdArgs {
   T* part;          // [HETRD_NSUM][gpad]
   int gpad;
   unsigned* bar;    // grid barrier counter (zeroed before every launch)
+  long long* dbg;   // optional [8] cycle counters of CTA 0 (diagnostics), may be null
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -135,13 +137,19 @@ struct HetrdSmem {
   double beta, sigma_re, sigma_im, tau_re, tau_im, alpha2_re, alpha2_im;
 };
 
+// Bytes of the x staging area: n elements rounded up to whole unrolled spans (+ one span of slack for the even base).
+template <bool C>
+__host__ __device__ inline size_t hetrd_xs_bytes(int n) {
+  return ((size_t)(n + 2 + HETRD_SPAN - 1) / HETRD_SPAN * HETRD_SPAN) * sizeof(typename HS<C>::T);
+}
+
 template <bool C>
 __global__ void __launch_bounds__(HETRD_THREADS, 1) hetrd_panel_kernel(const HetrdArgs<C> a) {
   using H = HS<C>;
   using T = typename H::T;
   extern __shared__ __align__(16) unsigned char hsm_raw[];
   T* xs = reinterpret_cast<T*>(hsm_raw);
-  HetrdSmem<C>& sm = *reinterpret_cast<HetrdSmem<C>*>(hsm_raw + (((size_t)a.n * sizeof(T)) + 15) / 16 * 16);
+  HetrdSmem<C>& sm = *reinterpret_cast<HetrdSmem<C>*>(hsm_raw + hetrd_xs_bytes<C>(a.n));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = gridDim.x, b = blockIdx.x;
   const int n = a.n;
@@ -164,63 +172,78 @@ __global__ void __launch_bounds__(HETRD_THREADS, 1) hetrd_panel_kernel(const Het
     const int c = a.k0 + j;      // column being reduced
     const int f = c + 1;         // first row of x / of the trailing matrix
     const int n1 = n - f;        // trailing size
+    long long tc0 = 0, tc1 = 0, tc2 = 0, tc3 = 0, tc4 = 0, tc5 = 0;
+    const bool prof = a.dbg != nullptr && b == 0 && tid == 0;
+    if (prof) tc0 = clock64();
     hetrd_grid_barrier(a.bar, bar_target);  // B1: x complete
+    if (prof) tc1 = clock64();
 
     // ---- phase B: y_raw = A[f:, f:] x for this CTA's row slab, plus the partial sums --------------------
     const int kbase = f & ~1;    // x staged from an even index (vector loads in the real case)
-    for (int k = kbase + tid; k < n; k += HETRD_THREADS) xs[k - kbase] = (k >= f) ? H::ldcg(a.xbuf + k) : H::zero();
+    const int nk = n - kbase;
+    const int nk_pad = (nk + HETRD_SPAN - 1) / HETRD_SPAN * HETRD_SPAN;  // zero tail: the unrolled loop needs no guards
+    for (int k = tid; k < nk_pad; k += HETRD_THREADS) {
+      const int kk = kbase + k;
+      xs[k] = (kk >= f && kk < n) ? H::ldcg(a.xbuf + kk) : H::zero();
+    }
     __syncthreads();
     const int R = (n1 + G - 1) / G;             // rows per CTA
     const int r_lo = f + b * R;
     const int rows = max(0, min(n, r_lo + R) - r_lo);
-    int S = 1;                                  // k segments per row (few rows per CTA: spread a row over warps)
-    if (R < HETRD_WARPS) {
-      S = HETRD_WARPS / max(R, 1);
-      while (S > 1 && (n - kbase) / S < 128) S >>= 1;
-      if (S > 8) S = 8;
-    }
-    const int nk = n - kbase;
-    const int seglen = ((nk + S - 1) / S + 63) & ~63;
+    // k segments per row: with few rows per CTA a row is spread over several warps (two tasks per warp is the aim);
+    // a segment is a whole number of unrolled spans.
+    int S = 1;
+    if (R < 2 * HETRD_WARPS) S = max(1, min(min(2 * HETRD_WARPS / max(R, 1), nk_pad / HETRD_SPAN), 16));
+    const int seglen = ((nk_pad / HETRD_SPAN + S - 1) / S) * HETRD_SPAN;
     for (int task = warp; task < rows * S; task += HETRD_WARPS) {
       const int row = r_lo + task / S, seg = task % S;
-      const int ka = kbase + seg * seglen, kb = min(n, ka + seglen);
-      const T* arow = a.A + (long long)row * a.lda;
-      T acc0 = H::zero(), acc1 = H::zero();
+      const int ka = seg * seglen, kb = min(nk_pad, ka + seglen);  // relative to kbase
+      const T* arow = a.A + (long long)row * a.lda + kbase;
+      T acc;
       if (C) {
-        for (int k = ka + lane; k < kb; k += 64) {
-          const T a0 = arow[k];
-          const T x0 = xs[k - kbase];
-          const bool two = k + 32 < kb;
-          const T a1 = two ? arow[k + 32] : H::zero();
-          const T x1 = two ? xs[k + 32 - kbase] : H::zero();
-          acc0 = H::fma(a0, x0, acc0);
-          acc1 = H::fma(a1, x1, acc1);
+        // HETRD_UNR independent 16-byte loads in flight per lane; indices past the row are clamped (x is zero there)
+        const int kmax = (int)a.lda - 1 - kbase;
+        T c0 = H::zero(), c1 = H::zero(), c2 = H::zero(), c3 = H::zero();
+        for (int k = ka + lane; k < kb; k += 32 * 8) {
+          T av[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) av[u] = arow[min(k + 32 * u, kmax)];
+#pragma unroll
+          for (int u = 0; u < 8; u += 4) {
+            c0 = H::fma(av[u], xs[k + 32 * u], c0);
+            c1 = H::fma(av[u + 1], xs[k + 32 * (u + 1)], c1);
+            c2 = H::fma(av[u + 2], xs[k + 32 * (u + 2)], c2);
+            c3 = H::fma(av[u + 3], xs[k + 32 * (u + 3)], c3);
+          }
         }
+        acc = H::add(H::add(c0, c1), H::add(c2, c3));
       } else {
         const double* ar = reinterpret_cast<const double*>(arow);
         const double* xr = reinterpret_cast<const double*>(xs);
+        const int kmax = (int)a.lda - 2 - kbase;  // even
         double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        for (int k = ka + 2 * lane; k < kb; k += 128) {  // ka, kbase even: 16-byte aligned pairs
-          const double2 a0 = (k + 1 < n) ? *reinterpret_cast<const double2*>(ar + k) : make_double2(ar[k], 0.0);
-          const double2 x0 = *reinterpret_cast<const double2*>(xr + (k - kbase));
-          s0 = ::fma(a0.x, x0.x, s0);
-          s1 = ::fma(a0.y, (k + 1 < kb) ? x0.y : 0.0, s1);
-          const int k2 = k + 64;
-          if (k2 < kb) {
-            const double2 a1 = (k2 + 1 < n) ? *reinterpret_cast<const double2*>(ar + k2) : make_double2(ar[k2], 0.0);
-            const double2 x1 = *reinterpret_cast<const double2*>(xr + (k2 - kbase));
-            s2 = ::fma(a1.x, x1.x, s2);
-            s3 = ::fma(a1.y, (k2 + 1 < kb) ? x1.y : 0.0, s3);
+        for (int k = ka + 2 * lane; k < kb; k += 64 * 8) {  // kbase, ka even: 16-byte aligned pairs
+          double2 av[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) av[u] = *reinterpret_cast<const double2*>(ar + min(k + 64 * u, kmax));
+#pragma unroll
+          for (int u = 0; u < 8; u += 2) {
+            const double2 x0 = *reinterpret_cast<const double2*>(xr + k + 64 * u);
+            const double2 x1 = *reinterpret_cast<const double2*>(xr + k + 64 * (u + 1));
+            s0 = ::fma(av[u].x, x0.x, s0);
+            s1 = ::fma(av[u].y, x0.y, s1);
+            s2 = ::fma(av[u + 1].x, x1.x, s2);
+            s3 = ::fma(av[u + 1].y, x1.y, s3);
           }
         }
-        acc0 = H::make((s0 + s1) + (s2 + s3), 0.0);
+        acc = H::make((s0 + s1) + (s2 + s3), 0.0);
       }
-      T acc = H::add(acc0, acc1);
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) acc = H::add(acc, H::shfl_xor(acc, off));
       if (lane == 0) sm.psum[task] = acc;
     }
     __syncthreads();
+    if (prof) tc2 = clock64();
     // per-row: combine the segments (fixed order), publish y_raw, and the row's terms of xx / xy / xa
     if (tid < 128) {
       T cxx = H::zero(), cxy = H::zero(), cxa = H::zero();
@@ -252,41 +275,66 @@ __global__ void __launch_bounds__(HETRD_THREADS, 1) hetrd_panel_kernel(const Het
       sm.wred[warp][HNB + lane] = aw;
     }
     __syncthreads();
-    for (int off = 64; off > 0; off >>= 1) {  // fixed-order tree over the (zero-padded) 128 row slots
-      if (tid < off) {
-        sm.rowred[0][tid] = H::add(sm.rowred[0][tid], sm.rowred[0][tid + off]);
-        sm.rowred[1][tid] = H::add(sm.rowred[1][tid], sm.rowred[1][tid + off]);
-        sm.rowred[2][tid] = H::add(sm.rowred[2][tid], sm.rowred[2][tid + off]);
-      }
-      __syncthreads();
+    if (warp < 3) {  // fixed-order reduction of the (zero-padded) 128 row slots: 4 per lane, then a butterfly
+      T s4 = H::add(H::add(sm.rowred[warp][lane], sm.rowred[warp][lane + 32]),
+                    H::add(sm.rowred[warp][lane + 64], sm.rowred[warp][lane + 96]));
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) s4 = H::add(s4, H::shfl_xor(s4, off));
+      if (lane == 0) a.part[(long long)warp * a.gpad + b] = s4;
     }
-    if (tid < 3) a.part[(long long)tid * a.gpad + b] = sm.rowred[tid][0];
-    if (tid >= 32 && tid < 32 + 2 * HNB) {
-      const int q = tid - 32;
+    if (tid >= 96 && tid < 96 + 2 * HNB) {
+      const int q = tid - 96;
       T s = sm.wred[0][q];
       for (int w = 1; w < HETRD_WARPS; ++w) s = H::add(s, sm.wred[w][q]);
       a.part[(long long)(3 + q) * a.gpad + b] = s;
     }
+    if (prof) tc3 = clock64();
     hetrd_grid_barrier(a.bar, bar_target);  // B2: partial sums, y_raw and x visible everywhere
+    if (prof) tc4 = clock64();
 
     // ---- grid reduction of the 3 + 2j sums, identically in every CTA ------------------------------------
-    for (int q = warp; q < HETRD_NSUM; q += HETRD_WARPS) {
-      const bool used = q < 3 || (q < 3 + HNB ? q - 3 < j : q - 3 - HNB < j);
-      T s = H::zero();
-      if (used)
-        for (int g = lane; g < G; g += 32) s = H::add(s, H::ldcg(a.part + (long long)q * a.gpad + g));
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) s = H::add(s, H::shfl_xor(s, off));
-      if (lane == 0) sm.sums[q] = s;
+    // Warp 0 first issues the loads its scalar phase needs, so that their latency hides behind the reduction.
+    T pre_alpha = H::zero(), pre_yraw = H::zero(), pre_aff = H::zero(), pre_rv = H::zero(), pre_rw = H::zero();
+    if (warp == 0) {
+      pre_alpha = H::ldcg(a.xbuf + f);
+      pre_yraw = H::ldcg(a.ybuf + f);
+      pre_aff = a.A[(long long)f * a.lda + f];
+      if (lane < j) {  // row f of the panel matrices, columns < j (written at least one barrier ago)
+        pre_rv = H::ldcg(a.V + (long long)f * HNB + lane);
+        pre_rw = H::ldcg(a.W + (long long)f * HNB + lane);
+      }
     }
-    if (warp == 0 && lane < j) {  // row f of the panel matrices, columns < j (written at least one barrier ago)
-      sm.rowV[lane] = H::ldcg(a.V + (long long)f * HNB + lane);
-      sm.rowW[lane] = H::ldcg(a.W + (long long)f * HNB + lane);
+    {
+      // Each warp owns the sums q = warp, warp + 16, ...; all of its loads are issued before the first use.
+      constexpr int QMAX = (HETRD_NSUM + HETRD_WARPS - 1) / HETRD_WARPS, GMAX = 5;  // G <= 160
+      T val[QMAX][GMAX];
+#pragma unroll
+      for (int t = 0; t < QMAX; ++t) {
+        const int q = warp + t * HETRD_WARPS;
+        const bool used = q < 3 || (q < HETRD_NSUM && (q < 3 + HNB ? q - 3 < j : q - 3 - HNB < j));
+#pragma unroll
+        for (int u = 0; u < GMAX; ++u) {
+          const int g = lane + 32 * u;
+          val[t][u] = (used && g < G) ? H::ldcg(a.part + (long long)q * a.gpad + g) : H::zero();
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < QMAX; ++t) {
+        const int q = warp + t * HETRD_WARPS;
+        T sacc = H::add(H::add(H::add(val[t][0], val[t][1]), H::add(val[t][2], val[t][3])), val[t][4]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sacc = H::add(sacc, H::shfl_xor(sacc, off));
+        if (lane == 0 && q < HETRD_NSUM) sm.sums[q] = sacc;
+      }
+    }
+    if (warp == 0 && lane < j) {
+      sm.rowV[lane] = pre_rv;
+      sm.rowW[lane] = pre_rw;
     }
     __syncthreads();
     // ---- Householder scalars and the derived small vectors (warp 0, redundantly in every CTA) -----------
     if (warp == 0) {
-      const T alpha = H::ldcg(a.xbuf + f);
+      const T alpha = pre_alpha;
       const double xnorm2 = H::re(sm.sums[0]);
       const bool trivial = (xnorm2 <= 0.0) && (H::im(alpha) == 0.0);
       double beta, tau_re, tau_im, sig_re, sig_im;
@@ -296,11 +344,13 @@ __global__ void __launch_bounds__(HETRD_THREADS, 1) hetrd_panel_kernel(const Het
       } else {
         const double nrm = sqrt(H::abs2(alpha) + fmax(xnorm2, 0.0));
         beta = H::re(alpha) >= 0.0 ? -nrm : nrm;
-        tau_re = (beta - H::re(alpha)) / beta;
-        tau_im = -H::im(alpha) / beta;
-        const double dr = H::re(alpha) - beta, di = H::im(alpha), den = dr * dr + di * di;  // sigma = 1/(alpha-beta)
-        sig_re = dr / den;
-        sig_im = -di / den;
+        const double inv_beta = 1.0 / beta;
+        tau_re = (beta - H::re(alpha)) * inv_beta;
+        tau_im = -H::im(alpha) * inv_beta;
+        const double dr = H::re(alpha) - beta, di = H::im(alpha);  // sigma = 1 / (alpha - beta)
+        const double inv_den = 1.0 / (dr * dr + di * di);
+        sig_re = dr * inv_den;
+        sig_im = -di * inv_den;
       }
       const T sigma = H::make(sig_re, sig_im), tau = H::make(tau_re, tau_im);
       // V^H v = sigma (V^H x - beta conj(V[f, :])),  likewise W
@@ -320,14 +370,14 @@ __global__ void __launch_bounds__(HETRD_THREADS, 1) hetrd_panel_kernel(const Het
         cross += __shfl_xor_sync(0xffffffffu, cross, off);
         y0c = H::add(y0c, H::shfl_xor(y0c, off));
       }
-      const double aff = H::re(a.A[(long long)f * a.lda + f]);
+      const double aff = H::re(pre_aff);
       const double sig2 = sig_re * sig_re + sig_im * sig_im;
       const double vAv = sig2 * (H::re(sm.sums[1]) - 2.0 * beta * H::re(sm.sums[2]) + beta * beta * aff);
       const double yHv = vAv - 2.0 * cross;
       // w = tau y + alpha2 v,  alpha2 = -1/2 tau conj(tau) (y^H v)   (real: -1/2 tau^2 y^T v)
       const double t2 = tau_re * tau_re + tau_im * tau_im;
       const T alpha2 = H::scale(-0.5 * t2 * yHv, H::make(1.0, 0.0));
-      const T yraw_f = H::ldcg(a.ybuf + f);
+      const T yraw_f = pre_yraw;
       const T y0 = H::sub(H::mul(sigma, H::sub(yraw_f, H::make(beta * aff, 0.0))), y0c);
       const T w0 = H::add(H::mul(tau, y0), alpha2);
       if (lane == 0) {
@@ -342,59 +392,82 @@ __global__ void __launch_bounds__(HETRD_THREADS, 1) hetrd_panel_kernel(const Het
           a.tau[c] = tau;
         }
       }
-      if (b == 0) {  // compact-WY factor: T[:j, j] = -tau T[:j, :j] (V^H v),  T[j, j] = tau
-        T s = H::zero();
-        if (lane < j)
-          for (int k = lane; k < j; ++k) s = H::fma(sm.Tf[lane][k], sm.Vv[k], s);
-        __syncwarp();
-        if (lane < j) sm.Tf[lane][j] = H::mul(H::make(-tau_re, -tau_im), s);
-        if (lane == 0) sm.Tf[j][j] = tau;
-      }
     }
     __syncthreads();
-    // ---- phase C (+ phase A of the next column), one thread per row ------------------------------------
+    if (prof) tc5 = clock64();
+    // ---- phase C (+ phase A of the next column): one warp per row, lane q = panel column q ---------------
     {
       const double beta = sm.beta;
       const T sigma = H::make(sm.sigma_re, sm.sigma_im), tau = H::make(sm.tau_re, sm.tau_im);
       const T alpha2 = H::make(sm.alpha2_re, sm.alpha2_im);
       const bool next = j + 1 < a.jb;
       const long long plane = a.npad * 2 * HNB, vplane = a.npad * a.ldv;
-      for (long long r = f + gtid; r < n; r += gthreads) {
-        const T arf = a.A[r * a.lda + f];
-        const T v = (r == f) ? H::make(1.0, 0.0) : H::mul(sigma, H::ldcg(a.xbuf + r));
-        T y = H::mul(sigma, H::sub(H::ldcg(a.ybuf + r), H::scale(beta, arf)));
-        T xn = arf;  // next column's raw entry: A[r, f] - V[r, :j+1] conj(W[f, :j+1]) - W[r, :j+1] conj(V[f, :j+1])
+      const T wv_l = lane < j ? sm.Wv[lane] : H::zero(), vv_l = lane < j ? sm.Vv[lane] : H::zero();
+      const T rw_l = lane < j ? H::conj(sm.rowW[lane]) : H::zero(), rv_l = lane < j ? H::conj(sm.rowV[lane]) : H::zero();
+      const T rw_j = H::conj(sm.rowW[j]), rv_j = H::conj(sm.rowV[j]);
+      const int gw = b * HETRD_WARPS + warp, nw = G * HETRD_WARPS;
+      for (long long r = f + gw; r < n; r += nw) {
         T* vrow = a.V + r * HNB;
         T* wrow = a.W + r * HNB;
-        for (int q = 0; q < j; ++q) {
-          const T vq = vrow[q], wq = wrow[q];
-          y = H::sub(y, H::add(H::mul(vq, sm.Wv[q]), H::mul(wq, sm.Vv[q])));
-          xn = H::sub(xn, H::add(H::mul(vq, H::conj(sm.rowW[q])), H::mul(wq, H::conj(sm.rowV[q]))));
+        // one coalesced load of the row's panel entries; columns >= j hold stale data and are masked
+        const T vq = lane < j ? H::ldcg(vrow + lane) : H::zero();
+        const T wq = lane < j ? H::ldcg(wrow + lane) : H::zero();
+        const T arf = a.A[r * a.lda + f];          // uniform addresses: one transaction each, issued with the row loads
+        const T xr = H::ldcg(a.xbuf + r);
+        const T yr = H::ldcg(a.ybuf + r);
+        T ys = H::add(H::mul(vq, wv_l), H::mul(wq, vv_l));   // V[r, :j] (W^H v) + W[r, :j] (V^H v)
+        T xsum = H::add(H::mul(vq, rw_l), H::mul(wq, rv_l)); // V[r, :j] conj(W[f, :j]) + W[r, :j] conj(V[f, :j])
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          ys = H::add(ys, H::shfl_xor(ys, off));
+          xsum = H::add(xsum, H::shfl_xor(xsum, off));
         }
-        const T w = H::add(H::mul(tau, y), H::mul(alpha2, v));
-        xn = H::sub(xn, H::add(H::mul(v, H::conj(sm.rowW[j])), H::mul(w, H::conj(sm.rowV[j]))));
-        vrow[j] = v;
-        wrow[j] = w;
-        // planar GEMM operands
-        a.PW[r * 2 * HNB + j] = H::re(v);
-        a.PW[r * 2 * HNB + HNB + j] = H::re(w);
-        a.RW[r * 2 * HNB + j] = H::re(w);
-        a.RW[r * 2 * HNB + HNB + j] = H::re(v);
-        a.VT[(long long)c * a.ldv + r] = H::re(v);
-        a.VR[r * a.ldv + c] = H::re(v);
-        if (C) {
-          a.PW[plane + r * 2 * HNB + j] = H::im(v);
-          a.PW[plane + r * 2 * HNB + HNB + j] = H::im(w);
-          a.RW[plane + r * 2 * HNB + j] = H::im(w);
-          a.RW[plane + r * 2 * HNB + HNB + j] = H::im(v);
-          a.VT[vplane + (long long)c * a.ldv + r] = H::im(v);
-          a.VR[vplane + r * a.ldv + c] = -H::im(v);
-        }
-        if (next) {
-          if (r == f) a.d[f] = H::re(xn);
-          else a.xbuf[r] = xn;
+        if (lane == 0) {
+          const T v = (r == f) ? H::make(1.0, 0.0) : H::mul(sigma, xr);
+          const T y = H::sub(H::mul(sigma, H::sub(yr, H::scale(beta, arf))), ys);
+          const T w = H::add(H::mul(tau, y), H::mul(alpha2, v));
+          const T xn = H::sub(H::sub(arf, xsum), H::add(H::mul(v, rw_j), H::mul(w, rv_j)));
+          vrow[j] = v;
+          wrow[j] = w;
+          a.PW[r * 2 * HNB + j] = H::re(v);
+          a.PW[r * 2 * HNB + HNB + j] = H::re(w);
+          a.RW[r * 2 * HNB + j] = H::re(w);
+          a.RW[r * 2 * HNB + HNB + j] = H::re(v);
+          a.VT[(long long)c * a.ldv + r] = H::re(v);
+          a.VR[r * a.ldv + c] = H::re(v);
+          if (C) {
+            a.PW[plane + r * 2 * HNB + j] = H::im(v);
+            a.PW[plane + r * 2 * HNB + HNB + j] = H::im(w);
+            a.RW[plane + r * 2 * HNB + j] = H::im(w);
+            a.RW[plane + r * 2 * HNB + HNB + j] = H::im(v);
+            a.VT[vplane + (long long)c * a.ldv + r] = H::im(v);
+            a.VR[vplane + r * a.ldv + c] = -H::im(v);
+          }
+          if (next) {
+            if (r == f) a.d[f] = H::re(xn);
+            else a.xbuf[r] = xn;
+          }
         }
       }
+      // compact-WY factor (CTA 0, after its rows, off the other CTAs' critical path):
+      // T[:j, j] = -tau T[:j, :j] (V^H v),  T[j, j] = tau
+      if (b == 0 && warp == HETRD_WARPS - 1) {
+        T sT = H::zero();
+        if (lane < j)
+          for (int k = lane; k < j; ++k) sT = H::fma(sm.Tf[lane][k], sm.Vv[k], sT);
+        __syncwarp();
+        if (lane < j) sm.Tf[lane][j] = H::mul(H::make(-H::re(tau), -H::im(tau)), sT);
+        if (lane == 0) sm.Tf[j][j] = tau;
+      }
+    }
+    if (prof) {
+      const long long tc6 = clock64();
+      a.dbg[0] += tc1 - tc0;  // wait at B1
+      a.dbg[1] += tc2 - tc1;  // stage x + A x
+      a.dbg[2] += tc3 - tc2;  // row terms, V^H x / W^H x, CTA reduction, publish
+      a.dbg[3] += tc4 - tc3;  // wait at B2
+      a.dbg[4] += tc5 - tc4;  // grid reduction + Householder scalars
+      a.dbg[5] += tc6 - tc5;  // phase C / next x
     }
   }
   // panel done: publish the compact-WY factor
@@ -407,7 +480,7 @@ __global__ void __launch_bounds__(HETRD_THREADS, 1) hetrd_panel_kernel(const Het
 
 template <bool C>
 size_t hetrd_smem_bytes(int n) {
-  return (((size_t)n * sizeof(typename HS<C>::T)) + 15) / 16 * 16 + sizeof(HetrdSmem<C>) + 16;
+  return hetrd_xs_bytes<C>(n) + sizeof(HetrdSmem<C>) + 16;
 }
 
 // Rows of the panel operands that the next her2k / back-transformation must see as zero.

@@ -5,6 +5,8 @@
 #include <cusolverDn.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>

@@ -134,11 +134,15 @@ def test_large_fit_uses_device_prepass_and_matches_host_path(monkeypatch):
     # Uniformly weighted bins: the device returns the order statistics at the ranks the reference's interpolation
     # brackets (`_binstats.uniform_rank_plan`), so the medians are the host recipe's; only the mean absolute
     # deviations are summed in a different order.
-    assert rel_err(a_dev.shift_, a_host.shift_) < 1e-14 and rel_err(a_dev.scale_, a_host.scale_) < 1e-13
-    assert rel_err(a_dev.A_, a_host.A_) < 1e-11
-    assert m_dev.γ_ == m_host.γ_
-    assert rel_err(m_dev.β̂_, m_host.β̂_) < 1e-9
-    assert rel_err(m_dev.loo_residuals_, m_host.loo_residuals_) < 1e-9
+    errs = {
+        "shift": rel_err(a_dev.shift_, a_host.shift_), "scale": rel_err(a_dev.scale_, a_host.scale_),
+        "A": rel_err(a_dev.A_, a_host.A_), "beta": rel_err(m_dev.β̂_, m_host.β̂_),
+        "loo": rel_err(m_dev.loo_residuals_, m_host.loo_residuals_),
+    }
+    assert errs["shift"] < 1e-14 and errs["scale"] < 1e-13, errs
+    assert errs["A"] < 1e-11, errs
+    assert m_dev.γ_ == m_host.γ_, errs
+    assert errs["beta"] < 1e-9 and errs["loo"] < 1e-9, errs
 
 
 @pytest.mark.gpu
