@@ -7,6 +7,7 @@ from ._feature_maps import (
     OrthogonalRandomFourierFeatures,
     RandomFourierFeatures,
 )
+from ._multi import devices, set_devices
 from ._neo_ls_svm import NeoLSSVM
 
 __all__ = [
@@ -18,4 +19,6 @@ __all__ = [
     "KernelApproximatingFeatureMap",
     "OrthogonalRandomFourierFeatures",
     "RandomFourierFeatures",
+    "devices",
+    "set_devices",
 ]

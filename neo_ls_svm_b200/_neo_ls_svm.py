@@ -39,6 +39,7 @@ from ._quantizer import unique_values
 _DEVICE_FINITE_SCAN_MIN = 1 << 24  # elements of X above which the NaN/inf scan runs on the device copy
 
 _DEVICE_STATE = "_device_state"
+_SHARDED_PREDICT_MIN_ROWS = 1 << 16  # below this one GPU answers faster than the shards can be dealt out
 
 
 def _is_frame(obj) -> bool:
@@ -84,9 +85,9 @@ class NeoLSSVM(BaseEstimator):
     def _gpu():
         import torch
 
-        from . import _lib
+        from . import _lib, _multi
 
-        ctx = _lib.context()
+        ctx = _lib.context(_multi.devices()[0])  # the first selected GPU hosts the replicated solves and the pre-pass
         return ctx, torch, torch.device("cuda", ctx.device)
 
     def _primal_device_state(self, want_std: bool = False):
@@ -131,7 +132,13 @@ class NeoLSSVM(BaseEstimator):
         yd = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float64)).to(dev)
         sd = torch.from_numpy(s_norm).to(dev)
         shd, Wd = torch.from_numpy(shift).to(dev), torch.from_numpy(W).to(dev)
-        fit = _primal.primal_fit(Xd, yd, sd, shd, Wd, self._estimator_type == "classifier", ctx=ctx)
+        from . import _multi
+
+        devs = _multi.devices()
+        if len(devs) > 1:  # rows sharded over the selected GPUs (NLS_DEVICES / set_devices), SURVEY.md §8e
+            fit = _multi.primal_fit_sharded(X, y, s_norm, shift, W, self._estimator_type == "classifier", devs, X_primary=Xd)
+        else:
+            fit = _primal.primal_fit(Xd, yd, sd, shd, Wd, self._estimator_type == "classifier", ctx=ctx)
         del Xd
         cdt = np.complex64 if dt == np.float32 else np.complex128
         self.γs_ = fit.gammas.astype(dt)
@@ -273,7 +280,14 @@ class NeoLSSVM(BaseEstimator):
         dt = X.dtype
         ctx, torch, dev = self._gpu()
         if self.primal_:
+            from . import _multi
+
             st = self._primal_device_state(want_std)
+            devs = _multi.devices()
+            if len(devs) > 1 and X.shape[0] >= _SHARDED_PREDICT_MIN_ROWS:  # independent rows: shard, no collective
+                yhat, sigma = _multi.primal_predict_sharded(
+                    X, st["shift"], st["W"], st["beta"], st.get("B"), st.get("w"), devs, want_decision, want_std)
+                return (yhat.astype(dt) if yhat is not None else None), (sigma.astype(dt) if sigma is not None else None)
             Xd = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).to(dev)
             yhat, sigma = ctx.primal_predict(
                 Xd, st["shift"], st["W"], beta=st["beta"] if want_decision else None,

@@ -98,6 +98,7 @@ struct HetrdArgs {
   T* ybuf;          // n
   T* part;          // [HETRD_NSUM][gpad]
   int gpad;
+  T* zpart;         // SYM only: [G][npad] column partials z_b[k] = sum_{rows r > k of CTA b} conj(A[r][k]) x[r]
   unsigned* bar;    // grid barrier counter (zeroed before every launch)
   long long* dbg;   // optional [8] cycle counters of CTA 0 (diagnostics), may be null
 };
@@ -124,9 +125,10 @@ __device__ __forceinline__ void hetrd_grid_barrier(unsigned* ctr, unsigned& targ
 }
 
 // Shared-memory layout of the panel kernel (dynamic): x staging area first (n elements of T), then fixed scratch.
-template <bool C>
+template <bool C, bool SYM>
 struct HetrdSmem {
   using T = typename HS<C>::T;
+  T ysm[SYM ? HETRD_WARPS * 128 : 1];  // SYM: per-warp partial row sums of the strictly lower triangle
   T sums[HETRD_NSUM];            // grid-reduced: 0 xx, 1 xy, 2 xa, 3.. V^H x, 3+HNB.. W^H x
   T Vv[HNB], Wv[HNB];            // V^H v, W^H v
   T rowV[HNB], rowW[HNB];        // row c+1 of the panel matrices (becomes row c of the next column)
@@ -138,18 +140,25 @@ struct HetrdSmem {
 };
 
 // Bytes of the x staging area: n elements rounded up to whole unrolled spans (+ one span of slack for the even base).
+constexpr int HETRD_XPAD = 2048;  // x is zero-padded to whole column panels of the symmetric path (>= HETRD_SPAN)
 template <bool C>
 __host__ __device__ inline size_t hetrd_xs_bytes(int n) {
-  return ((size_t)(n + 2 + HETRD_SPAN - 1) / HETRD_SPAN * HETRD_SPAN) * sizeof(typename HS<C>::T);
+  return ((size_t)(n + 2 + HETRD_XPAD - 1) / HETRD_XPAD * HETRD_XPAD) * sizeof(typename HS<C>::T);
 }
 
-template <bool C>
+// SYM = false: every CTA reads full rows of the trailing matrix (latency-optimised, small matrices).
+// SYM = true : only the strictly lower triangle is read (half the HBM traffic): element (r, k), k < r, contributes
+//              A[r][k] x[k] to y[r] and conj(A[r][k]) x[r] to y[k]; the second kind is accumulated per CTA in
+//              registers (a warp owns a fixed set of columns), written as one partial vector per CTA and summed over
+//              the CTAs by the consumer of y[k].  Rows are dealt to the CTAs in two blocks (b and 2G-1-b) so that
+//              every CTA gets the same share of the triangle.
+template <bool C, bool SYM>
 __global__ void __launch_bounds__(HETRD_THREADS, 1) hetrd_panel_kernel(const HetrdArgs<C> a) {
   using H = HS<C>;
   using T = typename H::T;
   extern __shared__ __align__(16) unsigned char hsm_raw[];
   T* xs = reinterpret_cast<T*>(hsm_raw);
-  HetrdSmem<C>& sm = *reinterpret_cast<HetrdSmem<C>*>(hsm_raw + hetrd_xs_bytes<C>(a.n));
+  HetrdSmem<C, SYM>& sm = *reinterpret_cast<HetrdSmem<C, SYM>*>(hsm_raw + hetrd_xs_bytes<C>(a.n));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int G = gridDim.x, b = blockIdx.x;
   const int n = a.n;
@@ -181,66 +190,185 @@ __global__ void __launch_bounds__(HETRD_THREADS, 1) hetrd_panel_kernel(const Het
     // ---- phase B: y_raw = A[f:, f:] x for this CTA's row slab, plus the partial sums --------------------
     const int kbase = f & ~1;    // x staged from an even index (vector loads in the real case)
     const int nk = n - kbase;
-    const int nk_pad = (nk + HETRD_SPAN - 1) / HETRD_SPAN * HETRD_SPAN;  // zero tail: the unrolled loop needs no guards
+    constexpr int XPAD = SYM ? HETRD_XPAD : HETRD_SPAN;
+    const int nk_pad = (nk + XPAD - 1) / XPAD * XPAD;  // zero tail: the unrolled loops need no guards
     for (int k = tid; k < nk_pad; k += HETRD_THREADS) {
       const int kk = kbase + k;
       xs[k] = (kk >= f && kk < n) ? H::ldcg(a.xbuf + kk) : H::zero();
     }
+    if (SYM)
+      for (int t = tid; t < HETRD_WARPS * 128; t += HETRD_THREADS) sm.ysm[t] = H::zero();
     __syncthreads();
-    const int R = (n1 + G - 1) / G;             // rows per CTA
-    const int r_lo = f + b * R;
-    const int rows = max(0, min(n, r_lo + R) - r_lo);
-    // k segments per row: with few rows per CTA a row is spread over several warps (two tasks per warp is the aim);
-    // a segment is a whole number of unrolled spans.
+    // Rows of this CTA: one contiguous slab, or (SYM) the two blocks b and 2G-1-b of 2G equal blocks.
+    const int R = (n1 + G - 1) / G;
+    int r_lo, rows_a, r_hi, rows_b;
+    if (SYM) {  // block beta = rows [f + beta n1 / 2G, f + (beta + 1) n1 / 2G): heights differ by at most one
+      const long long twoG = 2LL * G;
+      r_lo = f + (int)((long long)b * n1 / twoG);
+      rows_a = f + (int)((long long)(b + 1) * n1 / twoG) - r_lo;
+      r_hi = f + (int)((twoG - 1 - b) * n1 / twoG);
+      rows_b = f + (int)((twoG - b) * n1 / twoG) - r_hi;
+    } else {
+      r_lo = f + b * R;
+      rows_a = max(0, min(n, r_lo + R) - r_lo);
+      r_hi = 0;
+      rows_b = 0;
+    }
+    const int rows = rows_a + rows_b;
+    auto row_of = [&](int li) { return li < rows_a ? r_lo + li : r_hi + (li - rows_a); };
     int S = 1;
-    if (R < 2 * HETRD_WARPS) S = max(1, min(min(2 * HETRD_WARPS / max(R, 1), nk_pad / HETRD_SPAN), 16));
-    const int seglen = ((nk_pad / HETRD_SPAN + S - 1) / S) * HETRD_SPAN;
-    for (int task = warp; task < rows * S; task += HETRD_WARPS) {
-      const int row = r_lo + task / S, seg = task % S;
-      const int ka = seg * seglen, kb = min(nk_pad, ka + seglen);  // relative to kbase
-      const T* arow = a.A + (long long)row * a.lda + kbase;
-      T acc;
-      if (C) {
-        // HETRD_UNR independent 16-byte loads in flight per lane; indices past the row are clamped (x is zero there)
-        const int kmax = (int)a.lda - 1 - kbase;
-        T c0 = H::zero(), c1 = H::zero(), c2 = H::zero(), c3 = H::zero();
-        for (int k = ka + lane; k < kb; k += 32 * 8) {
-          T av[8];
+    if (!SYM) {
+      // k segments per row: with few rows per CTA a row is spread over several warps (two tasks per warp is the aim);
+      // a segment is a whole number of unrolled spans.
+      S = 1;
+      if (R < 2 * HETRD_WARPS) S = max(1, min(min(2 * HETRD_WARPS / max(R, 1), nk_pad / HETRD_SPAN), 16));
+      const int seglen = ((nk_pad / HETRD_SPAN + S - 1) / S) * HETRD_SPAN;
+      for (int task = warp; task < rows * S; task += HETRD_WARPS) {
+        const int row = r_lo + task / S, seg = task % S;
+        const int ka = seg * seglen, kb = min(nk_pad, ka + seglen);  // relative to kbase
+        const T* arow = a.A + (long long)row * a.lda + kbase;
+        T acc;
+        if (C) {
+          // HETRD_UNR independent 16-byte loads in flight per lane; indices past the row are clamped (x is zero there)
+          const int kmax = (int)a.lda - 1 - kbase;
+          T c0 = H::zero(), c1 = H::zero(), c2 = H::zero(), c3 = H::zero();
+          for (int k = ka + lane; k < kb; k += 32 * 8) {
+            T av[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) av[u] = arow[min(k + 32 * u, kmax)];
+            for (int u = 0; u < 8; ++u) av[u] = arow[min(k + 32 * u, kmax)];
 #pragma unroll
-          for (int u = 0; u < 8; u += 4) {
-            c0 = H::fma(av[u], xs[k + 32 * u], c0);
-            c1 = H::fma(av[u + 1], xs[k + 32 * (u + 1)], c1);
-            c2 = H::fma(av[u + 2], xs[k + 32 * (u + 2)], c2);
-            c3 = H::fma(av[u + 3], xs[k + 32 * (u + 3)], c3);
+            for (int u = 0; u < 8; u += 4) {
+              c0 = H::fma(av[u], xs[k + 32 * u], c0);
+              c1 = H::fma(av[u + 1], xs[k + 32 * (u + 1)], c1);
+              c2 = H::fma(av[u + 2], xs[k + 32 * (u + 2)], c2);
+              c3 = H::fma(av[u + 3], xs[k + 32 * (u + 3)], c3);
+            }
           }
-        }
-        acc = H::add(H::add(c0, c1), H::add(c2, c3));
-      } else {
-        const double* ar = reinterpret_cast<const double*>(arow);
-        const double* xr = reinterpret_cast<const double*>(xs);
-        const int kmax = (int)a.lda - 2 - kbase;  // even
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        for (int k = ka + 2 * lane; k < kb; k += 64 * 8) {  // kbase, ka even: 16-byte aligned pairs
-          double2 av[8];
+          acc = H::add(H::add(c0, c1), H::add(c2, c3));
+        } else {
+          const double* ar = reinterpret_cast<const double*>(arow);
+          const double* xr = reinterpret_cast<const double*>(xs);
+          const int kmax = (int)a.lda - 2 - kbase;  // even
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+          for (int k = ka + 2 * lane; k < kb; k += 64 * 8) {  // kbase, ka even: 16-byte aligned pairs
+            double2 av[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) av[u] = *reinterpret_cast<const double2*>(ar + min(k + 64 * u, kmax));
+            for (int u = 0; u < 8; ++u) av[u] = *reinterpret_cast<const double2*>(ar + min(k + 64 * u, kmax));
 #pragma unroll
-          for (int u = 0; u < 8; u += 2) {
-            const double2 x0 = *reinterpret_cast<const double2*>(xr + k + 64 * u);
-            const double2 x1 = *reinterpret_cast<const double2*>(xr + k + 64 * (u + 1));
-            s0 = ::fma(av[u].x, x0.x, s0);
-            s1 = ::fma(av[u].y, x0.y, s1);
-            s2 = ::fma(av[u + 1].x, x1.x, s2);
-            s3 = ::fma(av[u + 1].y, x1.y, s3);
+            for (int u = 0; u < 8; u += 2) {
+              const double2 x0 = *reinterpret_cast<const double2*>(xr + k + 64 * u);
+              const double2 x1 = *reinterpret_cast<const double2*>(xr + k + 64 * (u + 1));
+              s0 = ::fma(av[u].x, x0.x, s0);
+              s1 = ::fma(av[u].y, x0.y, s1);
+              s2 = ::fma(av[u + 1].x, x1.x, s2);
+              s3 = ::fma(av[u + 1].y, x1.y, s3);
+            }
           }
+          acc = H::make((s0 + s1) + (s2 + s3), 0.0);
         }
-        acc = H::make((s0 + s1) + (s2 + s3), 0.0);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc = H::add(acc, H::shfl_xor(acc, off));
+        if (lane == 0) sm.psum[task] = acc;
       }
+    } else {
+      constexpr int VEC = C ? 1 : 2;                 // elements per 16-byte load
+      constexpr int U = 2;                           // loads per row and tile
+      constexpr int WC = 32 * VEC * U;               // columns of one warp in a column panel
+      constexpr int CPW = WC * HETRD_WARPS;          // columns of a column panel (divides HETRD_XPAD)
+      const int kmax = (int)a.lda - VEC - kbase;     // clamp for loads past the row (x is zero there)
+      const double* xsd = reinterpret_cast<const double*>(xs);
+      for (int cp0 = 0; cp0 < nk_pad; cp0 += CPW) {
+        const int span0 = kbase + cp0 + warp * WC;    // first column of this warp's span (absolute)
+        const int kw = cp0 + warp * WC + lane * VEC;  // this lane's first column, relative to kbase
+        T zacc[U * VEC];
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) acc = H::add(acc, H::shfl_xor(acc, off));
-      if (lane == 0) sm.psum[task] = acc;
+        for (int q = 0; q < U * VEC; ++q) zacc[q] = H::zero();
+        if (span0 < n) {
+          // x at this lane's columns: loaded once per span, shared by all rows
+          double2 xv[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) xv[u] = *reinterpret_cast<const double2*>(xsd + (C ? 2 : 1) * (kw + 32 * VEC * u));
+          const int off0 = (C ? 2 : 1) * min(kw, kmax), off1 = (C ? 2 : 1) * min(kw + 32 * VEC, kmax);
+#pragma unroll 1
+          for (int grp = 0; grp < 2; ++grp) {
+            const int g_lo = grp ? r_hi : r_lo, g_rows = grp ? rows_b : rows_a, li0 = grp ? rows_a : 0;
+#pragma unroll 1
+            for (int rb = 0; rb < g_rows; rb += 8) {
+              const int r0 = g_lo + rb, nr = min(8, g_rows - rb);
+              if (span0 >= r0 + nr - 1) continue;  // the span lies on or above the diagonal for these rows
+              const double* abase = reinterpret_cast<const double*>(a.A + (long long)r0 * a.lda + kbase);
+              const long long rstride = (C ? 2 : 1) * a.lda;
+              double2 av[8][U];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const double* arow = abase + (long long)min(i, nr - 1) * rstride;
+                av[i][0] = *reinterpret_cast<const double2*>(arow + off0);
+                av[i][1] = *reinterpret_cast<const double2*>(arow + off1);
+              }
+              const bool interior = (span0 + WC <= r0) && nr == 8;  // every column of the span is left of every row
+              T yacc[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int r = r0 + i;
+                const T xr = i < nr ? xs[r - kbase] : H::zero();
+                T y = H::zero();
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                  const int k = kbase + kw + 32 * VEC * u;
+                  if (C) {
+                    const bool keep = interior || (i < nr && k < r);
+                    const T e0 = keep ? H::make(av[i][u].x, av[i][u].y) : H::zero();
+                    y = H::fma(e0, H::make(xv[u].x, xv[u].y), y);
+                    zacc[u] = H::cfma(e0, xr, zacc[u]);
+                  } else {
+                    const double e0 = (interior || (i < nr && k < r)) ? av[i][u].x : 0.0;
+                    const double e1 = (interior || (i < nr && k + 1 < r)) ? av[i][u].y : 0.0;
+                    y = H::make(::fma(e0, xv[u].x, ::fma(e1, xv[u].y, H::re(y))), 0.0);
+                    zacc[2 * u] = H::make(::fma(e0, H::re(xr), H::re(zacc[2 * u])), 0.0);
+                    zacc[2 * u + 1] = H::make(::fma(e1, H::re(xr), H::re(zacc[2 * u + 1])), 0.0);
+                  }
+                }
+                yacc[i] = y;
+              }
+              // Transposing reduction of the 8 row sums over the 32 lanes (9 exchanges instead of 40): after the three
+              // halving steps lane L holds row 4 b4 + 2 b3 + b2 (bits of L), two butterfly steps finish the sum.
+              {
+                const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+                T t4[4], t2[2], t1;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const T send = h16 ? yacc[i] : yacc[i + 4], keep = h16 ? yacc[i + 4] : yacc[i];
+                  t4[i] = H::add(keep, H::shfl_xor(send, 16));
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                  const T send = h8 ? t4[i] : t4[i + 2], keep = h8 ? t4[i + 2] : t4[i];
+                  t2[i] = H::add(keep, H::shfl_xor(send, 8));
+                }
+                {
+                  const T send = h4 ? t2[0] : t2[1], keep = h4 ? t2[1] : t2[0];
+                  t1 = H::add(keep, H::shfl_xor(send, 4));
+                }
+                t1 = H::add(t1, H::shfl_xor(t1, 2));
+                t1 = H::add(t1, H::shfl_xor(t1, 1));
+                const int row_i = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                if ((lane & 3) == 0 && row_i < nr) {
+                  T* dst = &sm.ysm[warp * 128 + li0 + rb + row_i];
+                  *dst = H::add(*dst, t1);
+                }
+              }
+            }
+          }
+        }
+        // this CTA's partial of y[k] for the warp's columns (zeros where it has no rows below k)
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int v2 = 0; v2 < VEC; ++v2) {
+            const int k = kbase + kw + 32 * VEC * u + v2;
+            if (k >= f && k < n) a.zpart[(long long)b * a.npad + k] = zacc[u * VEC + v2];
+          }
+      }
     }
     __syncthreads();
     if (prof) tc2 = clock64();
@@ -248,13 +376,23 @@ __global__ void __launch_bounds__(HETRD_THREADS, 1) hetrd_panel_kernel(const Het
     if (tid < 128) {
       T cxx = H::zero(), cxy = H::zero(), cxa = H::zero();
       if (tid < rows) {
-        const int row = r_lo + tid;
-        T y = sm.psum[tid * S];
-        for (int s = 1; s < S; ++s) y = H::add(y, sm.psum[tid * S + s]);
-        a.ybuf[row] = y;
+        const int row = row_of(tid);
         const T x = xs[row - kbase];
+        if (!SYM) {
+          T y = sm.psum[tid * S];
+          for (int s = 1; s < S; ++s) y = H::add(y, sm.psum[tid * S + s]);
+          a.ybuf[row] = y;
+          cxy = H::cmul(x, y);
+        } else {
+          // ybuf holds the strictly-lower part plus the diagonal term; the column partials are added by the consumer.
+          // x^H A x = 2 Re sum_r conj(x_r) ylow_r + sum_r a_rr |x_r|^2
+          T ylow = sm.ysm[tid];
+          for (int w = 1; w < HETRD_WARPS; ++w) ylow = H::add(ylow, sm.ysm[w * 128 + tid]);
+          const double diag = H::re(a.A[(long long)row * a.lda + row]);
+          a.ybuf[row] = H::add(ylow, H::scale(diag, x));
+          cxy = H::make(2.0 * H::re(H::cmul(x, ylow)) + diag * H::abs2(x), 0.0);
+        }
         if (row != f) cxx = H::make(H::abs2(x), 0.0);
-        cxy = H::cmul(x, y);
         cxa = H::cmul(x, a.A[(long long)row * a.lda + f]);
       }
       sm.rowred[0][tid] = cxx;
@@ -266,7 +404,7 @@ __global__ void __launch_bounds__(HETRD_THREADS, 1) hetrd_panel_kernel(const Het
       T av = H::zero(), aw = H::zero();
       if (lane < j)
         for (int t = warp; t < rows; t += HETRD_WARPS) {
-          const int row = r_lo + t;
+          const int row = row_of(t);
           const T x = xs[row - kbase];
           av = H::cfma(H::ldcg(a.V + (long long)row * HNB + lane), x, av);
           aw = H::cfma(H::ldcg(a.W + (long long)row * HNB + lane), x, aw);
@@ -292,6 +430,36 @@ __global__ void __launch_bounds__(HETRD_THREADS, 1) hetrd_panel_kernel(const Het
     hetrd_grid_barrier(a.bar, bar_target);  // B2: partial sums, y_raw and x visible everywhere
     if (prof) tc4 = clock64();
 
+    if (SYM) {
+      // ---- y[k] += sum over the CTAs of their column partials: every CTA completes a contiguous range of k (coalesced
+      // reads of G partial vectors), then one more grid barrier makes the finished y visible --------------------------
+      // Rz <= 128 elements per CTA; four threads share an element (a quarter of the CTAs each, 4 loads in flight),
+      // combined through shared memory in a fixed order.
+      const int Rz = (n1 + G - 1) / G;
+      {
+        const int t = tid & 127, part = tid >> 7;  // 4 parts x 128 elements
+        const long long k = (long long)f + (long long)b * Rz + t;
+        T z0 = H::zero(), z1 = H::zero(), z2 = H::zero(), z3 = H::zero();
+        if (t < Rz && k < n) {
+          const int g_lo = part * ((G + 3) / 4), g_hi = min(G, g_lo + (G + 3) / 4);
+          int g = g_lo;
+          for (; g + 4 <= g_hi; g += 4) {
+            z0 = H::add(z0, H::ldcg(a.zpart + (long long)g * a.npad + k));
+            z1 = H::add(z1, H::ldcg(a.zpart + (long long)(g + 1) * a.npad + k));
+            z2 = H::add(z2, H::ldcg(a.zpart + (long long)(g + 2) * a.npad + k));
+            z3 = H::add(z3, H::ldcg(a.zpart + (long long)(g + 3) * a.npad + k));
+          }
+          for (; g < g_hi; ++g) z0 = H::add(z0, H::ldcg(a.zpart + (long long)g * a.npad + k));
+        }
+        sm.psum[tid] = H::add(H::add(z0, z1), H::add(z2, z3));
+        __syncthreads();
+        if (part == 0 && t < Rz && k < n) {
+          const T z = H::add(H::add(sm.psum[t], sm.psum[128 + t]), H::add(sm.psum[256 + t], sm.psum[384 + t]));
+          a.ybuf[k] = H::add(H::ldcg(a.ybuf + k), z);
+        }
+      }
+      hetrd_grid_barrier(a.bar, bar_target);  // B3 (symmetric path only)
+    }
     // ---- grid reduction of the 3 + 2j sums, identically in every CTA ------------------------------------
     // Warp 0 first issues the loads its scalar phase needs, so that their latency hides behind the reduction.
     T pre_alpha = H::zero(), pre_yraw = H::zero(), pre_aff = H::zero(), pre_rv = H::zero(), pre_rw = H::zero();
@@ -478,9 +646,9 @@ __global__ void __launch_bounds__(HETRD_THREADS, 1) hetrd_panel_kernel(const Het
   }
 }
 
-template <bool C>
+template <bool C, bool SYM>
 size_t hetrd_smem_bytes(int n) {
-  return hetrd_xs_bytes<C>(n) + sizeof(HetrdSmem<C>) + 16;
+  return hetrd_xs_bytes<C>(n) + sizeof(HetrdSmem<C, SYM>) + 16;
 }
 
 // Rows of the panel operands that the next her2k / back-transformation must see as zero.
@@ -524,6 +692,7 @@ struct OpHer2k {
     int nt;            // trailing size
     double* Aout;      // &A[r0, r0]; complex: interleaved
     long long lda;     // in elements
+    int lower_only;    // update the lower triangle (incl. the diagonal) only: all the symmetric A x path reads
   };
   static __device__ __forceinline__ Tile tile(const Params& p) {
     Tile t;
@@ -531,7 +700,7 @@ struct OpHer2k {
     t.m0 = blockIdx.y * BM;
     t.k_begin = 0;
     t.k_end = p.A.kext;
-    t.valid = true;
+    t.valid = !p.lower_only || t.n0 < t.m0 + BM;
     return t;
   }
   static __device__ __forceinline__ void epilogue(const Params& p, const Tile& t, Acc& acc, int warp_m, int warp_n,
@@ -545,7 +714,7 @@ struct OpHer2k {
         const int col = t.n0 + warp_n * 32 + 8 * j + 2 * (lane & 3);
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          if (col + e >= p.nt) continue;
+          if (col + e >= p.nt || (p.lower_only && col + e > row)) continue;
           if (C) {
             double2* o = reinterpret_cast<double2*>(p.Aout) + (long long)row * p.lda + col + e;
             double2 v = *o;
@@ -599,18 +768,91 @@ struct OpBT1 {
   }
 };
 
-// C2[row][j] = sum_i (sum_splits C1[row][i]) T[j][i]   (C2 = C1 T^T), written planar with row pitch HNB.
+// ---- two panels of 32 reflectors merged into one block reflector of 64 (back-transformation only) ----------------
+// (I - V1 T1 V1^H)(I - V2 T2 V2^H) = I - [V1 V2] T64 [V1 V2]^H,   T64 = [[T1, -T1 (V1^H V2) T2], [0, T2]].
+constexpr int BTW = 2 * HNB;  // width of a merged block reflector
+
+// Cross Gram X_p = V1^H V2 of every pair p (one CTA each): rows [64p, 64p+32) of VT against rows [64p+32, 64p+64),
+// contracted over the coordinates.  MODE_COMPLEX yields V1 conj(V2) summed over k, i.e. conj(X); stored as such.
+template <bool C>
+struct OpCrossGram {
+  struct Params {
+    Operand A, B;     // both = VT (planar)
+    int n;            // coordinates (K extent)
+    double* X;        // [pairs][planes][HNB][HNB]
+  };
+  static __device__ __forceinline__ Tile tile(const Params& p) {
+    Tile t;
+    t.m0 = blockIdx.x * BTW;
+    t.n0 = blockIdx.x * BTW + HNB;
+    t.k_begin = (blockIdx.x * BTW) & ~(BK - 1);
+    t.k_end = p.n;
+    t.valid = true;
+    return t;
+  }
+  static __device__ __forceinline__ void epilogue(const Params& p, const Tile&, Acc& acc, int warp_m, int warp_n,
+                                                  int lane, uint8_t*) {
+    if (warp_m != 0 || warp_n != 0) return;  // the 32 x 32 corner of the tile
+    double* xr = p.X + (long long)blockIdx.x * (C ? 2 : 1) * HNB * HNB;
+    double* xi = xr + HNB * HNB;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int row = 8 * i + (lane >> 2), col = 8 * j + 2 * (lane & 3) + e;
+          xr[row * HNB + col] = acc.r[i][j][e];
+          if (C) xi[row * HNB + col] = acc.i[i][j][e];
+        }
+  }
+};
+
+// T64 of every pair from the two panel factors and the cross Gram; one CTA of 32 x 32 threads per pair.
+// jb2 = reflectors in the second panel of the LAST pair (0: the pair has a single panel).
+template <bool C>
+__global__ void __launch_bounds__(1024) bt_merge_t_kernel(const typename HS<C>::T* __restrict__ Tfac,
+                                                          const double* __restrict__ X, int npanels,
+                                                          typename HS<C>::T* __restrict__ T64) {
+  using H = HS<C>;
+  using T = typename H::T;
+  __shared__ T t1[HNB][HNB + 1], xm[HNB][HNB + 1];  // xm: X, then T1 X
+  const int p = blockIdx.x, i = threadIdx.y, j = threadIdx.x;
+  const bool has2 = 2 * p + 1 < npanels;
+  const T* T1 = Tfac + (long long)(2 * p) * HNB * HNB;
+  const T* T2 = Tfac + (long long)(2 * p + 1) * HNB * HNB;
+  const double* xr = X + (long long)p * (C ? 2 : 1) * HNB * HNB;
+  t1[i][j] = (j >= i) ? T1[i * HNB + j] : H::zero();
+  const T t2_ij = (has2 && j >= i) ? T2[i * HNB + j] : H::zero();
+  // stored value is sum_k V1[k, i] conj(V2[k, j]) = conj(X[i][j])
+  xm[i][j] = has2 ? H::conj(H::make(xr[i * HNB + j], C ? xr[HNB * HNB + i * HNB + j] : 0.0)) : H::zero();
+  __syncthreads();
+  T s = H::zero();
+  for (int k = i; k < HNB; ++k) s = H::fma(t1[i][k], xm[k][j], s);  // (T1 X)[i][j]
+  __syncthreads();
+  xm[i][j] = s;
+  __syncthreads();
+  T c12 = H::zero();
+  if (has2)
+    for (int k = 0; k <= j; ++k) c12 = H::fma(xm[i][k], T2[k * HNB + j], c12);  // (T1 X T2)[i][j]
+  T* out = T64 + (long long)p * BTW * BTW;
+  out[i * BTW + j] = t1[i][j];
+  out[i * BTW + HNB + j] = H::make(-H::re(c12), -H::im(c12));
+  out[(HNB + i) * BTW + j] = H::zero();
+  out[(HNB + i) * BTW + HNB + j] = t2_ij;
+}
+
+// C2[row][j] = sum_i (sum_splits C1[row][i]) T[j][i]   (C2 = C1 T^T, T upper triangular, width jb <= 64), written
+// planar with row pitch BTW.  Block: 4 rows x 64 columns.
 template <bool C>
 __global__ void __launch_bounds__(256) bt_apply_t_kernel(const double* __restrict__ ws, int splits, long long rows_pad,
                                                          int n_rows, const typename HS<C>::T* __restrict__ Tg, int jb,
                                                          double* __restrict__ C2) {
   using H = HS<C>;
   using T = typename H::T;
-  __shared__ T Ts[HNB][HNB + 1];
-  __shared__ T c1[8][HNB];
-  for (int t = threadIdx.x; t < HNB * HNB; t += 256) Ts[t / HNB][t % HNB] = Tg[t];
-  const int ly = threadIdx.x >> 5, lx = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * 8 + ly;
+  __shared__ T c1[4][BTW];
+  const int ly = threadIdx.x >> 6, lx = threadIdx.x & 63;
+  const long long row = (long long)blockIdx.x * 4 + ly;
   T s = H::zero();
   if (row < n_rows && lx < jb) {
     double re = 0.0, im = 0.0;
@@ -626,9 +868,9 @@ __global__ void __launch_bounds__(256) bt_apply_t_kernel(const double* __restric
   if (row < n_rows) {
     T o = H::zero();
     if (lx < jb)
-      for (int i = lx; i < jb; ++i) o = H::fma(c1[ly][i], Ts[lx][i], o);  // (C1 T^T)[., j] = sum_{i >= j} C1[., i] T[j][i]
-    C2[row * HNB + lx] = H::re(o);
-    if (C) C2[rows_pad * HNB + row * HNB + lx] = H::im(o);
+      for (int i = lx; i < jb; ++i) o = H::fma(c1[ly][i], Tg[lx * BTW + i], o);  // sum_{i >= j} C1[., i] T[j][i]
+    C2[row * BTW + lx] = H::re(o);
+    if (C) C2[rows_pad * BTW + row * BTW + lx] = H::im(o);
   }
 }
 

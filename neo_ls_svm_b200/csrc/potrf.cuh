@@ -1,0 +1,189 @@
+// potrf.cuh — hand-written Cholesky factorisation M = U^H U (U upper triangular, row-major: the layout of
+// scipy.linalg.cho_factor(..., lower=False)) and the two triangular solves of cho_solve with one right-hand side.
+// Replaces scipy.linalg.cho_factor / cho_solve at the reference's _neo_ls_svm.py:177-178 (complex m x m, primal) and
+// :313-314 (real n x n, dual).
+//
+// Blocked right-looking algorithm, block size CNB = 64:
+//   chol_diag_kernel   U_kk = chol(M_kk) in shared memory (one CTA)
+//   chol_panel_kernel  U_k,rest = U_kk^-H M_k,rest: one thread per column, the column's 64 entries live in shared memory;
+//                      also writes the block row transposed and planar (PT[j][p]), the K-contiguous operand of the update
+//   OpCholUpdate       M_rest,rest -= U_k,rest^H U_k,rest on the FP64 DMMA GEMM core (upper-triangular tiles only, K = 64)
+// The strict lower triangle of the output keeps whatever the input held (scipy's cho_factor does the same).
+// Solves: block forward substitution with U^H, block back substitution with U (diag solve + update kernel per block).
+#pragma once
+#include "hetrd.cuh"  // HS<C> scalar helpers
+
+namespace nls {
+
+constexpr int CNB = 64;
+
+// In place on the diagonal block M[k0:k0+nb, k0:k0+nb] (upper part).  info: first non-positive pivot (1-based), else 0.
+template <bool C>
+__global__ void __launch_bounds__(256) chol_diag_kernel(typename HS<C>::T* __restrict__ M, long long ld, int k0, int nb,
+                                                        int* __restrict__ info) {
+  using H = HS<C>;
+  using T = typename H::T;
+  extern __shared__ __align__(16) unsigned char cd_raw[];
+  T(*S)[CNB + 1] = reinterpret_cast<T(*)[CNB + 1]>(cd_raw);
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
+  for (int i = ty; i < nb; i += 4)
+    if (tx < nb) S[i][tx] = (tx >= i) ? M[(long long)(k0 + i) * ld + k0 + tx] : H::zero();
+  __syncthreads();
+  for (int p = 0; p < nb; ++p) {
+    const double piv = H::re(S[p][p]);
+    if (!(piv > 0.0)) {
+      if (threadIdx.x == 0 && atomicCAS(info, 0, k0 + p + 1) == 0) {}
+      return;  // uniform: every thread reads the same pivot
+    }
+    const double inv = 1.0 / sqrt(piv);
+    __syncthreads();
+    if (ty == 0 && tx >= p && tx < nb) S[p][tx] = (tx == p) ? H::make(sqrt(piv), 0.0) : H::scale(inv, S[p][tx]);
+    __syncthreads();
+    for (int i = p + 1 + ty; i < nb; i += 4)
+      if (tx >= i && tx < nb) S[i][tx] = H::sub(S[i][tx], H::cmul(S[p][i], S[p][tx]));  // -= conj(U[p][i]) U[p][j]
+    __syncthreads();
+  }
+  for (int i = ty; i < nb; i += 4)
+    if (tx >= i && tx < nb) M[(long long)(k0 + i) * ld + k0 + tx] = S[i][tx];
+}
+
+// Block row: for every column j >= k0 + nb solve U_kk^H x = M[k0:k0+nb, j]; x overwrites the column.  64 columns per
+// CTA (one thread each), the tile and U_kk in shared memory.  PT (planar, pitch CNB): PT[plane][j][p] = x_p.
+template <bool C>
+__global__ void __launch_bounds__(64) chol_panel_kernel(typename HS<C>::T* __restrict__ M, long long ld, int n, int k0,
+                                                        int nb, double* __restrict__ PT, long long pt_plane) {
+  using H = HS<C>;
+  using T = typename H::T;
+  extern __shared__ __align__(16) unsigned char cp_raw[];
+  T(*Ukk)[CNB + 1] = reinterpret_cast<T(*)[CNB + 1]>(cp_raw);
+  T(*X)[CNB] = reinterpret_cast<T(*)[CNB]>(cp_raw + sizeof(T) * CNB * (CNB + 1));
+  const int c = threadIdx.x;
+  const long long j = (long long)k0 + nb + (long long)blockIdx.x * 64 + c;
+  for (int i = 0; i < nb; ++i)
+    if (c < nb) Ukk[i][c] = (c >= i) ? M[(long long)(k0 + i) * ld + k0 + c] : H::zero();
+  const bool live = j < n;
+  for (int p = 0; p < nb; ++p) X[p][c] = live ? M[(long long)(k0 + p) * ld + j] : H::zero();
+  __syncthreads();
+  for (int p = 0; p < nb; ++p) {
+    const T x = H::scale(1.0 / H::re(Ukk[p][p]), X[p][c]);
+    X[p][c] = x;
+    for (int q = p + 1; q < nb; ++q) X[q][c] = H::sub(X[q][c], H::cmul(Ukk[p][q], x));  // -= conj(U[p][q]) x_p
+  }
+  if (live) {
+    for (int p = 0; p < nb; ++p) {
+      const T x = X[p][c];
+      M[(long long)(k0 + p) * ld + j] = x;
+      PT[j * CNB + p] = H::re(x);
+      if (C) PT[pt_plane + j * CNB + p] = H::im(x);
+    }
+    for (int p = nb; p < CNB; ++p) {  // a short last block: the update contracts over CNB
+      PT[j * CNB + p] = 0.0;
+      if (C) PT[pt_plane + j * CNB + p] = 0.0;
+    }
+  }
+}
+
+// Trailing update, upper-triangular tiles: M[r0+i][r0+j] -= sum_p conj(U[p][i]) U[p][j].  MODE_COMPLEX accumulates
+// sum_p U[p][i] conj(U[p][j]), the conjugate of what is subtracted.
+template <bool C>
+struct OpCholUpdate {
+  struct Params {
+    Operand A, B;   // both = PT rows of the trailing columns
+    int nt;         // trailing size
+    double* Mout;   // &M[r0][r0]; complex: interleaved
+    long long ld;   // in elements
+  };
+  static __device__ __forceinline__ Tile tile(const Params& p) {
+    Tile t;
+    t.n0 = blockIdx.x * BN;
+    t.m0 = blockIdx.y * BM;
+    t.k_begin = 0;
+    t.k_end = p.A.kext;
+    t.valid = t.n0 + BN > t.m0;  // the tile touches the upper triangle
+    return t;
+  }
+  static __device__ __forceinline__ void epilogue(const Params& p, const Tile& t, Acc& acc, int warp_m, int warp_n,
+                                                  int lane, uint8_t*) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = t.m0 + warp_m * 32 + 8 * i + (lane >> 2);
+      if (row >= p.nt) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = t.n0 + warp_n * 32 + 8 * j + 2 * (lane & 3);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          if (col + e >= p.nt || col + e < row) continue;
+          if (C) {
+            double2* o = reinterpret_cast<double2*>(p.Mout) + (long long)row * p.ld + col + e;
+            double2 v = *o;
+            v.x -= acc.r[i][j][e];
+            v.y += acc.i[i][j][e];
+            *o = v;
+          } else {
+            p.Mout[(long long)row * p.ld + col + e] -= acc.r[i][j][e];
+          }
+        }
+      }
+    }
+  }
+};
+
+// ---- triangular solves with one right-hand side --------------------------------------------------------------
+// Diagonal block: forward (U_kk^H y = b_k) or backward (U_kk x = y_k), one CTA of 64 threads, column-oriented.
+template <bool C>
+__global__ void __launch_bounds__(64) chol_solve_diag_kernel(const typename HS<C>::T* __restrict__ U, long long ld, int k0,
+                                                             int nb, int backward, typename HS<C>::T* __restrict__ v) {
+  using H = HS<C>;
+  using T = typename H::T;
+  __shared__ T xs[CNB];
+  const int c = threadIdx.x;
+  if (c < nb) xs[c] = v[k0 + c];
+  __syncthreads();
+  if (!backward) {
+    for (int p = 0; p < nb; ++p) {
+      const T x = H::scale(1.0 / H::re(U[(long long)(k0 + p) * ld + k0 + p]), xs[p]);
+      __syncthreads();
+      if (c == p) xs[p] = x;
+      if (c > p && c < nb) xs[c] = H::sub(xs[c], H::cmul(U[(long long)(k0 + p) * ld + k0 + c], x));  // conj(U[p][c]) y_p
+      __syncthreads();
+    }
+  } else {
+    for (int p = nb - 1; p >= 0; --p) {
+      const T x = H::scale(1.0 / H::re(U[(long long)(k0 + p) * ld + k0 + p]), xs[p]);
+      __syncthreads();
+      if (c == p) xs[p] = x;
+      if (c < p) xs[c] = H::sub(xs[c], H::mul(U[(long long)(k0 + c) * ld + k0 + p], x));  // U[c][p] x_p
+      __syncthreads();
+    }
+  }
+  if (c < nb) v[k0 + c] = xs[c];
+}
+
+// Forward: v[j] -= sum_p conj(U[k0+p][j]) v[k0+p] for j >= k0 + nb.  Backward: v[i] -= sum_p U[i][k0+p] v[k0+p], i < k0.
+template <bool C>
+__global__ void __launch_bounds__(256) chol_solve_update_kernel(const typename HS<C>::T* __restrict__ U, long long ld,
+                                                                int n, int k0, int nb, int backward,
+                                                                typename HS<C>::T* __restrict__ v) {
+  using H = HS<C>;
+  using T = typename H::T;
+  __shared__ T xs[CNB];
+  if (threadIdx.x < nb) xs[threadIdx.x] = v[k0 + threadIdx.x];
+  __syncthreads();
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (!backward) {
+    const long long j = k0 + nb + t;
+    if (j >= n) return;
+    T acc = v[j];
+    for (int p = 0; p < nb; ++p) acc = H::sub(acc, H::cmul(U[(long long)(k0 + p) * ld + j], xs[p]));
+    v[j] = acc;
+  } else {
+    if (t >= k0) return;
+    T acc = v[t];
+    const T* row = U + t * ld + k0;
+    for (int p = 0; p < nb; ++p) acc = H::sub(acc, H::mul(row[p], xs[p]));
+    v[t] = acc;
+  }
+}
+
+}  // namespace nls
