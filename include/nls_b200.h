@@ -122,6 +122,11 @@ int nls_primal_coeffs(nls_ctx* ctx, const double* Q, const double* lam, const do
 int nls_cholesky_solve(nls_ctx* ctx, const double* A, int m, double diag_shift, const double* b,
                        double* U_out, double* beta_out);
 
+/* U^-1 (n x n row-major) of an upper-triangular factor U (n x n row-major; whatever lies below its diagonal is
+ * ignored, as with scipy's cho_factor output): the basis predict_std contracts with, (gamma C + A)^-1 = U^-1 U^-H
+ * (_neo_ls_svm.py:467-469 primal, :473-475 dual).  is_complex != 0: complex128 (interleaved), else float64. */
+int nls_triangular_inverse(nls_ctx* ctx, const double* U, int n, int is_complex, double* B_out);
+
 /* ---------------------------------------------------------------------------------------------
  * Stage 4 — leave-one-out sweep.  Replaces _neo_ls_svm.py:128-165 for the local rows:
  *     T = phi Q;  P = Re(T * v);  H = s^2 |T|^2 inv_c;  loo = (P r - y) / (1 - H r),

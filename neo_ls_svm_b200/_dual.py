@@ -75,9 +75,10 @@ def _device_state(model):
         return st
     ctx, torch, dev = model._gpu()
     n = model.X_.shape[0]
-    U = torch.triu(torch.from_numpy(np.asarray(model.L_[0], dtype=np.float64)).to(dev))
-    # (γS⁻² + F)⁻¹ = U⁻¹ U⁻ᵀ  ⇒  σ² = 1 − ‖(K U⁻¹)ᵢ‖²: Bt = (U⁻¹)ᵀ with unit weights.
-    Uinv = torch.linalg.solve_triangular(U, torch.eye(n, dtype=torch.float64, device=dev), upper=True)
+    U = torch.from_numpy(np.ascontiguousarray(model.L_[0], dtype=np.float64)).to(dev)
+    # (γS⁻² + F)⁻¹ = U⁻¹ U⁻ᵀ  ⇒  σ² = 1 − ‖(K U⁻¹)ᵢ‖²: Bt = (U⁻¹)ᵀ with unit weights (nls_triangular_inverse reads
+    # the upper triangle only, like cho_solve does).
+    Uinv = ctx.triangular_inverse(U)
     alpha = torch.from_numpy(np.asarray(model.α̂_, dtype=np.float64)).to(dev)
     st = {
         "kind": "dual",

@@ -48,6 +48,7 @@ def _signatures(lib: C.CDLL) -> None:
         "nls_ctx_last_eig_sweeps": ([p], i),
         "nls_primal_coeffs": ([p, p, p, p, i, d, d, p, p], i),
         "nls_cholesky_solve": ([p, p, i, d, p, p, p], i),
+        "nls_triangular_inverse": ([p, p, i, i, p], i),
         "nls_primal_loo_sweep": ([p, p, p, p, i64, i, p, p, i, p, p, p, d, p, i, i, p, p], i),
         "nls_primal_finalize": ([p, p, p, p, i64, i, p, p, i, p, p, d, d, p, p, i, p, p, p, p, p, p], i),
         "nls_primal_predict": ([p, p, i64, i, p, p, i, p, p, p, i, p, p], i),
@@ -280,8 +281,10 @@ class Context:
         import torch
 
         m = U.shape[0]
-        eye = torch.eye(m, dtype=U.dtype, device=U.device)
-        return torch.linalg.solve_triangular(torch.triu(U), eye, upper=True).contiguous()
+        U = U.contiguous()
+        out = torch.empty((m, m), dtype=U.dtype, device=U.device)
+        check(self.lib.nls_triangular_inverse(self.handle, ptr(U), m, int(U.is_complex()), ptr(out)))
+        return out
 
     def primal_loo_sweep(self, X, y, s, shift, W, Q, lam, v, inv_c: float, gammas, classifier: bool, stash=None):
         """Per-γ error sums (3×G); `stash` (n×G float64, optional) receives σ²ᵢ(γ_g) for every row."""

@@ -108,8 +108,7 @@ class NeoLSSVM(BaseEstimator):
             # (γC + A)⁻¹ = U⁻¹ U⁻ᴴ: the variance kernel takes the triangular B = U⁻¹ with unit weights and
             # skips the zero half of the contraction (4m² instead of 8m² flops per row).  Built once, lazily.
             m = st["U"].shape[0]
-            U = torch.triu(st["U"])
-            st["B"] = torch.linalg.solve_triangular(U, torch.eye(m, dtype=torch.complex128, device=dev), upper=True).contiguous()
+            st["B"] = ctx.triangular_inverse(st["U"])  # hand-written blocked inverse (csrc/potrf.cuh), upper triangle only
             st["w"] = torch.ones(m, dtype=torch.float64, device=dev)
         return st
 

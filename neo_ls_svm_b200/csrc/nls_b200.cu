@@ -23,6 +23,7 @@
 #include "stedc_host.h"
 #include "stedc.cuh"
 #include "hetrd.cuh"
+#include "potrf.cuh"
 
 using namespace nls;
 
@@ -71,7 +72,7 @@ struct DevBuf {
 
 // Scratch of the tridiagonalisation / divide-and-conquer eigensolver (csrc/eig_driver.inc), grow-only.
 struct EigBuffers {
-  DevBuf aw, vw, pwrw, vtvr, vecs, tfac, part, y, qa, qb, qp, u1, u2, delta, dc_d, dc_i, dc_desc, dc_rot, ws, c2;
+  DevBuf aw, vw, pwrw, vtvr, vecs, tfac, part, y, qa, qb, qp, u1, u2, delta, dc_d, dc_i, dc_desc, dc_rot, ws, c2, chol;
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -381,7 +382,7 @@ extern "C" int nls_ctx_destroy(nls_ctx* ctx) {
   {
     EigBuffers& e = ctx->eig;
     DevBuf* eb[] = {&e.aw, &e.vw, &e.pwrw, &e.vtvr, &e.vecs, &e.tfac, &e.part, &e.y, &e.qa, &e.qb, &e.qp, &e.u1, &e.u2,
-                    &e.delta, &e.dc_d, &e.dc_i, &e.dc_desc, &e.dc_rot, &e.ws, &e.c2};
+                    &e.delta, &e.dc_d, &e.dc_i, &e.dc_desc, &e.dc_rot, &e.ws, &e.c2, &e.chol};
     for (DevBuf* b : eb)
       if (b->p) cudaFree(b->p);
   }
@@ -943,8 +944,143 @@ extern "C" int nls_primal_coeffs(nls_ctx* ctx, const double* Q, const double* la
   return NLS_OK;
 }
 
+// Hand-written blocked Cholesky M = U^H U in place (csrc/potrf.cuh): M is n x n row-major with pitch ld elements
+// (complex: interleaved); the upper triangle becomes U, the strict lower triangle is left as it was.
+template <bool C>
+static int chol_factor(nls_ctx* ctx, double* Mraw, int n, long long ld) {
+  using T = typename HS<C>::T;
+  T* M = reinterpret_cast<T*>(Mraw);
+  const int planes = C ? 2 : 1;
+  const long long npad = round_up(n, 128);
+  NLS_TRY(ensure(ctx, ctx->eig.chol, (size_t)planes * npad * CNB * 8 + 64));
+  double* PT = (double*)ctx->eig.chol.p;
+  int* info = (int*)(PT + (size_t)planes * npad * CNB);
+  cudaStream_t st = ctx->stream;
+  CUDA_TRY(cudaMemsetAsync(info, 0, sizeof(int), st));
+  const size_t smem_d = sizeof(T) * CNB * (CNB + 1), smem_p = smem_d + sizeof(T) * CNB * CNB;
+  static bool attr_set[64][2] = {{false}};
+  if (!attr_set[ctx->device & 63][C]) {
+    CUDA_TRY(cudaFuncSetAttribute(chol_diag_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
+    CUDA_TRY(cudaFuncSetAttribute(chol_panel_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+    attr_set[ctx->device & 63][C] = true;
+  }
+  ProfScope scope(ctx, NLS_PROF_OTHER);
+  for (int k0 = 0; k0 < n; k0 += CNB) {
+    const int nb = std::min(CNB, n - k0);
+    chol_diag_kernel<C><<<1, 256, smem_d, st>>>(M, ld, k0, nb, info);
+    NLS_TRY(check_launch(ctx, "chol_diag_kernel"));
+    const int r0 = k0 + nb, nt = n - r0;
+    if (nt <= 0) break;
+    chol_panel_kernel<C><<<(nt + 63) / 64, 64, smem_p, st>>>(M, ld, n, k0, nb, PT, npad * CNB);
+    NLS_TRY(check_launch(ctx, "chol_panel_kernel"));
+    typename OpCholUpdate<C>::Params up;
+    up.A = Operand{PT + (long long)r0 * CNB, CNB, nt, CNB, (int)npad, 0};
+    up.B = up.A;
+    up.nt = nt;
+    up.Mout = reinterpret_cast<double*>(M + (long long)r0 * ld + r0);
+    up.ld = ld;
+    const dim3 grid((nt + BN - 1) / BN, (nt + BM - 1) / BM);
+    if (C) {
+      NLS_TRY((launch_gemm<MODE_COMPLEX, OpCholUpdate<C>>(ctx, up, grid, planes * npad - r0, planes * npad - r0, NLS_PROF_OTHER, "chol_update")));
+    } else {
+      NLS_TRY((launch_gemm<MODE_REAL, OpCholUpdate<C>>(ctx, up, grid, planes * npad - r0, planes * npad - r0, NLS_PROF_OTHER, "chol_update")));
+    }
+  }
+  int h_info = 0;
+  CUDA_TRY(cudaMemcpyAsync(&h_info, info, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (h_info != 0) return fail(NLS_ERR_SOLVER, "Cholesky factorisation failed: the leading minor of order %d is not positive definite", h_info);
+  return NLS_OK;
+}
+
+// v <- (U^H U)^-1 v by block forward and back substitution.
+template <bool C>
+static int chol_solve(nls_ctx* ctx, const double* Uraw, int n, long long ld, double* vraw) {
+  using T = typename HS<C>::T;
+  const T* U = reinterpret_cast<const T*>(Uraw);
+  T* v = reinterpret_cast<T*>(vraw);
+  cudaStream_t st = ctx->stream;
+  for (int k0 = 0; k0 < n; k0 += CNB) {
+    const int nb = std::min(CNB, n - k0), nt = n - k0 - nb;
+    chol_solve_diag_kernel<C><<<1, 64, 0, st>>>(U, ld, k0, nb, 0, v);
+    if (nt > 0) chol_solve_update_kernel<C><<<(nt + 255) / 256, 256, 0, st>>>(U, ld, n, k0, nb, 0, v);
+    ctx->launches += 1 + (nt > 0);
+  }
+  for (int k0 = ((n - 1) / CNB) * CNB; k0 >= 0; k0 -= CNB) {
+    const int nb = std::min(CNB, n - k0);
+    chol_solve_diag_kernel<C><<<1, 64, 0, st>>>(U, ld, k0, nb, 1, v);
+    if (k0 > 0) chol_solve_update_kernel<C><<<(k0 + 255) / 256, 256, 0, st>>>(U, ld, n, k0, nb, 1, v);
+    ctx->launches += 1 + (k0 > 0);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(NLS_ERR_CUDA, "triangular solve launch failed: %s", cudaGetErrorString(e));
+  return NLS_OK;
+}
+
+// B_out = U^-1 (n x n row-major, pitch n) of the upper triangle of U (pitch ld elements); csrc/potrf.cuh.
+template <bool C>
+static int tri_inverse(nls_ctx* ctx, const double* Uraw, int n, long long ld, double* Bout) {
+  using T = typename HS<C>::T;
+  const int planes = C ? 2 : 1;
+  const long long npad = round_up(n, 128), ldu = round_up(n, 16);
+  const size_t plane = (size_t)npad * ldu;
+  EigBuffers& B = ctx->eig;
+  NLS_TRY(ensure(ctx, B.qa, (size_t)planes * plane * 8));                  // planar U
+  NLS_TRY(ensure(ctx, B.qb, (size_t)planes * plane * 8));                  // Xt
+  NLS_TRY(ensure(ctx, B.qp, (size_t)planes * CNB * ldu * 8));              // R
+  double* Up = (double*)B.qa.p;
+  double* Xt = (double*)B.qb.p;
+  double* R = (double*)B.qp.p;
+  cudaStream_t st = ctx->stream;
+  ProfScope scope(ctx, NLS_PROF_OTHER);
+  CUDA_TRY(cudaMemsetAsync(Up, 0, (size_t)planes * plane * 8, st));
+  CUDA_TRY(cudaMemsetAsync(Xt, 0, (size_t)planes * plane * 8, st));
+  trtri_split_kernel<C><<<grid_for((long long)n * n), 256, 0, st>>>(reinterpret_cast<const T*>(Uraw), ld, n, Up, ldu, (long long)plane);
+  NLS_TRY(check_launch(ctx, "trtri_split_kernel"));
+  const size_t smem = sizeof(T) * CNB * (CNB + 1) + sizeof(T) * CNB * CNB;
+  static bool attr_set[64][2] = {{false}};
+  if (!attr_set[ctx->device & 63][C]) {
+    CUDA_TRY(cudaFuncSetAttribute(trtri_block_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[ctx->device & 63][C] = true;
+  }
+  for (int k0 = ((n - 1) / CNB) * CNB; k0 >= 0; k0 -= CNB) {
+    const int nb = std::min(CNB, n - k0), k_lo = k0 + nb;
+    if (k_lo < n) {
+      typename OpTrtriProduct<C>::Params pp;
+      pp.A = Operand{Up + (long long)k0 * ldu, ldu, nb, n, (int)npad, 0};
+      pp.B = Operand{Xt, ldu, n, n, (int)npad, 0};
+      pp.nb = nb;
+      pp.j0 = k_lo;
+      pp.n = n;
+      pp.k_lo = k_lo;
+      pp.R = R;
+      pp.ldr = ldu;
+      pp.rplane = (long long)CNB * ldu;
+      const dim3 grid((n - k_lo + BN - 1) / BN, 1);
+      if (C) {
+        NLS_TRY((launch_gemm<MODE_COMPLEX, OpTrtriProduct<C>>(ctx, pp, grid, planes * npad - k0, planes * npad, NLS_PROF_OTHER, "trtri_product")));
+      } else {
+        NLS_TRY((launch_gemm<MODE_REAL, OpTrtriProduct<C>>(ctx, pp, grid, planes * npad - k0, planes * npad, NLS_PROF_OTHER, "trtri_product")));
+      }
+    }
+    trtri_block_kernel<C><<<(n - k0 + 63) / 64, 64, smem, st>>>(Up, ldu, (long long)plane, n, k0, nb, R, ldu, (long long)CNB * ldu, Xt);
+    NLS_TRY(check_launch(ctx, "trtri_block_kernel"));
+  }
+  trtri_export_kernel<C><<<dim3((n + 31) / 32, (n + 31) / 32), 256, 0, st>>>(Xt, ldu, (long long)plane, n, reinterpret_cast<T*>(Bout));
+  return check_launch(ctx, "trtri_export_kernel");
+}
+
+// U^-1 of an upper-triangular factor (anything below the diagonal of U is ignored): the basis of predict_std,
+// (gamma C + A)^-1 = U^-1 U^-H (_neo_ls_svm.py:467-469 primal / :473-475 dual).  is_complex selects complex128.
+extern "C" int nls_triangular_inverse(nls_ctx* ctx, const double* U, int n, int is_complex, double* B_out) {
+  if (!ctx || !U || !B_out || n < 1) return fail(NLS_ERR_INVALID, "bad argument to nls_triangular_inverse");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  return is_complex ? tri_inverse<true>(ctx, U, n, n, B_out) : tri_inverse<false>(ctx, U, n, n, B_out);
+}
+
 // U (upper, row-major, M = U^H U like scipy.linalg.cho_factor) of M = A + diag_shift * I, and
-// beta = M^-1 b.   _neo_ls_svm.py:177-178.
+// beta = M^-1 b.   _neo_ls_svm.py:177-178.  Hand-written blocked Cholesky (csrc/potrf.cuh); cuSOLVER's Zpotrf / Zpotrs
+// only as the comparator (nls_ctx_set_eigensolver(1) / NLS_EIG=cusolver).
 extern "C" int nls_cholesky_solve(nls_ctx* ctx, const double* A, int m, double diag_shift, const double* b,
                                   double* U_out, double* beta_out) {
   if (!ctx || !A || !U_out || m < 1) return fail(NLS_ERR_INVALID, "bad argument to nls_cholesky_solve");
@@ -953,6 +1089,14 @@ extern "C" int nls_cholesky_solve(nls_ctx* ctx, const double* A, int m, double d
   CUDA_TRY(cudaMemcpyAsync(U_out, A, (size_t)mm * 16, cudaMemcpyDeviceToDevice, ctx->stream));
   add_diag_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(U_out, m, diag_shift);
   NLS_TRY(check_launch(ctx, "add_diag_kernel"));
+  if (ctx->eig_kind != 1) {
+    NLS_TRY(chol_factor<true>(ctx, U_out, m, m));
+    if (b && beta_out) {
+      CUDA_TRY(cudaMemcpyAsync(beta_out, b, (size_t)m * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+      NLS_TRY(chol_solve<true>(ctx, U_out, m, m, beta_out));
+    }
+    return NLS_OK;
+  }
   // Row-major M read column-major is conj(M); its LOWER Cholesky factor stored column-major is
   // exactly U row-major with M = U^H U.
   int lwork = 0;
@@ -1415,17 +1559,23 @@ extern "C" int nls_dual_finalize(nls_ctx* ctx, int n, const double* y, const dou
     NLS_TRY(check_launch(ctx, "pad_rows_kernel"));
     dual_add_diag_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(U_out, n, sn, gamma);
     NLS_TRY(check_launch(ctx, "dual_add_diag_kernel"));
-    int lwork = 0;
-    SOLVER_TRY(cusolverDnDpotrf_bufferSize(ctx->solver, CUBLAS_FILL_MODE_LOWER, n, U_out, n, &lwork));
-    NLS_TRY(ensure(ctx, ctx->solver_ws, (size_t)lwork * 8 + 64));
-    int* info = (int*)((char*)ctx->solver_ws.p + (size_t)lwork * 8);
-    SOLVER_TRY(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, n, U_out, n, (double*)ctx->solver_ws.p, lwork, info));
-    int h_info = 0;
-    CUDA_TRY(cudaMemcpyAsync(&h_info, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    if (h_info != 0) return fail(NLS_ERR_SOLVER, "dual Cholesky factorisation failed: info = %d", h_info);
-    CUDA_TRY(cudaMemcpyAsync(alpha_out, y, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    SOLVER_TRY(cusolverDnDpotrs(ctx->solver, CUBLAS_FILL_MODE_LOWER, n, 1, U_out, n, alpha_out, n, info));
+    if (ctx->eig_kind != 1) {  // hand-written blocked Cholesky + triangular solves (csrc/potrf.cuh)
+      NLS_TRY(chol_factor<false>(ctx, U_out, n, n));
+      CUDA_TRY(cudaMemcpyAsync(alpha_out, y, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+      NLS_TRY(chol_solve<false>(ctx, U_out, n, n, alpha_out));
+    } else {  // cuSOLVER comparator
+      int lwork = 0;
+      SOLVER_TRY(cusolverDnDpotrf_bufferSize(ctx->solver, CUBLAS_FILL_MODE_LOWER, n, U_out, n, &lwork));
+      NLS_TRY(ensure(ctx, ctx->solver_ws, (size_t)lwork * 8 + 64));
+      int* info = (int*)((char*)ctx->solver_ws.p + (size_t)lwork * 8);
+      SOLVER_TRY(cusolverDnDpotrf(ctx->solver, CUBLAS_FILL_MODE_LOWER, n, U_out, n, (double*)ctx->solver_ws.p, lwork, info));
+      int h_info = 0;
+      CUDA_TRY(cudaMemcpyAsync(&h_info, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      if (h_info != 0) return fail(NLS_ERR_SOLVER, "dual Cholesky factorisation failed: info = %d", h_info);
+      CUDA_TRY(cudaMemcpyAsync(alpha_out, y, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+      SOLVER_TRY(cusolverDnDpotrs(ctx->solver, CUBLAS_FILL_MODE_LOWER, n, 1, U_out, n, alpha_out, n, info));
+    }
   } else if (alpha_eig_out) {
     CUDA_TRY(cudaMemcpyAsync(alpha_out, alpha_eig_out, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   }

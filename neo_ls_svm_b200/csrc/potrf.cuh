@@ -186,4 +186,124 @@ __global__ void __launch_bounds__(256) chol_solve_update_kernel(const typename H
   }
 }
 
+
+// =============================================================================================
+// Triangular inverse X = U^-1 (U upper, row-major; what predict_std contracts with: (gamma C + A)^-1 = U^-1 U^-H,
+// _neo_ls_svm.py:467-469 / :473-475).  Block back substitution over the block rows from the bottom,
+//     X_k,: = U_kk^-1 (E_k,: - U_k,k+1: X_k+1:,:),
+// with the product on the FP64 DMMA GEMM core.  X is built TRANSPOSED and conjugated (Xt[j][p] = conj(X[p][j]),
+// planar), which is the K-contiguous operand the next block rows' products need; trtri_export turns it around.
+// =============================================================================================
+// Planar copy of the upper triangle of U (zeros below the diagonal).
+template <bool C>
+__global__ void trtri_split_kernel(const typename HS<C>::T* __restrict__ U, long long ld, int n, double* __restrict__ Up,
+                                   long long ldu, long long uplane) {
+  const long long total = (long long)n * n;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long i = t / n, j = t % n;
+    const typename HS<C>::T v = (j >= i) ? U[i * ld + j] : HS<C>::zero();
+    Up[i * ldu + j] = HS<C>::re(v);
+    if (C) Up[uplane + i * ldu + j] = HS<C>::im(v);
+  }
+}
+
+// R[i][j] = sum_{p >= k_lo} U[k0+i][p] X[p][j] for the columns j >= j0.
+template <bool C>
+struct OpTrtriProduct {
+  struct Params {
+    Operand A, B;      // A = planar U rows k0.., B = Xt rows (planar, conjugated)
+    int nb, j0, n, k_lo;
+    double* R;         // [planes][CNB][ldr]
+    long long ldr, rplane;
+  };
+  static __device__ __forceinline__ Tile tile(const Params& p) {
+    Tile t;
+    t.m0 = 0;
+    t.n0 = p.j0 + blockIdx.x * BN;
+    t.k_begin = p.k_lo;
+    t.k_end = p.n;
+    t.valid = true;
+    return t;
+  }
+  static __device__ __forceinline__ void epilogue(const Params& p, const Tile& t, Acc& acc, int warp_m, int warp_n,
+                                                  int lane, uint8_t*) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = warp_m * 32 + 8 * i + (lane >> 2);
+      if (row >= p.nb) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = t.n0 + warp_n * 32 + 8 * j + 2 * (lane & 3);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          if (col + e >= p.n) continue;
+          p.R[(long long)row * p.ldr + col + e] = acc.r[i][j][e];
+          if (C) p.R[p.rplane + (long long)row * p.ldr + col + e] = acc.i[i][j][e];
+        }
+      }
+    }
+  }
+};
+
+// Block row k of X: for every column j >= k0 solve U_kk x = e_j[k0:k0+nb] - R[:, j] (R = 0 for j < k0 + nb) and store
+// Xt[j][k0 + i] = conj(x_i).  64 columns per CTA, one thread each.
+template <bool C>
+__global__ void __launch_bounds__(64) trtri_block_kernel(const double* __restrict__ Up, long long ldu, long long uplane,
+                                                         int n, int k0, int nb, const double* __restrict__ R, long long ldr,
+                                                         long long rplane, double* __restrict__ Xt) {
+  using H = HS<C>;
+  using T = typename H::T;
+  extern __shared__ __align__(16) unsigned char tb_raw[];
+  T(*Ukk)[CNB + 1] = reinterpret_cast<T(*)[CNB + 1]>(tb_raw);
+  T(*X)[CNB] = reinterpret_cast<T(*)[CNB]>(tb_raw + sizeof(T) * CNB * (CNB + 1));
+  const int c = threadIdx.x;
+  const long long j = (long long)k0 + (long long)blockIdx.x * 64 + c;
+  for (int i = 0; i < nb; ++i)
+    if (c < nb) {
+      const long long o = (long long)(k0 + i) * ldu + k0 + c;
+      Ukk[i][c] = H::make(Up[o], C ? Up[uplane + o] : 0.0);
+    }
+  const bool live = j < n;
+  for (int i = 0; i < nb; ++i) {
+    T rhs = H::make((j == k0 + i) ? 1.0 : 0.0, 0.0);
+    if (live && j >= k0 + nb) rhs = H::sub(rhs, H::make(R[(long long)i * ldr + j], C ? R[rplane + (long long)i * ldr + j] : 0.0));
+    X[i][c] = rhs;
+  }
+  __syncthreads();
+  for (int p = nb - 1; p >= 0; --p) {
+    // 1 / U[p][p] for a complex diagonal entry (Cholesky factors have a real one, a general triangular U need not)
+    const T d = Ukk[p][p];
+    const double den = H::abs2(d);
+    const T x = H::mul(X[p][c], H::make(H::re(d) / den, -H::im(d) / den));
+    X[p][c] = x;
+    for (int q = 0; q < p; ++q) X[q][c] = H::sub(X[q][c], H::mul(Ukk[q][p], x));
+  }
+  if (live)
+    for (int i = 0; i < nb; ++i) {
+      const long long o = j * ldu + k0 + i;
+      Xt[o] = H::re(X[i][c]);
+      if (C) Xt[uplane + o] = -H::im(X[i][c]);
+    }
+}
+
+// Bout[p][j] = X[p][j] = conj(Xt[j][p]); 32 x 32 tiles through shared memory.
+template <bool C>
+__global__ void __launch_bounds__(256) trtri_export_kernel(const double* __restrict__ Xt, long long ldu, long long uplane,
+                                                           int n, typename HS<C>::T* __restrict__ Bout) {
+  __shared__ double tr[32][33], ti[32][33];
+  const int j0 = blockIdx.x * 32, p0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int jj = ty; jj < 32; jj += 8) {
+    const int j = j0 + jj, p = p0 + tx;
+    const bool ok = j < n && p < n;
+    tr[jj][tx] = ok ? Xt[(long long)j * ldu + p] : 0.0;
+    ti[jj][tx] = (ok && C) ? Xt[uplane + (long long)j * ldu + p] : 0.0;
+  }
+  __syncthreads();
+  for (int pp = ty; pp < 32; pp += 8) {
+    const int p = p0 + pp, j = j0 + tx;
+    if (p < n && j < n) Bout[(long long)p * n + j] = HS<C>::make(tr[tx][pp], -ti[tx][pp]);
+  }
+}
+
 }  // namespace nls

@@ -292,6 +292,40 @@ def test_dc_eigensolver_is_deterministic(gpu):
     assert torch.equal(l1, l2) and torch.equal(Q1, Q2)
 
 
+@pytest.mark.parametrize("m", [1, 2, 63, 64, 65, 130, 513, 1025])
+def test_cholesky_and_triangular_inverse_match_lapack(m, gpu):
+    """The hand-written blocked Cholesky (M = UᴴU in scipy's cho_factor layout), its two triangular solves and the
+    blocked triangular inverse against LAPACK, on a Hermitian positive definite matrix with condition 1e10; the strict
+    lower triangle of the factor keeps garbage and must be ignored by the inverse."""
+    import scipy.linalg as sl
+
+    from neo_ls_svm_b200 import _lib
+
+    _, dev, _, torch = gpu
+    ctx = _lib.Context(0)
+    rng = np.random.default_rng(3000 + m)
+    Qm, _ = np.linalg.qr(rng.standard_normal((m, m)) + 1j * rng.standard_normal((m, m)))
+    A = (Qm * np.logspace(0, -10, m)) @ Qm.conj().T
+    A = (A + A.conj().T) / 2
+    b = rng.standard_normal(m) + 1j * rng.standard_normal(m)
+    shift = 1e-3
+    U, beta = ctx.cholesky_solve(dev(A), shift, dev(b))
+    Uh, bh = U.cpu().numpy(), beta.cpu().numpy()
+    ref_c, _ = sl.cho_factor(A + shift * np.eye(m), lower=False)
+    ref_beta = sl.cho_solve((ref_c, False), b)
+    assert rel_err(np.triu(Uh), np.triu(ref_c)) < 1e-12
+    assert rel_err(bh, ref_beta) < 1e-10
+    dirty = U + torch.tril(torch.full_like(U, 7.0 - 3.0j), diagonal=-1)
+    Binv = ctx.triangular_inverse(dirty.contiguous()).cpu().numpy()
+    assert np.max(np.abs(np.tril(Binv, -1))) == 0.0
+    assert rel_err(Binv, np.linalg.inv(np.triu(ref_c))) < 1e-10
+    # real symmetric instantiation (the dual path's factor)
+    Ar = np.real(A) + shift * np.eye(m)
+    Ur = np.triu(np.linalg.cholesky(Ar).T)
+    Br = ctx.triangular_inverse(dev(Ur)).cpu().numpy()
+    assert rel_err(Br, np.linalg.inv(Ur)) < 1e-10
+
+
 @pytest.mark.parametrize("jb", ["8", "4"])
 @pytest.mark.parametrize("m", [1, 2, 3, 15, 16, 17, 33, 100, 300])
 def test_jacobi_odd_sizes_and_clusters(jb, m, gpu, monkeypatch):
