@@ -155,7 +155,8 @@ def device_bin_location_spread(Xd, rows, s_bins, ctx=None):
     perm_d, w_d = torch.from_numpy(perm).to(dev), torch.from_numpy(w).to(dev)
     tiles_d, bt_d = torch.from_numpy(tiles).to(dev), torch.from_numpy(bin_tiles).to(dev)
     flat = [np.ravel(sb) for sb in s_bins]
-    uniform = all(len(f) > 0 and np.all(f == f[0]) for f in flat)
+    # equal weights within every bin <=> min == max (two reductions instead of a comparison array per bin)
+    uniform = all(len(f) > 0 and f.min() == f.max() for f in flat)
     if uniform:
         plans = [uniform_rank_plan(float(f[0]), len(f)) for f in flat]
         ones = torch.ones_like(w_d)

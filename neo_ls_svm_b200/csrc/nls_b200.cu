@@ -110,6 +110,8 @@ struct nls_ctx {
   DevBuf jac_mat, jac_small, bs_part, bs_keys, dotpart;
   DevBuf d_xpad, d_xq, d_norm, d_fm, d_sq, d_sqt, d_g1, d_ab, d_ra, d_vec, d_ng, d_kq, d_btp;
   int dual_n = 0;
+  const void* dual_y = nullptr;   // the y / sn the pending dual sweep was run with: nls_dual_finalize must be given
+  const void* dual_sn = nullptr;  // the same ones (guards against interleaving two models on one context)
   EigBuffers eig;
   std::vector<double> last_d, last_e;  // tridiagonal form produced by the last eigensolve (host copies)
   // profiling
@@ -1528,6 +1530,8 @@ extern "C" int nls_dual_sweep(nls_ctx* ctx, const double* Xt, int n, int p, cons
   sweep_reduce_kernel<<<(3 * G + 255) / 256, 256, 0, ctx->stream>>>((const double*)ctx->part.p, mtiles, G, sums_out);
   NLS_TRY(check_launch(ctx, "sweep_reduce_kernel"));
   ctx->dual_n = n;
+  ctx->dual_y = y;
+  ctx->dual_sn = sn;
   return NLS_OK;
 }
 
@@ -1536,6 +1540,9 @@ extern "C" int nls_dual_finalize(nls_ctx* ctx, int n, const double* y, const dou
                                  double* sigma2_out, double* Bt_out, double* w_out) {
   if (!ctx || !y || !sn || !alpha_out) return fail(NLS_ERR_INVALID, "null pointer");
   if (ctx->dual_n != n || n < 2) return fail(NLS_ERR_INVALID, "nls_dual_finalize must follow nls_dual_sweep with the same n");
+  if (ctx->dual_y != (const void*)y || ctx->dual_sn != (const void*)sn)
+    return fail(NLS_ERR_INVALID, "nls_dual_finalize: y / sn are not the arrays of the last nls_dual_sweep on this context "
+                                 "(the sweep's kernel matrix and eigenbasis are context state: finish one model before starting another)");
   CUDA_TRY(cudaSetDevice(ctx->device));
   const long long ldn = round_up(n, 16);
   double* F = (double*)ctx->d_fm.p;
