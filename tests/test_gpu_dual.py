@@ -57,11 +57,15 @@ def test_dual_sweep_matches_oracle(n, p):
     ref = orc.dual_fit(Xt, y, s, classifier=False)
     ctx = _lib.Context(0)
     dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()  # noqa: E731
-    sums, yhat_loo, lam = ctx.dual_sweep(dev(Xt), dev(y), dev(ref["s"]), dev(ref["sn"]), dev(gamma_grid(128)), False)
+    yd, snd = dev(y), dev(ref["sn"])
+    sums, yhat_loo, lam = ctx.dual_sweep(dev(Xt), yd, dev(ref["s"]), snd, dev(gamma_grid(128)), False)
     assert rel_err(lam.cpu().numpy(), ref["lam"]) < 1e-11
     assert rel_err(sums[0].cpu().numpy(), ref["loo_errors"]) < 1e-9
     assert int(np.argmin(sums[0].cpu().numpy())) == ref["opt"]
-    fin = ctx.dual_finalize(n, dev(y), dev(ref["sn"]), ref["gamma"])
+    # the sweep's kernel matrix and eigenbasis are context state: finalize must be handed the sweep's own y / sn
+    with pytest.raises(_lib.NlsError):
+        ctx.dual_finalize(n, dev(y), dev(ref["sn"]), ref["gamma"])
+    fin = ctx.dual_finalize(n, yd, snd, ref["gamma"])
     assert rel_err(fin["alpha"].cpu().numpy(), ref["alpha"]) < 1e-9
     assert rel_err(fin["alpha_eig"].cpu().numpy(), ref["alpha"]) < 1e-8
     assert rel_err(np.sqrt(fin["sigma2"].cpu().numpy()), ref["loo_std"]) < 1e-8
