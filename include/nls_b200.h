@@ -102,10 +102,16 @@ int nls_heev(nls_ctx* ctx, const double* A, int m, double scale, double* lam_out
 int nls_stedc(nls_ctx* ctx, int n, const double* d_host, const double* e_host, double* lam_out, double* Zt_out);
 /* The tridiagonal form (host arrays d: n, e: n - 1) the last eigensolve of this context reduced its matrix to. */
 int nls_ctx_last_tridiagonal(nls_ctx* ctx, int n, double* d_host, double* e_host);
-/* Which solver nls_heev runs: 0 = the hand-written parallel two-sided block Jacobi kernels
- * (csrc/jacobi.cuh), 1 = cuSOLVER Zheevd (library comparator), 2 = auto (default: Jacobi for
- * m <= 1100, cuSOLVER above).  Also selectable with NLS_EIG=jacobi|cusolver. */
+/* Which solver nls_heev (and the dual path's real symmetric solve) runs: 0 = the hand-written parallel two-sided
+ * block Jacobi kernels (csrc/jacobi_wide.cuh), 1 = cuSOLVER Zheevd / Dsyevd (library comparator, never the default),
+ * 2 = auto (default) = 3 = the hand-written tridiagonalisation + divide and conquer + back-transformation
+ * (csrc/hetrd.cuh, csrc/stedc.cuh).  Also selectable with NLS_EIG=jacobi|cusolver|dc. */
 int nls_ctx_set_eigensolver(nls_ctx* ctx, int kind);
+/* Which tensor-core path the eigenbasis projection T = phi Q of nls_primal_loo_sweep (_neo_ls_svm.py:134, :137) runs
+ * on: 1 (default) = tcgen05.mma kind::i8 with TMEM accumulators, FP64-accurate through the Ozaki scheme (7 signed
+ * base-128 digit planes per operand, 28 exact INT8 plane products, FP64 recombination; csrc/ozaki.cuh), 0 = FP64 DMMA
+ * like every other stage.  Also selectable with NLS_GEMM=ozaki|dmma. */
+int nls_ctx_set_gemm_core(nls_ctx* ctx, int kind);
 /* Number of Jacobi sweeps the last nls_heev call needed (0 for cuSOLVER). */
 int nls_ctx_last_eig_sweeps(const nls_ctx* ctx);
 

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnls_b200.so")
 SOURCES = ["nls_b200.cu"]
-HEADERS = ["ptx.cuh", "gemm_core.cuh", "ops.cuh", "small_kernels.cuh", "jacobi.cuh", "jacobi_wide.cuh", "binstats.cuh", "secular.h", "stedc_host.h", "stedc.cuh", "hetrd.cuh", "potrf.cuh", "eig_driver.inc", "../../include/nls_b200.h"]
+HEADERS = ["ptx.cuh", "gemm_core.cuh", "ops.cuh", "small_kernels.cuh", "jacobi.cuh", "jacobi_wide.cuh", "binstats.cuh", "secular.h", "stedc_host.h", "stedc.cuh", "hetrd.cuh", "potrf.cuh", "ozaki.cuh", "eig_driver.inc", "../../include/nls_b200.h"]
 
 
 def _stale() -> bool:

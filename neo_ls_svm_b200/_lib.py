@@ -45,6 +45,7 @@ def _signatures(lib: C.CDLL) -> None:
         "nls_stedc": ([p, i, p, p, p, p], i),
         "nls_ctx_last_tridiagonal": ([p, i, p, p], i),
         "nls_ctx_set_eigensolver": ([p, i], i),
+        "nls_ctx_set_gemm_core": ([p, i], i),
         "nls_ctx_last_eig_sweeps": ([p], i),
         "nls_primal_coeffs": ([p, p, p, p, i, d, d, p, p], i),
         "nls_cholesky_solve": ([p, p, i, d, p, p, p], i),
@@ -150,6 +151,11 @@ class Context:
         """'dc' (hand-written tridiagonalisation + divide and conquer; what 'auto', the default, runs), 'jacobi'
         (hand-written block Jacobi kernels) or 'cusolver' (library comparator)."""
         check(self.lib.nls_ctx_set_eigensolver(self.handle, {"jacobi": 0, "cusolver": 1, "auto": 2, "dc": 3}[kind]))
+
+    def set_gemm_core(self, kind: str) -> None:
+        """'ozaki' (default): the projection T = φQ runs on the INT8 tensor cores (tcgen05, Ozaki scheme, FP64-accurate);
+        'dmma': FP64 DMMA like the other stages."""
+        check(self.lib.nls_ctx_set_gemm_core(self.handle, {"dmma": 0, "ozaki": 1}[kind]))
 
     def last_eig_sweeps(self) -> int:
         return int(self.lib.nls_ctx_last_eig_sweeps(self.handle))

@@ -24,6 +24,7 @@
 #include "stedc.cuh"
 #include "hetrd.cuh"
 #include "potrf.cuh"
+#include "ozaki.cuh"
 
 using namespace nls;
 
@@ -109,6 +110,11 @@ struct nls_ctx {
   // dual path (state kept between nls_dual_sweep and nls_dual_finalize)
   DevBuf jac_mat, jac_small, bs_part, bs_keys, dotpart;
   DevBuf d_xpad, d_xq, d_norm, d_fm, d_sq, d_sqt, d_g1, d_ab, d_ra, d_vec, d_ng, d_kq, d_btp;
+  // INT8 (Ozaki) GEMM core of the projection (csrc/ozaki.cuh): digit planes of the chunk / of the basis, per-column
+  // exponents and recombination scales
+  DevBuf oz_a, oz_b, oz_small;
+  int gemm_core = 1;      // 1: projection on tcgen05 kind::i8 (Ozaki scheme, default), 0: everything on DMMA
+  bool oz_attr = false;   // dynamic shared memory opt-in of the INT8 kernels done on this device
   int dual_n = 0;
   const void* dual_y = nullptr;   // the y / sn the pending dual sweep was run with: nls_dual_finalize must be given
   const void* dual_sn = nullptr;  // the same ones (guards against interleaving two models on one context)
@@ -350,6 +356,9 @@ extern "C" int nls_ctx_create(int device, void* stream, nls_ctx** out) {
   if (env && strcmp(env, "cusolver") == 0) ctx->eig_kind = 1;
   if (env && strcmp(env, "jacobi") == 0) ctx->eig_kind = 0;
   if (env && strcmp(env, "dc") == 0) ctx->eig_kind = 3;
+  env = getenv("NLS_GEMM");
+  if (env && strcmp(env, "dmma") == 0) ctx->gemm_core = 0;
+  if (env && strcmp(env, "ozaki") == 0) ctx->gemm_core = 1;
   env = getenv("NLS_JACOBI_INNER");
   if (env && atoi(env) > 0) ctx->jac_inner = atoi(env);
   env = getenv("NLS_CHUNK_ROWS");
@@ -378,7 +387,7 @@ extern "C" int nls_ctx_destroy(nls_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->xc, &ctx->wt, &ctx->psi, &ctx->psiT, &ctx->pu, &ctx->bt, &ctx->rt, &ctx->small,
                     &ctx->part, &ctx->gram_ws, &ctx->border, &ctx->rowtmp, &ctx->solver_ws, &ctx->solver_mat,
                     &ctx->jac_mat, &ctx->jac_small, &ctx->bs_part, &ctx->bs_keys, &ctx->dotpart, &ctx->d_xpad, &ctx->d_xq, &ctx->d_norm, &ctx->d_fm, &ctx->d_sq, &ctx->d_sqt, &ctx->d_g1,
-                    &ctx->d_ab, &ctx->d_ra, &ctx->d_vec, &ctx->d_ng, &ctx->d_kq, &ctx->d_btp};
+                    &ctx->d_ab, &ctx->d_ra, &ctx->d_vec, &ctx->d_ng, &ctx->d_kq, &ctx->d_btp, &ctx->oz_a, &ctx->oz_b, &ctx->oz_small};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   {
@@ -930,6 +939,13 @@ extern "C" int nls_ctx_set_eigensolver(nls_ctx* ctx, int kind) {
 
 extern "C" int nls_ctx_last_eig_sweeps(const nls_ctx* ctx) { return ctx ? ctx->eig_sweeps : 0; }
 
+extern "C" int nls_ctx_set_gemm_core(nls_ctx* ctx, int kind) {
+  if (!ctx || kind < 0 || kind > 1)
+    return fail(NLS_ERR_INVALID, "GEMM core must be 0 (FP64 DMMA everywhere) or 1 (projection on the INT8 tensor cores, Ozaki scheme)");
+  ctx->gemm_core = kind;
+  return NLS_OK;
+}
+
 // v = Q^H b inv_c  and (optionally, gamma >= 0) beta_eig = Q (v / (lam + gamma)).
 extern "C" int nls_primal_coeffs(nls_ctx* ctx, const double* Q, const double* lam, const double* b, int m,
                                  double inv_c, double gamma, double* v_out, double* beta_eig_out) {
@@ -1125,6 +1141,65 @@ extern "C" int nls_cholesky_solve(nls_ctx* ctx, const double* A, int m, double d
 }
 
 // ---------------------------------------------------------------------------------------------
+// Projection on the INT8 tensor cores (csrc/ozaki.cuh)
+// ---------------------------------------------------------------------------------------------
+struct OzBasis {
+  const int8_t* planes;    // [n_tiles][nks][S][64 x 32 B]
+  const double* colscale;  // 2^(eA + eB_j) per complex column
+  int n_tiles, nks, eA;
+};
+
+static int oz_attr(nls_ctx* ctx) {
+  if (ctx->oz_attr) return NLS_OK;
+  CUDA_TRY(cudaFuncSetAttribute(oz::gemm_kernel_i8<oz::IMAGE, oz::EpiProject>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                oz::SMEM_BYTES));
+  ctx->oz_attr = true;
+  return NLS_OK;
+}
+
+// Digit planes of the basis [Re Q^T ; Im Q^T] (bs.bt), once per sweep call.
+static int oz_prep_basis(nls_ctx* ctx, const MapGeom& g, const BasisScratch& bs, int cols, OzBasis* out) {
+  NLS_TRY(oz_attr(ctx));
+  const int n_tiles = (cols + oz::TN / 2 - 1) / (oz::TN / 2);
+  const int nks = 2 * g.Dp / oz::KS;
+  const int padded = n_tiles * (oz::TN / 2);
+  NLS_TRY(ensure(ctx, ctx->oz_b, (size_t)n_tiles * nks * oz::B_STAGE));
+  NLS_TRY(ensure(ctx, ctx->oz_small, (size_t)padded * 16));
+  double* colscale = (double*)ctx->oz_small.p;
+  int* ex = (int*)(colscale + padded);
+  const int eA = oz::scale_exponent(1.0 / sqrt((double)g.D));  // |cos| D^-1/2, |sin| D^-1/2 <= D^-1/2
+  ProfScope scope(ctx, NLS_PROF_PROJECT);
+  oz::basis_exponent_kernel<<<(padded + 7) / 8, 256, 0, ctx->stream>>>(bs.bt, g.Np, g.Dp, g.D, cols, padded, eA, ex, colscale);
+  NLS_TRY(check_launch(ctx, "oz::basis_exponent_kernel"));
+  oz::slice_basis_kernel<oz::IMAGE><<<grid_for((long long)n_tiles * nks * oz::TN * 2), 256, 0, ctx->stream>>>(
+      bs.bt, g.Np, g.Dp, g.D, cols, ex, nks, n_tiles, (int8_t*)ctx->oz_b.p);
+  NLS_TRY(check_launch(ctx, "oz::slice_basis_kernel"));
+  out->planes = (const int8_t*)ctx->oz_b.p;
+  out->colscale = colscale;
+  out->n_tiles = n_tiles;
+  out->nks = nks;
+  out->eA = eA;
+  return NLS_OK;
+}
+
+// P = Re(T v), U = |T|^2 / c for the first `cols` columns of T = phi Q, phi = the planar chunk in ctx->psi.
+static int oz_project_chunk(nls_ctx* ctx, const MapGeom& g, const BasisScratch& bs, const OzBasis& ob, int rows, int cols,
+                            double inv_c, double* P, double* U) {
+  const int row_blocks = (rows + oz::TM - 1) / oz::TM;
+  NLS_TRY(ensure(ctx, ctx->oz_a, (size_t)((ctx->chunk_rows + oz::TM - 1) / oz::TM) * ob.nks * oz::A_STAGE));
+  ProfScope scope(ctx, NLS_PROF_PROJECT);
+  oz::slice_rows_kernel<oz::IMAGE><<<grid_for((long long)row_blocks * ob.nks * oz::TM * 2), 256, 0, ctx->stream>>>(
+      (const double*)ctx->psi.p, 2LL * g.Dp, rows, g.D, g.Dp, ldexp(1.0, oz::FRAC_BITS - ob.eA), ob.nks, row_blocks,
+      (int8_t*)ctx->oz_a.p);
+  NLS_TRY(check_launch(ctx, "oz::slice_rows_kernel"));
+  oz::GemmParams gp{(const int8_t*)ctx->oz_a.p, ob.planes, ob.nks, row_blocks, ob.n_tiles};
+  oz::EpiProject::Params ep{rows, cols, ob.colscale, bs.bias_r, bs.bias_i, bs.v_r, bs.v_i, inv_c, P, U, g.ldp};
+  const int grid = (int)std::min<long long>((long long)row_blocks * ob.n_tiles, ctx->sm_count);
+  oz::gemm_kernel_i8<oz::IMAGE, oz::EpiProject><<<grid, oz::THREADS, oz::SMEM_BYTES, ctx->stream>>>(gp, ep);
+  return check_launch(ctx, "oz::gemm_kernel_i8");
+}
+
+// ---------------------------------------------------------------------------------------------
 // Stage 4a + 4b
 // ---------------------------------------------------------------------------------------------
 extern "C" int nls_primal_loo_sweep(nls_ctx* ctx, const double* X, const double* y, const double* s, int64_t n, int d,
@@ -1151,6 +1226,10 @@ extern "C" int nls_primal_loo_sweep(nls_ctx* ctx, const double* X, const double*
   CUDA_TRY(cudaMemsetAsync(sums_out, 0, (size_t)3 * G * 8, ctx->stream));
   double* P = (double*)ctx->pu.p;
   double* U = P + cap * g.ldp;
+  // The projection T = phi Q runs on the INT8 tensor cores (Ozaki scheme, csrc/ozaki.cuh) unless the context says DMMA.
+  const bool use_oz = ctx->gemm_core == 1 && 2 * g.Dp <= oz::MAX_K && tail_split(g.m) > 0;
+  OzBasis oz{};
+  if (use_oz) NLS_TRY(oz_prep_basis(ctx, g, bs, tail_split(g.m), &oz));
   for (int64_t i0 = 0; i0 < n; i0 += cap) {
     const int rows = (int)std::min<int64_t>(cap, n - i0);
     const int mtiles = (rows + BM - 1) / BM;
@@ -1169,6 +1248,9 @@ extern "C" int nls_primal_loo_sweep(nls_ctx* ctx, const double* X, const double*
     }
     NLS_TRY(feature_chunk(ctx, g, X + i0 * d, shift, rows, FM_PLANAR, (double*)ctx->psi.p, 2LL * g.Dp, g.Dp, nullptr,
                           fused_spill ? &dots : nullptr));
+    if (use_oz) {
+      NLS_TRY(oz_project_chunk(ctx, g, bs, oz, rows, full_cols, inv_c, P, U));
+    } else {
     OpProject::Params pp;
     pp.A = psi_operand(ctx, g, rows);
     pp.B = basis_operand(g, bs.bt);
@@ -1185,6 +1267,7 @@ extern "C" int nls_primal_loo_sweep(nls_ctx* ctx, const double* X, const double*
     pp.m = full_cols;
     NLS_TRY((launch_gemm<MODE_COMPLEX, OpProject>(ctx, pp, dim3((full_cols + BN - 1) / BN, mtiles), rows, 2 * g.Np,
                                                    NLS_PROF_PROJECT, "project")));
+    }
     if (fused_spill) {
       ProfScope scope(ctx, NLS_PROF_PROJECT);
       project_spill_kernel<<<(rows + 255) / 256, 256, 0, ctx->stream>>>(dots.out, (g.D + BN - 1) / BN, cap, rows, full_cols,

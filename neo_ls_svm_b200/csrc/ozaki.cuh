@@ -40,6 +40,8 @@ constexpr int SMEM_BYTES = 1024 + NSTAGE * STAGE_BYTES;
 constexpr int THREADS = 320;       // producer warp, MMA warp, 8 epilogue warps
 constexpr int FRAC_BITS = 7 * S;   // 49
 constexpr uint32_t TMEM_COLS = 512;
+constexpr int IMAGE = 6;           // tile image the product uses: canonical K-major SWIZZLE_32B (see tile_off)
+constexpr int MAX_K = 65536;       // INT32 accumulators: (t + 1) 64^2 K < 2^31 for every level t <= 6
 
 // ---- tile images ----------------------------------------------------------------------------------
 // Byte offset of the 16-byte chunk c (0/1) of row r inside a [rows x 32 B] tile.

@@ -391,3 +391,33 @@ def test_gram_from_host_rows_equals_device_rows(golden, gpu):
     fit = _primal.primal_fit(None, None, None, dev(shift), dev(W), classifier, ctx=ctx, host_rows=(pin(X), pin(y_), pin(s)))
     assert fit.opt == int(g["opt"])
     assert rel_err(fit.beta_eig.cpu().numpy(), g["beta"]) < TOL_FIT
+
+
+@pytest.mark.parametrize("name", ["c1", "clf_small", "c3_small"])
+def test_int8_projection_core_matches_dmma(name, golden, gpu):
+    """The projection T = φQ on the INT8 tensor cores (tcgen05 kind::i8, Ozaki scheme: 7 digit planes, 28 exact plane
+    products, FP64 recombination; the default) against the FP64 DMMA core: same γ index, LOO curve / residuals / std far
+    inside the 1e-9 bar, and both against the reference's golden outputs."""
+    from neo_ls_svm_b200 import _lib
+
+    _, dev, _primal, _ = gpu
+    g = golden(name)
+    X, y_, s, Xt, classifier, shift, W = _case(name, g)
+    out = {}
+    for core in ("dmma", "ozaki"):
+        ctx = _lib.Context(0)
+        ctx.set_gemm_core(core)
+        ctx.set_chunk_rows(1024)  # several chunks with a ragged tail
+        n0 = ctx.launch_count()
+        out[core] = fit = _primal.primal_fit(dev(X), dev(y_), dev(s), dev(shift), dev(W), classifier, ctx=ctx)
+        out[core + "_launches"] = ctx.launch_count() - n0
+        assert fit.opt == int(g["opt"])
+        assert rel_err(fit.loo_errors, g["loo_errors"]) < TOL_FIT
+        assert rel_err(fit.rows["loo_residuals"].cpu().numpy(), g["loo_residuals"]) < TOL_FIT
+        assert_elementwise(fit.rows["loo_residuals"].cpu().numpy(), g["loo_residuals"])
+        assert rel_err(fit.rows["loo_std"].cpu().numpy(), g["loo_std"]) < TOL_FIT
+    a, b = out["dmma"], out["ozaki"]
+    assert out["ozaki_launches"] > out["dmma_launches"], "the INT8 core adds its slicing kernels: it must have run"
+    assert rel_err(b.loo_errors, a.loo_errors) < 1e-11
+    assert rel_err(b.rows["loo_residuals"].cpu().numpy(), a.rows["loo_residuals"].cpu().numpy()) < 1e-10
+    assert rel_err(b.rows["loo_std"].cpu().numpy(), a.rows["loo_std"].cpu().numpy()) < 1e-11
