@@ -112,7 +112,7 @@ struct nls_ctx {
   DevBuf d_xpad, d_xq, d_norm, d_fm, d_sq, d_sqt, d_g1, d_ab, d_ra, d_vec, d_ng, d_kq, d_btp;
   // INT8 (Ozaki) GEMM core of the projection (csrc/ozaki.cuh): digit planes of the chunk / of the basis, per-column
   // exponents and recombination scales
-  DevBuf oz_a, oz_b, oz_small;
+  DevBuf oz_a, oz_b, oz_g, oz_small;
   int gemm_core = 1;      // 1: projection on tcgen05 kind::i8 (Ozaki scheme, default), 0: everything on DMMA
   bool oz_attr = false;   // dynamic shared memory opt-in of the INT8 kernels done on this device
   int dual_n = 0;
@@ -141,6 +141,8 @@ static int ensure(nls_ctx* ctx, DevBuf& b, size_t bytes) {
   CUDA_TRY(cudaMemsetAsync(b.p, 0, bytes, ctx->stream));
   return NLS_OK;
 }
+
+static int oz_attr(nls_ctx* ctx);  // dynamic shared memory opt-in of the INT8 GEMM kernels (defined with the projection)
 
 static inline long long round_up(long long x, long long q) { return (x + q - 1) / q * q; }
 static inline int grid_for(long long total, int block = 256, int cap = 148 * 16) {
@@ -387,7 +389,7 @@ extern "C" int nls_ctx_destroy(nls_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->xc, &ctx->wt, &ctx->psi, &ctx->psiT, &ctx->pu, &ctx->bt, &ctx->rt, &ctx->small,
                     &ctx->part, &ctx->gram_ws, &ctx->border, &ctx->rowtmp, &ctx->solver_ws, &ctx->solver_mat,
                     &ctx->jac_mat, &ctx->jac_small, &ctx->bs_part, &ctx->bs_keys, &ctx->dotpart, &ctx->d_xpad, &ctx->d_xq, &ctx->d_norm, &ctx->d_fm, &ctx->d_sq, &ctx->d_sqt, &ctx->d_g1,
-                    &ctx->d_ab, &ctx->d_ra, &ctx->d_vec, &ctx->d_ng, &ctx->d_kq, &ctx->d_btp, &ctx->oz_a, &ctx->oz_b, &ctx->oz_small};
+                    &ctx->d_ab, &ctx->d_ra, &ctx->d_vec, &ctx->d_ng, &ctx->d_kq, &ctx->d_btp, &ctx->oz_a, &ctx->oz_b, &ctx->oz_g, &ctx->oz_small};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   {
@@ -559,7 +561,22 @@ static int gram_impl(nls_ctx* ctx, const double* X, const double* y, const doubl
   const int tiles_m = (D + BM - 1) / BM, tiles_n = (D + BN - 1) / BN;
   int n_tiles = 0;
   for (int kb = 0; kb < tiles_m; ++kb) n_tiles += std::max(0, tiles_n - 2 * kb);
-  const int splits = std::max(1, ctx->sm_count / n_tiles);
+  // INT8 (Ozaki) core: 128-feature row blocks x 32-feature column tiles, upper triangle only; the chunk's rows are K.
+  const bool use_oz = ctx->gemm_core == 1;
+  const int oz_rb = (D + oz::TM - 1) / oz::TM, oz_nt = (D + oz::TN / 2 - 1) / (oz::TN / 2);
+  int oz_tiles = 0;
+  for (int kb = 0; kb < oz_rb; ++kb) oz_tiles += oz_nt - 4 * kb;
+  // K (= 2 x the chunk's rows) is split so that one work item stays inside the INT32 accumulators (oz::MAX_K) and,
+  // for small D, so that every SM has a work item.
+  const int oz_min_splits = (int)((2 * round_up(ctx->chunk_rows, oz::KS) + oz::MAX_K - 1) / oz::MAX_K);
+  const int splits = use_oz ? std::max(oz_min_splits, ctx->sm_count / oz_tiles) : std::max(1, ctx->sm_count / n_tiles);
+  if (use_oz) {
+    NLS_TRY(oz_attr(ctx));
+    const size_t nks2_max = (size_t)2 * (round_up(ctx->chunk_rows, oz::KS) / oz::KS);
+    NLS_TRY(ensure(ctx, ctx->oz_a, (size_t)oz_rb * nks2_max * oz::A_STAGE));
+    NLS_TRY(ensure(ctx, ctx->oz_g, (size_t)oz_nt * nks2_max * oz::B_STAGE));
+    NLS_TRY(ensure(ctx, ctx->oz_small, 64));
+  }
   const size_t ws_bytes = (size_t)splits * 2 * D * D * 8;
   NLS_TRY(ensure(ctx, ctx->gram_ws, ws_bytes));
   NLS_TRY(ensure(ctx, ctx->border, (size_t)(4 * D + 2) * 8));
@@ -575,6 +592,23 @@ static int gram_impl(nls_ctx* ctx, const double* X, const double* y, const doubl
       arrived = std::min<int64_t>(n, (arrived / up->group_rows + 1) * up->group_rows);
     }
     NLS_TRY(feature_chunk(ctx, g, X + i0 * d, shift, rows, FM_TRANSPOSED, (double*)ctx->psiT.p, ldT, g.DpT, s + i0));
+    if (use_oz) {
+      ProfScope scope(ctx, NLS_PROF_GRAM);
+      double* sc = (double*)ctx->oz_small.p;
+      oz::gram_scale_kernel<<<1, 1024, 0, ctx->stream>>>(s + i0, rows, 1.0 / sqrt((double)D), sc);
+      NLS_TRY(check_launch(ctx, "oz::gram_scale_kernel"));
+      const int nksR = (int)(round_up(rows, oz::KS) / oz::KS);
+      oz::slice_gram_kernel<oz::IMAGE><<<grid_for((long long)oz_rb * 2 * nksR * oz::TM * 2), 256, 0, ctx->stream>>>(
+          (const double*)ctx->psiT.p, ldT, g.DpT, D, rows, sc, nksR, oz_rb, oz_nt, (int8_t*)ctx->oz_a.p, (int8_t*)ctx->oz_g.p);
+      NLS_TRY(check_launch(ctx, "oz::slice_gram_kernel"));
+      const int ks_per_split = (2 * nksR + splits - 1) / splits;
+      oz::GemmParams gp{(const int8_t*)ctx->oz_a.p, (const int8_t*)ctx->oz_g.p, 2 * nksR, oz_rb, oz_nt, 1, oz_tiles,
+                        (2 * nksR + ks_per_split - 1) / ks_per_split, ks_per_split};
+      oz::EpiGram::Params ep{D, sc + 1, (double*)ctx->gram_ws.p};
+      const int grid = (int)std::min<long long>((long long)gp.tiles * gp.splits, ctx->sm_count);
+      oz::gemm_kernel_i8<oz::IMAGE, oz::EpiGram><<<grid, oz::THREADS, oz::SMEM_BYTES, ctx->stream>>>(gp, ep);
+      NLS_TRY(check_launch(ctx, "oz::gemm_kernel_i8<EpiGram>"));
+    } else {
     OpGram::Params p;
     p.A = Operand{(const double*)ctx->psiT.p, ldT, 2 * g.DpT, rows, g.DpT, 0};
     p.B = p.A;
@@ -586,6 +620,7 @@ static int gram_impl(nls_ctx* ctx, const double* X, const double* y, const doubl
     p.ws = (double*)ctx->gram_ws.p;
     NLS_TRY((launch_gemm<MODE_COMPLEX, OpGram>(ctx, p, dim3(n_tiles, splits), 2 * g.DpT, 2 * g.DpT, NLS_PROF_GRAM,
                                                 "gram")));
+    }
     gram_border_kernel<<<2 * D + 1, 256, 0, ctx->stream>>>((const double*)ctx->psiT.p, ldT, D, g.DpT, rows, s + i0,
                                                            y + i0, border, scal);
     NLS_TRY(check_launch(ctx, "gram_border_kernel"));
@@ -1153,6 +1188,8 @@ static int oz_attr(nls_ctx* ctx) {
   if (ctx->oz_attr) return NLS_OK;
   CUDA_TRY(cudaFuncSetAttribute(oz::gemm_kernel_i8<oz::IMAGE, oz::EpiProject>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 oz::SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(oz::gemm_kernel_i8<oz::IMAGE, oz::EpiGram>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                oz::SMEM_BYTES));
   ctx->oz_attr = true;
   return NLS_OK;
 }
@@ -1192,7 +1229,7 @@ static int oz_project_chunk(nls_ctx* ctx, const MapGeom& g, const BasisScratch& 
       (const double*)ctx->psi.p, 2LL * g.Dp, rows, g.D, g.Dp, ldexp(1.0, oz::FRAC_BITS - ob.eA), ob.nks, row_blocks,
       (int8_t*)ctx->oz_a.p);
   NLS_TRY(check_launch(ctx, "oz::slice_rows_kernel"));
-  oz::GemmParams gp{(const int8_t*)ctx->oz_a.p, ob.planes, ob.nks, row_blocks, ob.n_tiles};
+  oz::GemmParams gp{(const int8_t*)ctx->oz_a.p, ob.planes, ob.nks, row_blocks, ob.n_tiles, 0, row_blocks * ob.n_tiles, 1, ob.nks};
   oz::EpiProject::Params ep{rows, cols, ob.colscale, bs.bias_r, bs.bias_i, bs.v_r, bs.v_i, inv_c, P, U, g.ldp};
   const int grid = (int)std::min<long long>((long long)row_blocks * ob.n_tiles, ctx->sm_count);
   oz::gemm_kernel_i8<oz::IMAGE, oz::EpiProject><<<grid, oz::THREADS, oz::SMEM_BYTES, ctx->stream>>>(gp, ep);

@@ -1,12 +1,13 @@
 // ozaki.cuh — FP64-accurate GEMM on the INT8 tensor cores (tcgen05.mma kind::i8, TMEM accumulators) by the Ozaki scheme.
 //
-// sm_100a has no FP64 kind on tcgen05; DMMA tops out at 128 flop/cycle/SM.  The eigenbasis projection T = phi Q
-// (reference: _neo_ls_svm.py:134, :137 — 44 % of the C3 fit) has bounded operands (|phi| <= D^-1/2, Q unitary), so
-// each operand row is scaled by a power of two to |x| <= 1/2, rounded ONCE to 49 fractional bits and cut exactly
-// into S = 7 signed base-128 digits x = 2^e sum_p d_p 128^-(p+1).  A digit-plane product A_p B_q^T is an exact
-// INT8 x INT8 -> INT32 GEMM; the S(S+1)/2 = 28 products with p + q <= 6 go into 7 TMEM accumulators (one per
-// level t = p + q, 7 x 64 = 448 of the 512 columns) and are recombined in FP64 in the epilogue, smallest level
-// first.  Dropped levels (p + q >= 7) are below 2^-47 of max|a| max|b| per term.
+// sm_100a has no FP64 kind on tcgen05; DMMA tops out at 128 flop/cycle/SM.  The Gram (reference: _neo_ls_svm.py:112-114)
+// and the eigenbasis projection T = phi Q (:134, :137) — 70 % of the C3 fit — have bounded operands (|phi| <= D^-1/2,
+// Q unitary), so each operand row is scaled by a power of two to |x| <= 0.495, rounded ONCE to 56 fractional bits
+// (more than FP64 carries) and cut exactly into S = 7 balanced base-256 digits x = 2^e sum_p d_p 256^-(p+1),
+// d_p in [-128, 127].  A digit-plane product A_p B_q^T is an exact INT8 x INT8 -> INT32 GEMM (K <= 16384 per work
+// item keeps every level inside INT32); the S(S+1)/2 = 28 products with p + q <= 6 go into 7 TMEM accumulators (one
+// per level t = p + q, 7 x 64 = 448 of the 512 columns) and are recombined in FP64 in the epilogue, smallest level
+// first.  Dropped levels (p + q >= 7) are below 2^-58 of max|a| max|b| per term.
 //
 // Data path (everything is laid out by our own slicing kernels, so no tensor maps are needed):
 //   * planes live in global memory TILE-MAJOR: [row block][k step][plane][rows x 32 bytes], each [rows x 32 B] tile
@@ -14,7 +15,9 @@
 //     tiles of 128 rows + 7 B tiles of 64 rows = 42 KB) is two contiguous blocks, fetched with two 1-D
 //     cp.async.bulk copies that complete on the stage's mbarrier.
 //   * persistent CTAs (one per SM), warp-specialised: warp 0 = bulk-copy producer (one lane), warp 1 = MMA issuer
-//     (one lane, 28 tcgen05.mma per stage, tcgen05.commit releases the stage), warps 2-9 = epilogue (tcgen05.ld,
+//     (one lane, 28 tcgen05.mma per stage, tcgen05.commit releases the stage; its descriptors must stay in UNIFORM
+//     registers — a 64-bit division feeding the loop bounds once turned every MMA into an ELECT + 4 R2UR.BROADCAST
+//     sequence and cost 25 % of the rate, so work indices are 32-bit), warps 2-9 = epilogue (tcgen05.ld,
 //     FP64 recombination, fused epilogue functor).  5 stages in flight; the accumulators are handed back to the
 //     MMA warp as soon as they are drained into registers, so the epilogue math and stores of tile i overlap the
 //     mainloop of tile i + 1.
@@ -26,7 +29,7 @@
 namespace nls {
 namespace oz {
 
-constexpr int S = 7;               // digit planes per operand (7 bits each)
+constexpr int S = 7;               // digit planes per operand (signed 8-bit digits)
 constexpr int TM = 128;            // rows of A per tile
 constexpr int TN = 64;             // rows of B per tile (32 complex columns: 32 "re" rows then 32 "im" rows)
 constexpr int KS = 32;             // k elements (bytes) per pipeline stage = one tcgen05.mma kind::i8 K step
@@ -38,10 +41,11 @@ constexpr int B_STAGE = S * B_TILE;
 constexpr int STAGE_BYTES = A_STAGE + B_STAGE;  // 43008
 constexpr int SMEM_BYTES = 1024 + NSTAGE * STAGE_BYTES;
 constexpr int THREADS = 320;       // producer warp, MMA warp, 8 epilogue warps
-constexpr int FRAC_BITS = 7 * S;   // 49
+constexpr int RADIX_BITS = 8;      // balanced base-256 digits
+constexpr int FRAC_BITS = RADIX_BITS * S;  // 56: more than the 53 bits of the FP64 operands
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int IMAGE = 6;           // tile image the product uses: canonical K-major SWIZZLE_32B (see tile_off)
-constexpr int MAX_K = 65536;       // INT32 accumulators: (t + 1) 64^2 K < 2^31 for every level t <= 6
+constexpr int MAX_K = 16384;       // INT32 accumulators: (t + 1) 128^2 K < 2^31 for every level t <= 6 (K per work item)
 
 // ---- tile images ----------------------------------------------------------------------------------
 // Byte offset of the 16-byte chunk c (0/1) of row r inside a [rows x 32 B] tile.
@@ -67,29 +71,40 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
 constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 
 // ---- digit extraction -----------------------------------------------------------------------------
-// x 2^-e in [-1/2, 1/2]  ->  V = rint(x 2^(49 - e))  =  sum_p d_p 128^(6 - p),  d_p in [-64, 63] (d_0 up to 64).
-// `scale` = 2^(49 - e).  The rounding happens once, in the FMA against 1.5 2^52 (round to nearest even).
+// x 2^-e in [-0.495, 0.495]  ->  V = rint(x 2^(56 - e))  =  sum_p d_p 256^(6 - p)  with BALANCED base-256 digits
+// d_p in [-128, 127] (every plane is a signed int8).  With W = V + 0x80..80 (seven bytes), digit p is byte (6 - p)
+// of W with its top bit flipped.  `scale` = 2^(56 - e); the product x * scale is exact, the conversion rounds once.
 __host__ __device__ __forceinline__ long long quantise(double x, double scale) {
 #ifdef __CUDA_ARCH__
-  const double t = fma(x, scale, 6755399441055744.0);
-  return __double_as_longlong(t) - 0x4338000000000000LL;
+  return __double2ll_rn(x * scale);
 #else
-  return (long long)__builtin_rint(x * scale);
+  return (long long)__builtin_llrint(x * scale);
 #endif
 }
-constexpr long long DIGIT_BIAS = 64LL * (1 + 128LL + 128LL * 128 + 128LL * 128 * 128 + 128LL * 128 * 128 * 128 +
-                                         128LL * 128 * 128 * 128 * 128 + 128LL * 128 * 128 * 128 * 128 * 128);
-__host__ __device__ __forceinline__ int digit(long long v_biased, int p) {  // p = 0 is the leading digit
-  const long long u = v_biased >> (7 * (S - 1 - p));
-  return (int)(p == 0 ? u : (u & 127)) - 64;
+constexpr long long DIGIT_BIAS = 0x0080808080808080LL;
+// all seven digits of one value as bytes (byte 6 - p = digit p, two's complement int8)
+__host__ __device__ __forceinline__ unsigned long long digit_bytes(long long v) {
+  return (unsigned long long)(v + DIGIT_BIAS) ^ (unsigned long long)DIGIT_BIAS;
+}
+__host__ __device__ __forceinline__ int digit(unsigned long long bytes, int p) {  // p = 0 is the leading digit
+  return (int)(signed char)((bytes >> (8 * (S - 1 - p))) & 0xff);
+}
+// weight of level t = p + q in the recombination: 256^-(t + 2)
+__host__ __device__ __forceinline__ double level_weight(int t) {
+#ifdef __CUDA_ARCH__
+  return __longlong_as_double((long long)(1023 - RADIX_BITS * (t + 2)) << 52);
+#else
+  return __builtin_ldexp(1.0, -RADIX_BITS * (t + 2));
+#endif
 }
 
-// Power-of-two exponent e with |x| 2^-e <= 1/2 for all |x| <= amax (0 when amax == 0).
+// Power-of-two exponent e with |x| 2^-e <= 0.495 for all |x| <= amax (0 when amax == 0): the balanced digits reach
+// 127/255 (256^7 - 1)/256^7 = 0.498 at most.
 __host__ __device__ __forceinline__ int scale_exponent(double amax) {
   if (!(amax > 0.0)) return 0;
   int ex;
   const double f = frexp(amax, &ex);  // amax = f 2^ex, f in [1/2, 1)
-  return f == 0.5 ? ex : ex + 1;
+  return f <= 0.99 ? ex + 1 : ex + 2;
 }
 
 // ---- slicing kernels ------------------------------------------------------------------------------
@@ -121,10 +136,10 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
         double2 v = make_double2(0.0, 0.0);
         if (col < D) v = *reinterpret_cast<const double2*>(src + j);
         if (col + 1 >= D) v.y = 0.0;
-        const long long q0 = quantise(v.x, scale) + DIGIT_BIAS, q1 = quantise(v.y, scale) + DIGIT_BIAS;
+        const unsigned long long q0 = digit_bytes(quantise(v.x, scale)), q1 = digit_bytes(quantise(v.y, scale));
 #pragma unroll
         for (int p = 0; p < S; ++p) {
-          const uint32_t b0 = (uint32_t)(digit(q0, p) & 0xff), b1 = (uint32_t)(digit(q1, p) & 0xff);
+          const uint32_t b0 = (uint32_t)(q0 >> (8 * (S - 1 - p))) & 0xff, b1 = (uint32_t)(q1 >> (8 * (S - 1 - p))) & 0xff;
           w[p][j >> 2] |= (b0 | (b1 << 8)) << (16 * ((j >> 1) & 1));
         }
       }
@@ -186,14 +201,94 @@ __global__ void __launch_bounds__(256) slice_basis_kernel(const double* __restri
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const double v = col0 + i < D ? src[i] : 0.0;
-        const long long q = quantise(v, scale) + DIGIT_BIAS;
+        const unsigned long long q = digit_bytes(quantise(v, scale));
 #pragma unroll
-        for (int p = 0; p < S; ++p) w[p][i >> 2] |= (uint32_t)(digit(q, p) & 0xff) << (8 * (i & 3));
+        for (int p = 0; p < S; ++p) w[p][i >> 2] |= ((uint32_t)(q >> (8 * (S - 1 - p))) & 0xff) << (8 * (i & 3));
       }
     }
     int8_t* dst = out + (blk * S) * B_TILE + tile_off<LAYOUT>(r, c);
 #pragma unroll
     for (int p = 0; p < S; ++p) *reinterpret_cast<uint4*>(dst + (long long)p * B_TILE) = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
+  }
+}
+
+// Gram operands from the weighted transposed feature chunk psiT (rows [0, DpT) = s_i cos, rows [DpT, 2 DpT) = s_i sin,
+// pitch ldT, `rows` valid entries per row).  With k = the chunk's row index i, K = 2 Rp (Rp = rows rounded up to 32):
+//   A side, feature f:            [ C_f(i) | S_f(i) ]
+//   B side, re row of feature l:  [ C_l(i) | S_l(i) ]         im row:  [ -S_l(i) | C_l(i) ]
+// so that R = C^T C + S^T S = Re A and I = S^T C - C^T S = Im A, the convention of OpGram.  One pass over psiT writes
+// both operand images.  scale_dev[0] = 2^(56 - e) with e the exponent of this chunk's largest |entry| bound.
+__global__ void __launch_bounds__(1024) gram_scale_kernel(const double* __restrict__ s, int rows, double dinv, double* __restrict__ out) {
+  __shared__ double red[32];
+  double amax = 0.0;
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) amax = fmax(amax, fabs(s[i]));
+#pragma unroll
+  for (int o = 16; o; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) amax = fmax(amax, red[w]);
+    const int e = scale_exponent(amax * dinv * (1.0 + 0x1p-50));  // fl(s cos / sqrt(D)) <= s_max D^-1/2 (1 + ulp)
+    out[0] = ldexp(1.0, FRAC_BITS - e);
+    out[1] = ldexp(1.0, 2 * e);
+  }
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(256) slice_gram_kernel(const double* __restrict__ psiT, long long ldT, int DpT, int D, int rows,
+                                                         const double* __restrict__ scale_dev, int nksR, int row_blocks,
+                                                         int n_tiles, int8_t* __restrict__ GA, int8_t* __restrict__ GB) {
+  const double scale = scale_dev[0];
+  const long long items = (long long)row_blocks * 2 * nksR * TM * 2;
+  const int nks2 = 2 * nksR;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(it & 1);
+    const int r = (int)((it >> 1) & (TM - 1));
+    long long rest = it >> 8;
+    const int ks = (int)(rest % nksR);
+    rest /= nksR;
+    const int h = (int)(rest & 1);
+    const int kb = (int)(rest >> 1);
+    const int f = kb * TM + r;
+    const int i0 = ks * KS + c * 16;
+    uint32_t w[S][4], wn[S][4];
+#pragma unroll
+    for (int p = 0; p < S; ++p)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[p][j] = wn[p][j] = 0;
+    if (f < D) {
+      const double* src = psiT + ((long long)h * DpT + f) * ldT + i0;
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        double2 v = make_double2(0.0, 0.0);
+        if (i0 + j < rows) v = *reinterpret_cast<const double2*>(src + j);
+        if (i0 + j + 1 >= rows) v.y = 0.0;
+        const long long v0 = quantise(v.x, scale), v1 = quantise(v.y, scale);
+        const unsigned long long q0 = digit_bytes(v0), q1 = digit_bytes(v1), n0 = digit_bytes(-v0), n1 = digit_bytes(-v1);
+#pragma unroll
+        for (int p = 0; p < S; ++p) {
+          const int sh = 8 * (S - 1 - p);
+          w[p][j >> 2] |= (((uint32_t)(q0 >> sh) & 0xff) | (((uint32_t)(q1 >> sh) & 0xff) << 8)) << (16 * ((j >> 1) & 1));
+          if (h) wn[p][j >> 2] |= (((uint32_t)(n0 >> sh) & 0xff) | (((uint32_t)(n1 >> sh) & 0xff) << 8)) << (16 * ((j >> 1) & 1));
+        }
+      }
+    }
+    int8_t* dst = GA + ((long long)kb * nks2 + h * nksR + ks) * S * A_TILE + tile_off<LAYOUT>(r, c);
+#pragma unroll
+    for (int p = 0; p < S; ++p) *reinterpret_cast<uint4*>(dst + (long long)p * A_TILE) = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
+    const int lb = f >> 5, r32 = f & 31;
+    if (lb < n_tiles) {
+      // re row: same K position and digits as the A side
+      dst = GB + ((long long)lb * nks2 + h * nksR + ks) * S * B_TILE + tile_off<LAYOUT>(r32, c);
+#pragma unroll
+      for (int p = 0; p < S; ++p) *reinterpret_cast<uint4*>(dst + (long long)p * B_TILE) = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
+      // im row: C goes to the second K half as it is, S to the first half negated
+      dst = GB + ((long long)lb * nks2 + (h ? 0 : nksR) + ks) * S * B_TILE + tile_off<LAYOUT>(32 + r32, c);
+#pragma unroll
+      for (int p = 0; p < S; ++p)
+        *reinterpret_cast<uint4*>(dst + (long long)p * B_TILE) =
+            h ? make_uint4(wn[p][0], wn[p][1], wn[p][2], wn[p][3]) : make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
+    }
   }
 }
 
@@ -228,7 +323,37 @@ struct GemmParams {
   const int8_t* A;   // [row_blocks][nks][S][128 x 32 B]
   const int8_t* B;   // [n_tiles][nks][S][64 x 32 B]
   int nks, row_blocks, n_tiles;
+  int upper;         // 1: only the tiles that touch the upper triangle (nb >= 4 rb): Hermitian Gram; 0: all of them
+  int tiles;         // tiles per K split (row_blocks * n_tiles, or the upper-triangular count)
+  int splits;        // the K range is cut into `splits` work items per tile (each with its own epilogue slot) ...
+  int ks_per_split;  // ... of this many k steps
 };
+
+struct Work {
+  int rb, nb, ks0, ks1, split;
+};
+
+// Work items run split-major, row block next, column tile fastest: CTAs that run side by side share operand blocks in L2.
+__device__ __forceinline__ Work get_work(const GemmParams& g, int w) {
+  Work k;
+  k.split = w / g.tiles;
+  int idx = w - k.split * g.tiles;
+  if (!g.upper) {
+    k.rb = idx / g.n_tiles;
+    k.nb = idx % g.n_tiles;
+  } else {
+    int kb = 0;
+    while (idx >= g.n_tiles - 4 * kb) {
+      idx -= g.n_tiles - 4 * kb;
+      ++kb;
+    }
+    k.rb = kb;
+    k.nb = 4 * kb + idx;
+  }
+  k.ks0 = k.split * g.ks_per_split;
+  k.ks1 = min(g.nks, k.ks0 + g.ks_per_split);
+  return k;
+}
 
 // Epilogue functors receive, per thread, one row and 16 consecutive complex columns: sr/si = the recombined real /
 // imaginary sums BEFORE the column scale 2^(eA + eB_j).
@@ -245,7 +370,8 @@ struct EpiProject {  // P = Re(T v), U = |T|^2 / c   (what OpProject writes; ref
     double* U;
     long long ld;
   };
-  static __device__ __forceinline__ void apply(const Params& p, long long row, int col0, const double (&sr)[16], const double (&si)[16]) {
+  static __device__ __forceinline__ void apply(const Params& p, const Work&, long long row, int col0, const double (&sr)[16],
+                                               const double (&si)[16]) {
     if (row >= p.n_rows) return;
     double pv[16], uv[16];
 #pragma unroll
@@ -285,7 +411,8 @@ struct EpiStore {  // raw T planes (probe / tests): Tr[row][col] = sr * colscale
     double* Ti;
     long long ld;
   };
-  static __device__ __forceinline__ void apply(const Params& p, long long row, int col0, const double (&sr)[16], const double (&si)[16]) {
+  static __device__ __forceinline__ void apply(const Params& p, const Work&, long long row, int col0, const double (&sr)[16],
+                                               const double (&si)[16]) {
     if (row >= p.n_rows) return;
 #pragma unroll
     for (int j = 0; j < 16; ++j)
@@ -293,6 +420,33 @@ struct EpiStore {  // raw T planes (probe / tests): Tr[row][col] = sr * colscale
         p.Tr[row * p.ld + col0 + j] = sr[j] * p.colscale[col0 + j];
         p.Ti[row * p.ld + col0 + j] = si[j] * p.colscale[col0 + j];
       }
+  }
+};
+
+// Stage 2 on the INT8 core: rows = features k (A side), columns = features l (B side), K = the chunk's rows.  Every
+// (split, tile) work item owns its part of the partial-sum workspace [split][2][D][D] and accumulates into it chunk
+// after chunk in a fixed order, exactly like OpGram (upper triangle only; gram_assemble_kernel mirrors it).
+//   reference: _neo_ls_svm.py:112-114.
+struct EpiGram {
+  struct Params {
+    int D;
+    const double* scale2;  // device scalar 2^(2 e) of this chunk (e = exponent of max_i s_i D^-1/2)
+    double* ws;
+  };
+  static __device__ __forceinline__ void apply(const Params& p, const Work& wk, long long row, int col0, const double (&sr)[16],
+                                               const double (&si)[16]) {
+    if (row >= p.D) return;
+    const double cs = *p.scale2;
+    double* wr = p.ws + (long long)wk.split * 2 * p.D * p.D + row * p.D;
+    double* wi = wr + (long long)p.D * p.D;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int l = col0 + j;
+      if (l < p.D && l >= row) {
+        wr[l] += sr[j] * cs;
+        wi[l] += si[j] * cs;
+      }
+    }
   }
 };
 
@@ -321,17 +475,16 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel_i8(GemmParams g, typen
   tc_fence_after();
   const uint32_t tmem = tmem_holder;
   const uint32_t smem_base = smem_u32(smem);
-  const long long total_tiles = (long long)g.row_blocks * g.n_tiles;
+  const int total_work = g.tiles * g.splits;
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
-      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const long long rb = tile / g.n_tiles;
-        const int nb = (int)(tile % g.n_tiles);
-        const int8_t* a = g.A + rb * g.nks * (long long)A_STAGE;
-        const int8_t* b = g.B + (long long)nb * g.nks * (long long)B_STAGE;
-        for (int ks = 0; ks < g.nks; ++ks, ++it) {
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const Work wk = get_work(g, w);
+        const int8_t* a = g.A + (long long)wk.rb * g.nks * (long long)A_STAGE;
+        const int8_t* b = g.B + (long long)wk.nb * g.nks * (long long)B_STAGE;
+        for (int ks = wk.ks0; ks < wk.ks1; ++ks, ++it) {
           const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
           mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
           const uint32_t fb = smem_u32(&full_bar[s]);
@@ -344,16 +497,17 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel_i8(GemmParams g, typen
   } else if (warp == 1) {
     if (lane == 0) {
       uint32_t it = 0, tile_i = 0;
-      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tile_i) {
+        const Work wk = get_work(g, w);
         mbar_wait(smem_u32(&tmem_empty_bar), (tile_i & 1) ^ 1);  // accumulators drained by the epilogue warps
         tc_fence_after();
-        for (int ks = 0; ks < g.nks; ++ks, ++it) {
+        for (int ks = wk.ks0; ks < wk.ks1; ++ks, ++it) {
           const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
           mbar_wait(smem_u32(&full_bar[s]), ph);
           tc_fence_after();
           const uint64_t da = smem_desc<LAYOUT>(smem_base + s * STAGE_BYTES);
           const uint64_t db = smem_desc<LAYOUT>(smem_base + s * STAGE_BYTES + A_STAGE);
-          const uint32_t acc0 = ks > 0 ? 1u : 0u;
+          const uint32_t acc0 = ks > wk.ks0 ? 1u : 0u;
 #pragma unroll
           for (int p = 0; p < S; ++p)
 #pragma unroll
@@ -372,9 +526,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel_i8(GemmParams g, typen
     const int quad = warp & 3;       // the TMEM lane quadrant this warp may access
     const int cb = (e >> 2) * 16;    // first of its 16 complex columns within the tile
     uint32_t tile_i = 0;
-    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
-      const long long rb = tile / g.n_tiles;
-      const int nb = (int)(tile % g.n_tiles);
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tile_i) {
+      const Work wk = get_work(g, w);
       mbar_wait(smem_u32(&tmem_full_bar), tile_i & 1);
       tc_fence_after();
       double sr[16], si[16];
@@ -387,7 +540,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel_i8(GemmParams g, typen
         tmem_ld16(taddr, ar);
         tmem_ld16(taddr + TN / 2, ai);
         tmem_ld_wait();
-        const double w = 1.0 / (double)(1ull << (7 * (t + 2)));  // 128^-(t+2)
+        const double w = level_weight(t);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           sr[j] = fma(i2d(ar[j]), w, sr[j]);
@@ -397,7 +550,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel_i8(GemmParams g, typen
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar));
-      Epi::apply(ep, rb * TM + quad * 32 + lane, nb * (TN / 2) + cb, sr, si);
+      Epi::apply(ep, wk, (long long)wk.rb * TM + quad * 32 + lane, wk.nb * (TN / 2) + cb, sr, si);
     }
   }
   tc_fence_before();

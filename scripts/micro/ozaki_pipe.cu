@@ -39,7 +39,7 @@ static int run(Problem& pr, bool timing) {
   const double scale = ldexp(1.0, oz::FRAC_BITS - pr.eA);
   oz::slice_rows_kernel<LAYOUT><<<sms * 16, 256>>>(pr.d_psi, 2LL * pr.Dp, pr.rows, pr.D, pr.Dp, scale, pr.nks, pr.row_blocks, pr.d_a);
   CK(cudaDeviceSynchronize());
-  oz::GemmParams g{pr.d_a, pr.d_b, pr.nks, pr.row_blocks, pr.n_tiles};
+  oz::GemmParams g{pr.d_a, pr.d_b, pr.nks, pr.row_blocks, pr.n_tiles, 0, pr.row_blocks * pr.n_tiles, 1, pr.nks};
   const long long ld = pr.Np;
   oz::EpiStore::Params es{pr.rows, pr.m, pr.d_cs, pr.d_tr, pr.d_ti, ld};
   CK(cudaFuncSetAttribute(oz::gemm_kernel_i8<LAYOUT, oz::EpiStore>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::SMEM_BYTES));
@@ -73,7 +73,7 @@ static int run(Problem& pr, bool timing) {
       const double a = col < pr.D ? pr.psi[(size_t)i * K + k] : 0.0;
       const double ya = col < pr.D ? pr.bt[(size_t)j * pr.Dp + col] : 0.0, yb = col < pr.D ? pr.bt[(size_t)(pr.Np + j) * pr.Dp + col] : 0.0;
       const double br = half == 0 ? ya : yb, bi = half == 0 ? -yb : ya;
-      const long long qa = oz::quantise(a, sa) + oz::DIGIT_BIAS, qr = oz::quantise(br, sb) + oz::DIGIT_BIAS, qi = oz::quantise(bi, sb) + oz::DIGIT_BIAS;
+      const unsigned long long qa = oz::digit_bytes(oz::quantise(a, sa)), qr = oz::digit_bytes(oz::quantise(br, sb)), qi = oz::digit_bytes(oz::quantise(bi, sb));
       for (int p = 0; p < oz::S; ++p) {
         da[p * K + k] = oz::digit(qa, p);
         dbr[p * K + k] = oz::digit(qr, p);
@@ -91,7 +91,7 @@ static int run(Problem& pr, bool timing) {
           ar += (long long)da[p * K + k] * dbr[(t - p) * K + k];
           ai += (long long)da[p * K + k] * dbi[(t - p) * K + k];
         }
-      const double w = ldexp(1.0, -7 * (t + 2));
+      const double w = oz::level_weight(t);
       sr = fma((double)ar, w, sr);
       si = fma((double)ai, w, si);
     }
