@@ -16,8 +16,9 @@ on the first 100k rows before timing.
 * `value`  : rows/s with X, y, s resident in HBM when the timed region starts.
 * `e2e`    : rows/s with HOST (pinned) X, y, s copied H2D and all results copied D2H inside every step; the upload
   goes through `nls_primal_gram_h2d`, which streams row groups on a copy stream underneath the Gram pass.
-* `roofline`: FP64 tensor (DMMA) roofline of the dominant kernel (the eigenbasis projection T = φQ),
-  timed with CUDA events around each launch; peak = DMMA register-loop peak measured in the same run.
+* `roofline`: tensor roofline of the dominant GEMM stage (and, under `stages`, of all three), timed with CUDA events
+  around each launch: FP64 DMMA stages against the DMMA register-loop peak, INT8 (Ozaki) stages against the
+  tcgen05 kind::i8 resident-tile peak, both measured in the same run.
 * `cpu_baseline`: the CPU oracle port of the reference algorithm on a bounded row sample, host cores.
 * `--impl reference`: the reference's CPU algorithm (oracle port, all host threads) on a bounded sample.
 """
@@ -233,7 +234,7 @@ def run_reference(args) -> None:
     print(json.dumps(line))
 
 
-def other_configs(ctx, peak_tflops: float, hbm_gbs: float) -> dict:
+def other_configs(ctx, peak_tflops: float, hbm_gbs: float, i8_peak: float = 0.0) -> dict:
     """The other BASELINE.json configurations and stage 5 on one GPU, each with the CPU time of the reference algorithm
     (oracle port on a bounded sample) beside it.  Parity-test cases in tests/; these are their timings."""
     import torch
@@ -244,6 +245,7 @@ def other_configs(ctx, peak_tflops: float, hbm_gbs: float) -> dict:
 
     dev = torch.device("cuda", ctx.device)
     out: dict = {}
+    int8 = os.environ.get("NLS_GEMM", "ozaki") != "dmma"
 
     def timed(fn, reps=1):
         torch.cuda.synchronize()
@@ -361,9 +363,15 @@ def other_configs(ctx, peak_tflops: float, hbm_gbs: float) -> dict:
     out["stage5"] = {
         "rows": n_s5, "seconds": t_s5, "rows_per_s": n_s5 / t_s5,
         "workload": f"predict + predict_std + 3-quantile conformal epilogue over {n_s5} rows, d={d}, num_features={D}",
-        "roofline_variance": {"bound": "tensor", "kernel": "gemm_kernel<MODE_COMPLEX, OpVariance> (4 m^2 flop/row, U^-1 basis)",
-                              "achieved": var_tf, "peak": peak_tflops, "unit": "TFLOP/s",
-                              "frac": var_tf / peak_tflops if var_tf and peak_tflops else None},
+        "roofline_variance": (
+            {"bound": "tensor", "kernel": "oz::gemm_kernel_i8<EpiVariance> (4 m^2 flop/row: U^-1 is triangular, so every column "
+                                          "tile contracts over its own k range only; 28 INT8 multiply-adds per FP64 one)",
+             "achieved": 28.0 * var_tf, "peak": i8_peak, "unit": "TOP/s (INT8)", "frac": 28.0 * var_tf / i8_peak if i8_peak else None,
+             "fp64_equivalent_tflops": var_tf, "vs_fp64_dmma_peak": var_tf / peak_tflops if peak_tflops else None}
+            if int8 and var_tf else
+            {"bound": "tensor", "kernel": "gemm_kernel<MODE_COMPLEX, OpVariance> (4 m^2 flop/row, U^-1 basis)",
+             "achieved": var_tf, "peak": peak_tflops, "unit": "TFLOP/s",
+             "frac": var_tf / peak_tflops if var_tf and peak_tflops else None}),
         "roofline_quantile_epilogue": {"bound": "hbm", "kernel": "quantile_epilogue_kernel (16 B in + 8 Q B out per row)",
                                        "achieved": epi_gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": epi_gbs / hbm_gbs,
                                        "ms": epi_ms},
@@ -430,6 +438,8 @@ def run_ours(args) -> None:
         fit = solve(Xd, yd, sd)
     peak_sustained = ctx.dmma_peak_tflops(20000) if rank == 0 else 0.0  # same loop right after the warm-up fits
     peak_tflops = max(peak_burst, peak_sustained)
+    i8_peak = ctx.i8_peak_tops(20000, 256) if rank == 0 else 0.0
+    i8_peak_n64 = ctx.i8_peak_tops(20000, 64) if rank == 0 else 0.0
     sampler = ClockSampler(local_rank)
     launches0 = ctx.launch_count()
     if rank == 0:
@@ -502,7 +512,7 @@ def run_ours(args) -> None:
         except Exception:  # noqa: BLE001
             hbm_gbs = 6545.6  # the pool's measured copy bandwidth (B200_PROFILING.md fallback)
         try:
-            configs = other_configs(ctx, peak_tflops, hbm_gbs)
+            configs = other_configs(ctx, peak_tflops, hbm_gbs, i8_peak)
         except Exception as exc:  # noqa: BLE001  (never lose the headline line to a side measurement)
             configs = {"error": repr(exc)}
 
@@ -528,11 +538,35 @@ def run_ours(args) -> None:
     if rank == 0:
         m = D + 1
         rows_local = r1 - r0
-        proj = prof["project"]
-        proj_flops = 8.0 * m * m * rows_local * args.steps  # algorithmic flops of T = φQ over the timed region
-        achieved = proj_flops / (proj["ms"] * 1e-3) / 1e12 if proj["ms"] > 0 else 0.0
         fit_tflops = n * flops_per_row(d, D, N_GAMMAS) * args.steps / (ms_total * 1e-3) / 1e12
         kernel_share = {k: v["ms"] for k, v in prof.items()}
+        int8 = os.environ.get("NLS_GEMM", "ozaki") != "dmma"
+        # The three GEMM stages, each against the peak of the tensor path it runs on.  Algorithmic work (SURVEY.md §8d /
+        # DESIGN.md §4): Gram 4m², projection 8m², sweep 4mG FP64 flop per row; on the INT8 core one FP64 multiply-add is
+        # 28 exact INT8 digit-plane multiply-adds (7 planes per operand, levels p + q <= 6), so its INT8 work is 28 x that.
+        # dram traffic per launch (32,768-row chunk) from `ncu --set full` captures under profiles/ (r1_ncu_full_gemm_kernels.md,
+        # r2f_ncu_full_int8.md); None where no capture exists.
+        stage_defs = {
+            "gram": (4.0 * m * m, int8, "oz::gemm_kernel_i8<EpiGram>" if int8 else "gemm_kernel<MODE_COMPLEX, OpGram>", None),
+            "project": (8.0 * m * m, int8, "oz::gemm_kernel_i8<EpiProject> (T = φQ)" if int8 else "gemm_kernel<MODE_COMPLEX, OpProject> (T = φQ)",
+                        None if int8 else 1.0895e9),
+            "sweep": (4.0 * m * N_GAMMAS, False, "gemm_kernel<MODE_DUAL_A, OpSweep> (fused LOO residual / reduction)", None),
+        }
+        stages = {}
+        for name, (fpr, on_int8, kernel, traffic) in stage_defs.items():
+            ms = prof[name]["ms"]
+            tf = fpr * rows_local * args.steps / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+            if on_int8:
+                stages[name] = {"bound": "tensor", "kernel": kernel, "achieved": 28.0 * tf, "peak": i8_peak, "unit": "TOP/s (INT8)",
+                                "frac": 28.0 * tf / i8_peak if i8_peak else None, "fp64_equivalent_tflops": tf,
+                                "vs_fp64_dmma_peak": tf / peak_tflops if peak_tflops else None,
+                                "frac_of_tile_shape_peak": 28.0 * tf / i8_peak_n64 if i8_peak_n64 else None}
+            else:
+                stages[name] = {"bound": "tensor", "kernel": kernel, "achieved": tf, "peak": peak_tflops, "unit": "TFLOP/s",
+                                "frac": tf / peak_tflops if peak_tflops else None}
+            stages[name]["ms_per_step"] = ms / args.steps
+            stages[name]["traffic"] = traffic if rows_local >= 32768 else None
+        dominant = max(stages, key=lambda k: stages[k]["ms_per_step"])
         cpu = None
         if world == 1:
             v, threads, kind, detail = cpu_reference_rows_per_s(args.cpu_rows, 1, 1)
@@ -558,17 +592,19 @@ def run_ours(args) -> None:
             "gpu_launches": int(launches.item()),
             "clocks": clocks,
             "roofline": {
-                "bound": "tensor", "kernel": "gemm_kernel<MODE_COMPLEX, OpProject> (T = φQ, 8m² flop/row)",
-                "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                "frac": achieved / peak_tflops if peak_tflops else None,
-                "peak_source": "FP64 DMMA register-resident loop measured in this run (nls_bench_dmma_peak), the larger "
-                               "of a cold-start burst and a post-warm-up reading; MEASURED_PEAKS.json has no FP64 "
-                               "figure. 148 SMs x 64 FMA/clk x 1.965 GHz = 37.2 TFLOP/s nominal",
-                "peak_burst": peak_burst, "peak_sustained": peak_sustained,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one projection launch (32768 rows) from
-                # profiles/r1_ncu_full_gemm_kernels.md; algorithmic bytes: 571 MB in + 537 MB out.
-                "traffic": 1.0895e9 if rows_local >= 32768 else None,
+                **{k: v for k, v in stages[dominant].items() if k != "ms_per_step"},
+                "stage": dominant,
+                "peak_source": "FP64: DMMA register-resident loop measured in this run (nls_bench_dmma_peak), the larger of a "
+                               "cold-start burst and a post-warm-up reading (148 SMs x 64 FMA/clk x 1.965 GHz = 37.2 TFLOP/s "
+                               "nominal). INT8: resident-tile tcgen05.mma kind::i8 loop measured in this run "
+                               "(nls_bench_i8_peak, M = 128, N = 256; 148 SMs x 8192 MAC/clk = 4.76 POP/s nominal at 1.965 GHz). "
+                               "MEASURED_PEAKS.json has neither figure",
+                "peak_fp64_dmma": peak_tflops, "peak_burst": peak_burst, "peak_sustained": peak_sustained,
+                "peak_int8": i8_peak, "peak_int8_at_tile_shape_n64": i8_peak_n64,
+                "stages": stages,
                 "fit_tflops": fit_tflops, "fit_frac": fit_tflops / (peak_tflops * world) if peak_tflops else None,
+                "fit_frac_note": "whole-fit algorithmic FP64 flop rate over the FP64 DMMA peak; above 1 means the INT8 "
+                                 "(Ozaki) stages beat what FP64 tensor cores could do at 100 %",
                 "kernel_ms": kernel_share,
             },
             "cpu_baseline": cpu,

@@ -56,7 +56,8 @@ int64_t nls_ctx_launch_count(const nls_ctx* ctx);
 int nls_ctx_profile(nls_ctx* ctx, int enable);
 int nls_ctx_profile_read(nls_ctx* ctx, double* ms_out /* [NLS_PROF_N] */, int64_t* launches_out /* [NLS_PROF_N] */);
 enum { NLS_PROF_FEATURE_MAP = 0, NLS_PROF_GRAM = 1, NLS_PROF_PROJECT = 2, NLS_PROF_SWEEP = 3,
-       NLS_PROF_VARIANCE = 4, NLS_PROF_OTHER = 5, NLS_PROF_N = 6 };
+       NLS_PROF_VARIANCE = 4, NLS_PROF_OTHER = 5, NLS_PROF_SLICE = 6 /* digit-plane slicing of the INT8 core */,
+       NLS_PROF_N = 7 };
 
 /* ---------------------------------------------------------------------------------------------
  * Stage 1 — feature map.  Replaces AffineFeatureMap.transform (_affine_feature_map.py:72-92) +
@@ -250,6 +251,9 @@ int nls_bin_mad(nls_ctx* ctx, const double* X, int64_t n, int d, const int64_t* 
 
 /* Micro-benchmarks used for the roofline denominators (bench.py / profiles/). */
 int nls_bench_dmma_peak(nls_ctx* ctx, int iters, double* tflops_out);
+/* INT8 tensor rate (TOP/s) of a resident-tile tcgen05.mma kind::i8 loop on every SM: n_cols = 256 (the hardware
+ * peak) or 64 (the shape of the Ozaki tile, bound by the shared-memory operand reads of each MMA). */
+int nls_bench_i8_peak(nls_ctx* ctx, int iters, int n_cols, double* tops_out);
 
 #ifdef __cplusplus
 }

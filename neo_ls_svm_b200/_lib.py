@@ -14,7 +14,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libnls_b200.so")
 
-PROF_KINDS = ("feature_map", "gram", "project", "sweep", "variance", "other")
+PROF_KINDS = ("feature_map", "gram", "project", "sweep", "variance", "other", "slice")
 
 _c_double_p = C.c_void_p  # device pointers are passed as integers
 _lib = None
@@ -60,6 +60,7 @@ def _signatures(lib: C.CDLL) -> None:
         "nls_bin_median_stats": ([p, p, i64, i, p, p, p, i, p, i, p, p, p], i),
         "nls_bin_mad": ([p, p, i64, i, p, p, p, i, p, i, p, p], i),
         "nls_bench_dmma_peak": ([p, i, C.POINTER(d)], i),
+        "nls_bench_i8_peak": ([p, i, i, C.POINTER(d)], i),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(lib, name)
@@ -176,6 +177,13 @@ class Context:
     def dmma_peak_tflops(self, iters: int = 20000) -> float:
         out = C.c_double()
         check(self.lib.nls_bench_dmma_peak(self.handle, iters, C.byref(out)))
+        return out.value
+
+    def i8_peak_tops(self, iters: int = 20000, n_cols: int = 256) -> float:
+        """INT8 tensor-core rate (TOP/s) of a resident-tile tcgen05.mma kind::i8 loop: n_cols = 256 is the hardware peak,
+        64 the shape the Ozaki tile uses."""
+        out = C.c_double()
+        check(self.lib.nls_bench_i8_peak(self.handle, iters, n_cols, C.byref(out)))
         return out.value
 
     # -- stages --------------------------------------------------------------------------------

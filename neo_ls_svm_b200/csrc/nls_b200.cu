@@ -593,17 +593,20 @@ static int gram_impl(nls_ctx* ctx, const double* X, const double* y, const doubl
     }
     NLS_TRY(feature_chunk(ctx, g, X + i0 * d, shift, rows, FM_TRANSPOSED, (double*)ctx->psiT.p, ldT, g.DpT, s + i0));
     if (use_oz) {
-      ProfScope scope(ctx, NLS_PROF_GRAM);
       double* sc = (double*)ctx->oz_small.p;
+      const int nksR = (int)(round_up(rows, oz::KS) / oz::KS);
+      {
+      ProfScope slice_scope(ctx, NLS_PROF_SLICE);
       oz::gram_scale_kernel<<<1, 1024, 0, ctx->stream>>>(s + i0, rows, 1.0 / sqrt((double)D), sc);
       NLS_TRY(check_launch(ctx, "oz::gram_scale_kernel"));
-      const int nksR = (int)(round_up(rows, oz::KS) / oz::KS);
       oz::slice_gram_kernel<oz::IMAGE><<<grid_for((long long)oz_rb * 2 * nksR * oz::TM * 2), 256, 0, ctx->stream>>>(
           (const double*)ctx->psiT.p, ldT, g.DpT, D, rows, sc, nksR, oz_rb, oz_nt, (int8_t*)ctx->oz_a.p, (int8_t*)ctx->oz_g.p);
       NLS_TRY(check_launch(ctx, "oz::slice_gram_kernel"));
+      }
+      ProfScope scope(ctx, NLS_PROF_GRAM);
       const int ks_per_split = (2 * nksR + splits - 1) / splits;
       oz::GemmParams gp{(const int8_t*)ctx->oz_a.p, (const int8_t*)ctx->oz_g.p, 2 * nksR, oz_rb, oz_nt, 1, oz_tiles,
-                        (2 * nksR + ks_per_split - 1) / ks_per_split, ks_per_split};
+                        (2 * nksR + ks_per_split - 1) / ks_per_split, ks_per_split, 0};
       oz::EpiGram::Params ep{D, sc + 1, (double*)ctx->gram_ws.p};
       const int grid = (int)std::min<long long>((long long)gp.tiles * gp.splits, ctx->sm_count);
       oz::gemm_kernel_i8<oz::IMAGE, oz::EpiGram><<<grid, oz::THREADS, oz::SMEM_BYTES, ctx->stream>>>(gp, ep);
@@ -1184,8 +1187,15 @@ struct OzBasis {
   int n_tiles, nks, eA;
 };
 
+// The projection-type products run on the INT8 core when the context says so and K fits the INT32 accumulators.
+static bool oz_usable(const nls_ctx* ctx, const MapGeom& g) {
+  return ctx->gemm_core == 1 && oz::feature_ksteps(g.D) * oz::KS <= oz::MAX_K && tail_split(g.m) > 0;
+}
+
 static int oz_attr(nls_ctx* ctx) {
   if (ctx->oz_attr) return NLS_OK;
+  CUDA_TRY(cudaFuncSetAttribute(oz::gemm_kernel_i8<oz::IMAGE, oz::EpiVariance>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                oz::SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(oz::gemm_kernel_i8<oz::IMAGE, oz::EpiProject>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 oz::SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(oz::gemm_kernel_i8<oz::IMAGE, oz::EpiGram>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1198,14 +1208,14 @@ static int oz_attr(nls_ctx* ctx) {
 static int oz_prep_basis(nls_ctx* ctx, const MapGeom& g, const BasisScratch& bs, int cols, OzBasis* out) {
   NLS_TRY(oz_attr(ctx));
   const int n_tiles = (cols + oz::TN / 2 - 1) / (oz::TN / 2);
-  const int nks = 2 * g.Dp / oz::KS;
+  const int nks = oz::feature_ksteps(g.D);
   const int padded = n_tiles * (oz::TN / 2);
   NLS_TRY(ensure(ctx, ctx->oz_b, (size_t)n_tiles * nks * oz::B_STAGE));
   NLS_TRY(ensure(ctx, ctx->oz_small, (size_t)padded * 16));
   double* colscale = (double*)ctx->oz_small.p;
   int* ex = (int*)(colscale + padded);
   const int eA = oz::scale_exponent(1.0 / sqrt((double)g.D));  // |cos| D^-1/2, |sin| D^-1/2 <= D^-1/2
-  ProfScope scope(ctx, NLS_PROF_PROJECT);
+  ProfScope scope(ctx, NLS_PROF_SLICE);
   oz::basis_exponent_kernel<<<(padded + 7) / 8, 256, 0, ctx->stream>>>(bs.bt, g.Np, g.Dp, g.D, cols, padded, eA, ex, colscale);
   NLS_TRY(check_launch(ctx, "oz::basis_exponent_kernel"));
   oz::slice_basis_kernel<oz::IMAGE><<<grid_for((long long)n_tiles * nks * oz::TN * 2), 256, 0, ctx->stream>>>(
@@ -1219,17 +1229,24 @@ static int oz_prep_basis(nls_ctx* ctx, const MapGeom& g, const BasisScratch& bs,
   return NLS_OK;
 }
 
+// Digit planes of the planar feature chunk in ctx->psi (the A operand of the projection-type products).
+static int oz_slice_chunk(nls_ctx* ctx, const MapGeom& g, const OzBasis& ob, int rows) {
+  const int row_blocks = (rows + oz::TM - 1) / oz::TM;
+  NLS_TRY(ensure(ctx, ctx->oz_a, (size_t)((ctx->chunk_rows + oz::TM - 1) / oz::TM) * ob.nks * oz::A_STAGE));
+  ProfScope slice_scope(ctx, NLS_PROF_SLICE);
+  oz::slice_rows_kernel<oz::IMAGE><<<grid_for((long long)row_blocks * ob.nks * oz::TM * 2), 256, 0, ctx->stream>>>(
+      (const double*)ctx->psi.p, 2LL * g.Dp, rows, g.D, g.Dp, ldexp(1.0, oz::FRAC_BITS - ob.eA), ob.nks, row_blocks,
+      (int8_t*)ctx->oz_a.p);
+  return check_launch(ctx, "oz::slice_rows_kernel");
+}
+
 // P = Re(T v), U = |T|^2 / c for the first `cols` columns of T = phi Q, phi = the planar chunk in ctx->psi.
 static int oz_project_chunk(nls_ctx* ctx, const MapGeom& g, const BasisScratch& bs, const OzBasis& ob, int rows, int cols,
                             double inv_c, double* P, double* U) {
   const int row_blocks = (rows + oz::TM - 1) / oz::TM;
-  NLS_TRY(ensure(ctx, ctx->oz_a, (size_t)((ctx->chunk_rows + oz::TM - 1) / oz::TM) * ob.nks * oz::A_STAGE));
+  NLS_TRY(oz_slice_chunk(ctx, g, ob, rows));
   ProfScope scope(ctx, NLS_PROF_PROJECT);
-  oz::slice_rows_kernel<oz::IMAGE><<<grid_for((long long)row_blocks * ob.nks * oz::TM * 2), 256, 0, ctx->stream>>>(
-      (const double*)ctx->psi.p, 2LL * g.Dp, rows, g.D, g.Dp, ldexp(1.0, oz::FRAC_BITS - ob.eA), ob.nks, row_blocks,
-      (int8_t*)ctx->oz_a.p);
-  NLS_TRY(check_launch(ctx, "oz::slice_rows_kernel"));
-  oz::GemmParams gp{(const int8_t*)ctx->oz_a.p, ob.planes, ob.nks, row_blocks, ob.n_tiles, 0, row_blocks * ob.n_tiles, 1, ob.nks};
+  oz::GemmParams gp{(const int8_t*)ctx->oz_a.p, ob.planes, ob.nks, row_blocks, ob.n_tiles, 0, row_blocks * ob.n_tiles, 1, ob.nks, 0};
   oz::EpiProject::Params ep{rows, cols, ob.colscale, bs.bias_r, bs.bias_i, bs.v_r, bs.v_i, inv_c, P, U, g.ldp};
   const int grid = (int)std::min<long long>((long long)row_blocks * ob.n_tiles, ctx->sm_count);
   oz::gemm_kernel_i8<oz::IMAGE, oz::EpiProject><<<grid, oz::THREADS, oz::SMEM_BYTES, ctx->stream>>>(gp, ep);
@@ -1264,7 +1281,7 @@ extern "C" int nls_primal_loo_sweep(nls_ctx* ctx, const double* X, const double*
   double* P = (double*)ctx->pu.p;
   double* U = P + cap * g.ldp;
   // The projection T = phi Q runs on the INT8 tensor cores (Ozaki scheme, csrc/ozaki.cuh) unless the context says DMMA.
-  const bool use_oz = ctx->gemm_core == 1 && 2 * g.Dp <= oz::MAX_K && tail_split(g.m) > 0;
+  const bool use_oz = oz_usable(ctx, g);
   OzBasis oz{};
   if (use_oz) NLS_TRY(oz_prep_basis(ctx, g, bs, tail_split(g.m), &oz));
   for (int64_t i0 = 0; i0 < n; i0 += cap) {
@@ -1341,11 +1358,35 @@ extern "C" int nls_primal_loo_sweep(nls_ctx* ctx, const double* X, const double*
 // Shared by stage 4c and stage 5: per-row yhat (two coefficient vectors) and sigma2 for a chunk.
 // ---------------------------------------------------------------------------------------------
 static int variance_chunk(nls_ctx* ctx, const MapGeom& g, const BasisScratch& bs, int rows, double* sigma2_out,
-                          int b_upper = 0) {
+                          int b_upper = 0, const OzBasis* ob = nullptr) {
   const int full_cols = tail_split(g.m);
+  const long long cap = ctx->chunk_rows;
+  if (ob) {
+    // INT8 core: two partial sums (column halves) per 32-column tile, the spill columns after them.
+    const int ntiles = 2 * ob->n_tiles + (full_cols < g.m ? 1 : 0);
+    NLS_TRY(ensure(ctx, ctx->part, (size_t)ntiles * cap * 8));
+    NLS_TRY(oz_slice_chunk(ctx, g, *ob, rows));
+    const int row_blocks = (rows + oz::TM - 1) / oz::TM;
+    {
+      ProfScope scope(ctx, NLS_PROF_VARIANCE);
+      oz::GemmParams gp{(const int8_t*)ctx->oz_a.p, ob->planes, ob->nks, row_blocks, ob->n_tiles, 0, row_blocks * ob->n_tiles,
+                        1, ob->nks, b_upper ? 1 : 0};
+      oz::EpiVariance::Params ep{rows, full_cols, ob->colscale, bs.bias_r, bs.bias_i, bs.w, (double*)ctx->part.p, cap};
+      const int grid = (int)std::min<long long>((long long)row_blocks * ob->n_tiles, ctx->sm_count);
+      oz::gemm_kernel_i8<oz::IMAGE, oz::EpiVariance><<<grid, oz::THREADS, oz::SMEM_BYTES, ctx->stream>>>(gp, ep);
+      NLS_TRY(check_launch(ctx, "oz::gemm_kernel_i8<EpiVariance>"));
+      if (full_cols < g.m) {
+        project_tail_kernel<<<(rows * 32 + 255) / 256, 256, 0, ctx->stream>>>(
+            (const double*)ctx->psi.p, 2LL * g.Dp, g.Dp, rows, g.D, bs.bt, g.Dp, g.Np, full_cols, g.m, bs.bias_r, bs.bias_i, 1,
+            nullptr, nullptr, 0.0, nullptr, nullptr, 0, bs.w, (double*)ctx->part.p + (size_t)2 * ob->n_tiles * cap);
+        NLS_TRY(check_launch(ctx, "project_tail_kernel"));
+      }
+    }
+    rowsum_reduce_kernel<<<(rows + 255) / 256, 256, 0, ctx->stream>>>((const double*)ctx->part.p, ntiles, cap, rows, sigma2_out);
+    return check_launch(ctx, "rowsum_reduce_kernel");
+  }
   const int gemm_tiles = (full_cols + BN - 1) / BN;
   const int ntiles = gemm_tiles + (full_cols < g.m ? 1 : 0);
-  const long long cap = ctx->chunk_rows;
   NLS_TRY(ensure(ctx, ctx->part, (size_t)ntiles * cap * 8));
   OpVariance::Params vp;
   vp.A = psi_operand(ctx, g, rows);
@@ -1390,6 +1431,9 @@ extern "C" int nls_primal_finalize(nls_ctx* ctx, const double* X, const double* 
     variance_weights_kernel<<<(g.m + 255) / 256, 256, 0, ctx->stream>>>(lam, g.m, inv_c, gamma, bs.w);
     NLS_TRY(check_launch(ctx, "variance_weights_kernel"));
   }
+  OzBasis oz{};
+  const bool use_oz = !sigma2_in && oz_usable(ctx, g);
+  if (use_oz) NLS_TRY(oz_prep_basis(ctx, g, bs, tail_split(g.m), &oz));
   const long long cap = ctx->chunk_rows;
   NLS_TRY(ensure(ctx, ctx->psi, (size_t)cap * 2 * g.Dp * 8));
   NLS_TRY(ensure(ctx, ctx->rowtmp, (size_t)3 * cap * 8));
@@ -1415,7 +1459,7 @@ extern "C" int nls_primal_finalize(nls_ctx* ctx, const double* X, const double* 
       NLS_TRY(check_launch(ctx, "rowdots_reduce_kernel"));
     } else {
       NLS_TRY(feature_chunk(ctx, g, X + i0 * d, shift, rows, FM_PLANAR, (double*)ctx->psi.p, 2LL * g.Dp, g.Dp, nullptr));
-      NLS_TRY(variance_chunk(ctx, g, bs, rows, sigma2_tmp));
+      NLS_TRY(variance_chunk(ctx, g, bs, rows, sigma2_tmp, 0, use_oz ? &oz : nullptr));
       gemv_pair_kernel<<<(rows * 32 + 255) / 256, 256, 0, ctx->stream>>>((const double*)ctx->psi.p, 2LL * g.Dp, g.Dp,
                                                                         rows, D, beta_eig, beta, num, fit);
       NLS_TRY(check_launch(ctx, "gemv_pair_kernel"));
@@ -1442,6 +1486,9 @@ extern "C" int nls_primal_predict(nls_ctx* ctx, const double* X, int64_t n, int 
     NLS_TRY(prep_basis(ctx, g, B, &bs, b_upper));
     CUDA_TRY(cudaMemcpyAsync(bs.w, w, (size_t)g.m * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   }
+  OzBasis oz{};
+  const bool use_oz = sigma_out && oz_usable(ctx, g);
+  if (use_oz) NLS_TRY(oz_prep_basis(ctx, g, bs, tail_split(g.m), &oz));
   const long long cap = ctx->chunk_rows;
   NLS_TRY(ensure(ctx, ctx->psi, (size_t)cap * 2 * g.Dp * 8));
   NLS_TRY(ensure(ctx, ctx->rowtmp, (size_t)3 * cap * 8));
@@ -1464,7 +1511,7 @@ extern "C" int nls_primal_predict(nls_ctx* ctx, const double* X, int64_t n, int 
       NLS_TRY(check_launch(ctx, "rowdots_reduce_kernel"));
     }
     if (sigma_out) {
-      NLS_TRY(variance_chunk(ctx, g, bs, rows, sigma2, b_upper));
+      NLS_TRY(variance_chunk(ctx, g, bs, rows, sigma2, b_upper, use_oz ? &oz : nullptr));
       sqrt_kernel<<<(rows + 255) / 256, 256, 0, ctx->stream>>>(sigma2, rows, sigma_out + i0);
       NLS_TRY(check_launch(ctx, "sqrt_kernel"));
     }
@@ -1853,6 +1900,41 @@ extern "C" int nls_bin_mad(nls_ctx* ctx, const double* X, int64_t n, int d, cons
   NLS_TRY(check_launch(ctx, "bs_mad_kernel"));
   bs_sum_kernel<<<(nbins * d + 255) / 256, 256, 0, ctx->stream>>>(partial, (const int2*)bin_tiles, nbins, d, spread_out);
   return check_launch(ctx, "bs_sum_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Micro-benchmark: resident-tile tcgen05.mma kind::i8 loop (INT8 tensor peak of this device), at the hardware's
+// widest single-CTA shape (n_cols = 256) or at the Ozaki tile's shape (n_cols = 64).
+// ---------------------------------------------------------------------------------------------
+template <int N>
+static int i8_peak(nls_ctx* ctx, int iters, double* tops_out) {
+  const int smem = 1024 + (oz::TM + N) * 128;
+  CUDA_TRY(cudaFuncSetAttribute(oz::i8_peak_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaEvent_t a, b;
+  CUDA_TRY(cudaEventCreate(&a));
+  CUDA_TRY(cudaEventCreate(&b));
+  oz::i8_peak_kernel<N><<<ctx->sm_count, 128, smem, ctx->stream>>>(iters / 8 + 1);
+  float ms = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    CUDA_TRY(cudaEventRecord(a, ctx->stream));
+    oz::i8_peak_kernel<N><<<ctx->sm_count, 128, smem, ctx->stream>>>(iters);
+    CUDA_TRY(cudaEventRecord(b, ctx->stream));
+    NLS_TRY(check_launch(ctx, "oz::i8_peak_kernel"));
+    CUDA_TRY(cudaEventSynchronize(b));
+    float t = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&t, a, b));
+    ms = t < ms ? t : ms;
+  }
+  *tops_out = (double)ctx->sm_count * iters * 4.0 * (2.0 * oz::TM * N * 32) / (ms * 1e-3) / 1e12;
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  return NLS_OK;
+}
+
+extern "C" int nls_bench_i8_peak(nls_ctx* ctx, int iters, int n_cols, double* tops_out) {
+  if (!ctx || !tops_out || iters < 1 || (n_cols != 64 && n_cols != 256)) return fail(NLS_ERR_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  return n_cols == 64 ? i8_peak<64>(ctx, iters, tops_out) : i8_peak<256>(ctx, iters, tops_out);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -108,6 +108,11 @@ __host__ __device__ __forceinline__ int scale_exponent(double amax) {
 }
 
 // ---- slicing kernels ------------------------------------------------------------------------------
+// K order of the projection-type products (K = the feature index of both halves of phi): k step 2 fb holds the cos
+// features 32 fb .. 32 fb + 31, k step 2 fb + 1 the sin features of the same block, nks = 2 ceil(D / 32).  With an
+// upper-triangular B (predict_std through U^-1) column tile nb then needs the contiguous range ks < 2 (nb + 1) only.
+__host__ __device__ __forceinline__ int feature_ksteps(int D) { return 2 * ((D + KS - 1) / KS); }
+
 // A operand: `rows` rows of the planar feature chunk psi = [C | S] (pitch ld, each half Dp wide, D valid), one
 // global exponent e.  Work item = one 16-byte chunk of one row of one k step; items run (chunk, row) fastest so
 // that a warp writes 512 contiguous bytes per plane.
@@ -122,17 +127,17 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
     const int ks = (int)(blk % nks);
     const long long rb = blk / nks;
     const long long row = rb * TM + r;
-    const int k0 = ks * KS + c * 16;
+    const int col0 = (ks >> 1) * KS + c * 16;  // first feature of this chunk, in half (ks & 1)
     uint32_t w[S][4];
 #pragma unroll
     for (int p = 0; p < S; ++p)
 #pragma unroll
       for (int j = 0; j < 4; ++j) w[p][j] = 0;
-    if (row < rows) {
-      const double* src = X + row * ld + k0;
+    if (row < rows && col0 < D) {
+      const double* src = X + row * ld + (ks & 1) * Dp + col0;
 #pragma unroll
       for (int j = 0; j < 16; j += 2) {
-        const int col = (k0 + j) % Dp;  // Dp is a multiple of 16: a chunk never straddles the two halves
+        const int col = col0 + j;
         double2 v = make_double2(0.0, 0.0);
         if (col < D) v = *reinterpret_cast<const double2*>(src + j);
         if (col + 1 >= D) v.y = 0.0;
@@ -151,7 +156,7 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double* __restric
 }
 
 // B operand of the projection: Bt = [Re Q^T ; Im Q^T] (2 Np x Dp, as the DMMA path keeps it).  Complex column j
-// becomes two rows of the real product over k in [0, 2 Dp):   re row = [ ya_j | yb_j ],  im row = [ -yb_j | ya_j ]
+// becomes two rows of the real product over both halves of k:   re row = [ ya_j | yb_j ],  im row = [ -yb_j | ya_j ]
 // (R = C ya + S yb = Re T,  I = S ya - C yb = -Im T: the convention of gemm_core's MODE_COMPLEX).
 // Pass 1: per-column exponents and the recombination scale 2^(eA + eB_j).
 __global__ void __launch_bounds__(256) basis_exponent_kernel(const double* __restrict__ Bt, int Np, int Dp, int D, int cols,
@@ -185,14 +190,13 @@ __global__ void __launch_bounds__(256) slice_basis_kernel(const double* __restri
     const int nb = (int)(blk / nks);
     const int j = nb * (TN / 2) + (r & (TN / 2 - 1));
     const bool im = r >= TN / 2;
-    const int k0 = ks * KS + c * 16;
-    const int half = k0 / Dp, col0 = k0 % Dp;
+    const int half = ks & 1, col0 = (ks >> 1) * KS + c * 16;
     uint32_t w[S][4];
 #pragma unroll
     for (int p = 0; p < S; ++p)
 #pragma unroll
       for (int q = 0; q < 4; ++q) w[p][q] = 0;
-    if (j < cols) {
+    if (j < cols && col0 < D) {
       // re row: half 0 -> ya, half 1 -> yb;   im row: half 0 -> -yb, half 1 -> ya
       const bool use_b = (half == 1) != im;
       const double sign = (im && half == 0) ? -1.0 : 1.0;
@@ -327,6 +331,7 @@ struct GemmParams {
   int tiles;         // tiles per K split (row_blocks * n_tiles, or the upper-triangular count)
   int splits;        // the K range is cut into `splits` work items per tile (each with its own epilogue slot) ...
   int ks_per_split;  // ... of this many k steps
+  int upper_k;       // 1: B is upper triangular in (feature, column): column tile nb needs ks < 2 (nb + 1) only
 };
 
 struct Work {
@@ -352,6 +357,7 @@ __device__ __forceinline__ Work get_work(const GemmParams& g, int w) {
   }
   k.ks0 = k.split * g.ks_per_split;
   k.ks1 = min(g.nks, k.ks0 + g.ks_per_split);
+  if (g.upper_k) k.ks1 = min(k.ks1, 2 * (k.nb + 1));
   return k;
 }
 
@@ -420,6 +426,36 @@ struct EpiStore {  // raw T planes (probe / tests): Tr[row][col] = sr * colscale
         p.Tr[row * p.ld + col0 + j] = sr[j] * p.colscale[col0 + j];
         p.Ti[row * p.ld + col0 + j] = si[j] * p.colscale[col0 + j];
       }
+  }
+};
+
+// Stage 4c / 5b: sigma2_i = sum_k |(phi B)_ik|^2 w_k (what OpVariance computes; reference _neo_ls_svm.py:184, :467-469).
+// Every thread sums its 16 columns; part[2 nb + column half][row], reduced in fixed order by rowsum_reduce_kernel.
+struct EpiVariance {
+  struct Params {
+    int n_rows, m;
+    const double* colscale;
+    const double* bias_r;
+    const double* bias_i;
+    const double* w;
+    double* part;
+    long long part_ld;
+  };
+  static __device__ __forceinline__ void apply(const Params& p, const Work& wk, long long row, int col0, const double (&sr)[16],
+                                               const double (&si)[16]) {
+    if (row >= p.n_rows) return;
+    double rs = 0.0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int col = col0 + j;
+      if (col < p.m) {
+        const double cs = p.colscale[col];
+        const double tr = sr[j] * cs + p.bias_r[col];
+        const double ti = p.bias_i[col] - si[j] * cs;
+        rs += (tr * tr + ti * ti) * p.w[col];
+      }
+    }
+    p.part[(long long)(2 * wk.nb + ((col0 >> 4) & 1)) * p.part_ld + row] = rs;
   }
 };
 
@@ -556,6 +592,54 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel_i8(GemmParams g, typen
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+}
+
+// ---- INT8 tensor peak of this device (bench.py's roofline denominator) -----------------------------
+// Every CTA (one per SM) issues `iters` trains of four resident-tile MMAs (M = 128, N columns, K = 32 each; operand
+// tiles in the K-major SWIZZLE_128B image, contents irrelevant) into one TMEM accumulator: no loads, no epilogue.
+// N = 256 is the widest single-CTA shape (the hardware peak, 8192 MAC/cycle/SM); N = 64 is the shape the 7-level
+// Ozaki tile has to use (7 x 64 TMEM columns), where every MMA is bound by its 6 KB of shared-memory operand reads.
+template <int N>
+__global__ void __launch_bounds__(128, 1) i8_peak_kernel(int iters) {
+  extern __shared__ uint8_t oz_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_holder;
+  constexpr uint32_t COLS = N <= 64 ? 64 : N <= 128 ? 128 : 256;
+  constexpr uint32_t IDESC_N = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+  const int tid = threadIdx.x;
+  for (int e = tid; e < (TM + N) * 128 / 16; e += 128) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+  if (tid < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    mbar_fence_init();
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_holder;
+  if (tid == 0) {
+    auto desc = [](uint32_t addr) {
+      return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    };
+    const uint64_t da = desc(smem_u32(smem)), db = desc(smem_u32(smem + TM * 128));
+    for (int i = 0; i < iters; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem),
+                     "l"(da + (uint64_t)(k * 2)), "l"(db + (uint64_t)(k * 2)), "r"(IDESC_N), "r"((i | k) ? 1u : 0u)
+                     : "memory");
+    umma_commit(smem_u32(&bar));
+  }
+  mbar_wait(smem_u32(&bar), 0);
+  tc_fence_after();
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(COLS));
 }
 
 }  // namespace oz

@@ -39,7 +39,7 @@ static int run(Problem& pr, bool timing) {
   const double scale = ldexp(1.0, oz::FRAC_BITS - pr.eA);
   oz::slice_rows_kernel<LAYOUT><<<sms * 16, 256>>>(pr.d_psi, 2LL * pr.Dp, pr.rows, pr.D, pr.Dp, scale, pr.nks, pr.row_blocks, pr.d_a);
   CK(cudaDeviceSynchronize());
-  oz::GemmParams g{pr.d_a, pr.d_b, pr.nks, pr.row_blocks, pr.n_tiles, 0, pr.row_blocks * pr.n_tiles, 1, pr.nks};
+  oz::GemmParams g{pr.d_a, pr.d_b, pr.nks, pr.row_blocks, pr.n_tiles, 0, pr.row_blocks * pr.n_tiles, 1, pr.nks, 0};
   const long long ld = pr.Np;
   oz::EpiStore::Params es{pr.rows, pr.m, pr.d_cs, pr.d_tr, pr.d_ti, ld};
   CK(cudaFuncSetAttribute(oz::gemm_kernel_i8<LAYOUT, oz::EpiStore>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::SMEM_BYTES));
@@ -57,7 +57,7 @@ static int run(Problem& pr, bool timing) {
     CK(cudaMemcpy(pr.ex.data(), pr.d_ex, pr.ex.size() * 4, cudaMemcpyDeviceToHost));
   }
   // host emulation on sampled entries
-  const int K = 2 * pr.Dp;
+  const int K = pr.nks * oz::KS;
   long long mism = 0;
   long double worst = 0;
   srand(11);
@@ -69,8 +69,8 @@ static int run(Problem& pr, bool timing) {
     const double sa = ldexp(1.0, oz::FRAC_BITS - pr.eA), sb = ldexp(1.0, oz::FRAC_BITS - pr.ex[j]);
     long double ref_r = 0, ref_i = 0, bound = 0;
     for (int k = 0; k < K; ++k) {
-      const int half = k / pr.Dp, col = k % pr.Dp;
-      const double a = col < pr.D ? pr.psi[(size_t)i * K + k] : 0.0;
+      const int half = (k / oz::KS) & 1, col = (k / oz::KS / 2) * oz::KS + k % oz::KS;  // interleaved K order of ozaki.cuh
+      const double a = col < pr.D ? pr.psi[(size_t)i * 2 * pr.Dp + half * pr.Dp + col] : 0.0;
       const double ya = col < pr.D ? pr.bt[(size_t)j * pr.Dp + col] : 0.0, yb = col < pr.D ? pr.bt[(size_t)(pr.Np + j) * pr.Dp + col] : 0.0;
       const double br = half == 0 ? ya : yb, bi = half == 0 ? -yb : ya;
       const unsigned long long qa = oz::digit_bytes(oz::quantise(a, sa)), qr = oz::digit_bytes(oz::quantise(br, sb)), qi = oz::digit_bytes(oz::quantise(bi, sb));
@@ -132,7 +132,7 @@ static void make(Problem& pr, int rows, int D, int m) {
   pr.rows = rows; pr.D = D; pr.m = m;
   pr.Dp = (D + 15) / 16 * 16;
   pr.Np = (m + 63) / 64 * 64;
-  pr.nks = 2 * pr.Dp / oz::KS;
+  pr.nks = oz::feature_ksteps(D);
   pr.row_blocks = (rows + oz::TM - 1) / oz::TM;
   pr.n_tiles = (m + 31) / 32;
   const int K = 2 * pr.Dp;
