@@ -16,6 +16,8 @@ here exists for API parity on small inputs (e.g. the dual path's n ≤ 1024 rows
 
 from __future__ import annotations
 
+import os
+from concurrent.futures import ThreadPoolExecutor
 from functools import cached_property
 from typing import Any
 
@@ -133,16 +135,74 @@ def _array_key(X) -> tuple:
     return (X.__array_interface__["data"][0], X.shape, X.dtype.str)
 
 
+class PendingUpload:
+    """Host→device copy of a large training matrix on a side stream, driven by a host thread, so that the 0.2 s a
+    pageable 2 GB upload takes runs underneath the host part of the supervised pre-pass (target quantisation) instead
+    of in front of it.  `result()` joins, orders the caller's stream after the copy and reports non-finite input."""
+
+    def __init__(self, X, device, scan_finite: bool):
+        import threading
+
+        import torch
+
+        self._torch, self._X, self._scan, self._device = torch, X, scan_finite, device
+        self._stream = torch.cuda.Stream(device)
+        self._stream.wait_stream(torch.cuda.current_stream(device))  # the block may be recycled from queued work
+        self._Xd = torch.empty(X.shape, dtype=torch.float64, device=device)
+        self._finite = self._event = self._error = None
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def _run(self) -> None:
+        torch = self._torch
+        try:
+            with torch.cuda.stream(self._stream):
+                src = torch.from_numpy(np.ascontiguousarray(self._X))
+                if src.dtype == torch.float64:
+                    self._Xd.copy_(src)
+                else:  # float32 rows cross the bus as they are and are widened on the device
+                    self._Xd.copy_(src.to(self._device))
+                if self._scan:
+                    self._finite = torch.isfinite(self._Xd).all()
+                self._event = self._stream.record_event()
+        except BaseException as exc:  # noqa: BLE001  (re-raised by result() on the caller's thread)
+            self._error = exc
+
+    def result(self):
+        if self._thread is not None:
+            self._thread.join()
+            self._thread = None
+            if self._error is not None:
+                raise self._error
+            self._torch.cuda.current_stream(self._device).wait_event(self._event)
+            if self._scan and not bool(self._finite):
+                import sklearn
+                from sklearn.utils import assert_all_finite
+
+                with sklearn.config_context(assume_finite=False):  # the caller may have switched re-validation off
+                    assert_all_finite(self._X, input_name="X")  # raises sklearn's ValueError
+        return self._Xd
+
+    def abandon(self) -> None:
+        if self._thread is not None:
+            self._thread.join()
+            self._thread = None
+
+
 def register_device_copy(X, Xd) -> None:
+    """Xd: the device tensor, or a PendingUpload that will produce it."""
     _DEVICE_COPIES[_array_key(X)] = Xd
 
 
 def release_device_copy(X) -> None:
-    _DEVICE_COPIES.pop(_array_key(X), None)
+    held = _DEVICE_COPIES.pop(_array_key(X), None)
+    if isinstance(held, PendingUpload):
+        held.abandon()
 
 
 def device_copy(X):
-    return _DEVICE_COPIES.get(_array_key(X))
+    held = _DEVICE_COPIES.get(_array_key(X))
+    return held.result() if isinstance(held, PendingUpload) else held
 
 
 def _bin_location_spread(X, rows, s_bins):
@@ -225,6 +285,17 @@ class AffineNormalizer(AffineFeatureMap):
         return self
 
 
+def _weight_cdf(p):
+    """The normalised running sum `RandomState.choice` builds from p (cast to float64 first, as it does)."""
+    cdf = np.cumsum(np.asarray(p, dtype=np.float64))
+    cdf /= cdf[-1]
+    return cdf
+
+
+def _cdf_lookup(cdf, uniforms):
+    return np.searchsorted(cdf, uniforms, side="right")
+
+
 def _weighted_draw(rng, p, size):
     """`rng.choice(len(p), size=size, p=p)` of a legacy RandomState, without its validation passes over p.
 
@@ -232,9 +303,7 @@ def _weighted_draw(rng, p, size):
     indices and the same generator state afterwards; p is a probability vector built a line earlier from
     validated sample weights, so re-checking it costs three more passes over up to n elements per call.
     """
-    cdf = np.cumsum(np.asarray(p, dtype=np.float64))  # `choice` casts p to float64 before the running sum
-    cdf /= cdf[-1]
-    return np.searchsorted(cdf, rng.random_sample(size), side="right")
+    return _cdf_lookup(_weight_cdf(p), rng.random_sample(size))
 
 
 def pairwise_distances(X, Y):
@@ -303,22 +372,38 @@ class AffineSeparator(AffineNormalizer):
 
         sizes = np.array([len(r) for r in rows])
         sw_by_bin = [sw[r] for r in rows]  # gathered once; every bin's complement concatenates six of them
+        # The three weighted draws per bin consume the generator in a fixed order (own seeds, complement, own sample)
+        # and nothing else touches it in between, so the uniforms are drawn first, in that order, and the 2 n_bins
+        # inverse-CDF lookups (a running sum over up to n weights each) then run side by side on the host threads.
+        uniforms = [(rng.random_sample(E), rng.random_sample(wide), rng.random_sample(wide)) for _ in range(n_bins)]
+
+        def draw_own(i):
+            cdf = _weight_cdf(np.ravel(s_bins[i]))
+            return _cdf_lookup(cdf, uniforms[i][0]), _cdf_lookup(cdf, uniforms[i][2])
+
+        def draw_rest(i):
+            w_rest = np.hstack([sw_by_bin[j] for j in range(n_bins) if j != i])
+            return _cdf_lookup(_weight_cdf(np.ravel(w_rest) / np.sum(w_rest)), uniforms[i][1])
+
+        with ThreadPoolExecutor(max_workers=max(1, min(os.cpu_count() or 1, 2 * n_bins))) as pool:
+            own_futures = [pool.submit(draw_own, i) for i in range(n_bins)]
+            rest_futures = [pool.submit(draw_rest, i) for i in range(n_bins)]
+            own_draws = [f.result() for f in own_futures]
+            rest_draws = [f.result() for f in rest_futures]
         directions, inside_edges, outside_edges = [], [], []
         for i in range(n_bins):
             own_rows = rows[i]
-            p_own = np.ravel(s_bins[i])
-            seeds = normalised(own_rows[_weighted_draw(rng, p_own, E)])
+            seeds = normalised(own_rows[own_draws[i][0]])
             # Sample the complement of bin i ("vstack of the other bins", :150-156) through row indices.
             others = [j for j in range(n_bins) if j != i]
-            w_rest = np.hstack([sw_by_bin[j] for j in others])
-            pick = _weighted_draw(rng, np.ravel(w_rest) / np.sum(w_rest), wide)
+            pick = rest_draws[i]
             offsets = np.concatenate([[0], np.cumsum(sizes[others])])
             which = np.searchsorted(offsets, pick, side="right") - 1
             rest_rows = np.array([rows[others[b]][k - offsets[b]] for b, k in zip(which, pick)])
             rest_sample = normalised(rest_rows)
             # Points of the complement closest to bin i, then points of bin i closest to those.
             outside = nearest_neighbours(seeds, rest_sample)
-            own_sample = normalised(own_rows[_weighted_draw(rng, p_own, wide)])
+            own_sample = normalised(own_rows[own_draws[i][1]])
             inside = nearest_neighbours(outside, own_sample)
             outside_edges.append(outside)
             inside_edges.append(inside)

@@ -175,7 +175,7 @@ def device_bin_location_spread(Xd, rows, s_bins, ctx=None):
         n_bs = [len(f) for f in flat]
         c1 = [min(max(pl[0] + 1, 0), nb - 1) for pl, nb in zip(plans, n_bs)]
         st1 = window(c1)
-        need2 = any(not ({pl[3], pl[3] + 1} & set(range(nb)) <= {c - 1, c, c + 1}) for pl, nb, c in zip(plans, n_bs, c1))
+        need2 = any(not ({r for r in (pl[3], pl[3] + 1) if 0 <= r < nb} <= {c - 1, c, c + 1}) for pl, nb, c in zip(plans, n_bs, c1))
         c2 = [min(max(pl[3] + 1, 0), nb - 1) for pl, nb in zip(plans, n_bs)] if need2 else c1
         st2 = window(c2) if need2 else st1
         centre_rows = []

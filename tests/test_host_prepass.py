@@ -179,3 +179,27 @@ def test_uniform_rank_plan_reproduces_the_reference_median():
         got = median_from_ranks(lambda r: srt[r], n_b, uniform_rank_plan(w, n_b))
         # same ranks, same formula; the reference's numba kernel may contract the last multiply-add
         assert np.max(np.abs(got - ref)) <= 4 * np.finfo(float).eps * max(1.0, np.max(np.abs(ref))), n_b
+
+
+def test_threaded_shuffle_split_equals_sklearn(monkeypatch):
+    """The conformal calibration split of a large fit (own permutation + threaded gathers) returns exactly what
+    sklearn.model_selection.train_test_split returns for the same arrays, train size and random state."""
+    from sklearn.model_selection import train_test_split
+
+    from neo_ls_svm_b200 import _neo_ls_svm as est
+
+    monkeypatch.setattr(est, "_THREADED_SPLIT_MIN_ROWS", 1000)
+    rng = np.random.default_rng(3)
+    n = 54_321
+    arrays = [rng.standard_normal(n), rng.standard_normal(n).astype(np.float32), rng.standard_normal(n), np.ones(n)]
+    for rs in (42, None, np.random.RandomState(7)):
+        rs_a, rs_b = (np.random.RandomState(7), np.random.RandomState(7)) if isinstance(rs, np.random.RandomState) else (rs, rs)
+        if rs is None:
+            np.random.seed(11)
+        ref = train_test_split(*arrays, train_size=1440, random_state=rs_a)
+        if rs is None:
+            np.random.seed(11)
+        got = est._shuffle_split(*arrays, train_size=1440, random_state=rs_b)
+        assert len(ref) == len(got) == 8
+        for a, b in zip(ref, got):
+            assert a.dtype == b.dtype and np.array_equal(a, b)
