@@ -544,13 +544,14 @@ def run_ours(args) -> None:
         # The three GEMM stages, each against the peak of the tensor path it runs on.  Algorithmic work (SURVEY.md §8d /
         # DESIGN.md §4): Gram 4m², projection 8m², sweep 4mG FP64 flop per row; on the INT8 core one FP64 multiply-add is
         # 28 exact INT8 digit-plane multiply-adds (7 planes per operand, levels p + q <= 6), so its INT8 work is 28 x that.
-        # dram traffic per launch (32,768-row chunk) from `ncu --set full` captures under profiles/ (r1_ncu_full_gemm_kernels.md,
-        # r2f_ncu_full_int8.md); None where no capture exists.
+        # `traffic`: dram__bytes_read.sum + dram__bytes_write.sum per launch (one 32,768-row chunk) from the `ncu --set full`
+        # captures summarised in profiles/r2g_ncu_full_int8.md (INT8 kernels, sweep) and profiles/r1_ncu_full_gemm_kernels.md.
         stage_defs = {
-            "gram": (4.0 * m * m, int8, "oz::gemm_kernel_i8<EpiGram>" if int8 else "gemm_kernel<MODE_COMPLEX, OpGram>", None),
+            "gram": (4.0 * m * m, int8, "oz::gemm_kernel_i8<EpiGram>" if int8 else "gemm_kernel<MODE_COMPLEX, OpGram>",
+                     1.6066e9 if int8 else None),
             "project": (8.0 * m * m, int8, "oz::gemm_kernel_i8<EpiProject> (T = φQ)" if int8 else "gemm_kernel<MODE_COMPLEX, OpProject> (T = φQ)",
-                        None if int8 else 1.0895e9),
-            "sweep": (4.0 * m * N_GAMMAS, False, "gemm_kernel<MODE_DUAL_A, OpSweep> (fused LOO residual / reduction)", None),
+                        1.0617e9 if int8 else 1.0895e9),
+            "sweep": (4.0 * m * N_GAMMAS, False, "gemm_kernel<MODE_DUAL_A, OpSweep> (fused LOO residual / reduction)", 0.8093e9),
         }
         stages = {}
         for name, (fpr, on_int8, kernel, traffic) in stage_defs.items():
