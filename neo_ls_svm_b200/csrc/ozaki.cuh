@@ -14,10 +14,10 @@
 //     already in the canonical K-major SWIZZLE_32B shared-memory image.  A pipeline stage (one k step of 32: 7 A
 //     tiles of 128 rows + 7 B tiles of 64 rows = 42 KB) is two contiguous blocks, fetched with two 1-D
 //     cp.async.bulk copies that complete on the stage's mbarrier.
-//   * persistent CTAs (one per SM), warp-specialised: warp 0 = bulk-copy producer (one lane), warp 1 = MMA issuer
-//     (one lane, 28 tcgen05.mma per stage, tcgen05.commit releases the stage; its descriptors must stay in UNIFORM
+//   * persistent CTAs (one per SM), warp-specialised: warp 0 = bulk-copy producer (one lane), warps 1-4 = MMA issuers
+//     (one lane each, 7 of the 28 tcgen05.mma per stage, tcgen05.commit releases the stage; descriptors must stay in UNIFORM
 //     registers — a 64-bit division feeding the loop bounds once turned every MMA into an ELECT + 4 R2UR.BROADCAST
-//     sequence and cost 25 % of the rate, so work indices are 32-bit), warps 2-9 = epilogue (tcgen05.ld,
+//     sequence and cost 25 % of the rate, so work indices are 32-bit), warps 5-12 = epilogue (tcgen05.ld,
 //     FP64 recombination, fused epilogue functor).  5 stages in flight; the accumulators are handed back to the
 //     MMA warp as soon as they are drained into registers, so the epilogue math and stores of tile i overlap the
 //     mainloop of tile i + 1.
@@ -40,7 +40,8 @@ constexpr int A_STAGE = S * A_TILE;
 constexpr int B_STAGE = S * B_TILE;
 constexpr int STAGE_BYTES = A_STAGE + B_STAGE;  // 43008
 constexpr int SMEM_BYTES = 1024 + NSTAGE * STAGE_BYTES;
-constexpr int THREADS = 320;       // producer warp, MMA warp, 8 epilogue warps
+constexpr int NISSUE = 4;          // MMA-issuing warps: issuer w owns the levels {6}, {5,0}, {4,1}, {3,2} (7 products each)
+constexpr int THREADS = 32 * (1 + NISSUE + 8);  // producer warp, MMA issuers, 8 epilogue warps
 constexpr int RADIX_BITS = 8;      // balanced base-256 digits
 constexpr int FRAC_BITS = RADIX_BITS * S;  // 56: more than the 53 bits of the FP64 operands
 constexpr uint32_t TMEM_COLS = 512;
@@ -307,6 +308,22 @@ __device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_
                "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
                : "memory");
 }
+// A operand from tensor memory (128 lanes x 8 columns per plane and k step), B from shared memory
+__device__ __forceinline__ void umma_i8_ta(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, 1, 0;\n tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem),
+               "r"(a_tmem), "l"(bdesc), "r"(IDESC)
+               : "memory");
+}
+// one [128 rows x 32 B] tile from shared memory into 8 TMEM columns (row r -> lane r)
+__device__ __forceinline__ void tmem_cp_tile(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+               "r"(0u)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -486,7 +503,14 @@ struct EpiGram {
   }
 };
 
-template <int LAYOUT, class Epi>
+// A_TMEM: the MMAs take their A operand from tensor memory.  At M = 128, N = 64 with both operands in shared memory a
+// k step moves 210 KB through the SM's 128 B/clk shared-memory port (28 x 6 KB of operand reads + the 42 KB the bulk
+// copies write) — the measured bound of the plain variant.  Copying each A plane once per k step into TMEM
+// (tcgen05.cp, 8 columns per plane: 448 + 56 = 504 of the 512 columns) cuts that to 126 KB.  Issuer w then owns the A
+// PLANES {0}, {1,6}, {2,5}, {3,4} (7 products each) instead of whole levels: its tcgen05.cp and the MMAs that read the
+// plane stay in one thread's program order, which is the only ordering tcgen05 guarantees.  Levels are then shared
+// between issuers, so no product may overwrite: the epilogue warps zero the accumulators (tcgen05.st) after draining.
+template <int LAYOUT, class Epi, bool A_TMEM = true>
 __global__ void __launch_bounds__(THREADS, 1) gemm_kernel_i8(GemmParams g, typename Epi::Params ep) {
   extern __shared__ uint8_t oz_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -500,9 +524,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel_i8(GemmParams g, typen
   if (tid == 32) {
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), NISSUE);  // one tcgen05.commit per issuer
     }
-    mbar_init(smem_u32(&tmem_full_bar), 1);
+    mbar_init(smem_u32(&tmem_full_bar), NISSUE);
     mbar_init(smem_u32(&tmem_empty_bar), 8);  // one arrival per epilogue warp
     mbar_fence_init();
   }
@@ -530,12 +554,20 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel_i8(GemmParams g, typen
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp <= NISSUE) {
+    // One issuing lane costs ~60 cycles per tcgen05.mma (ELECT / R2UR / UTCIMMA / branch chain) against the 48 the
+    // tensor pipe needs at this tile shape, so the 28 products are spread over NISSUE issuers.  An issuer owns WHOLE
+    // levels: the products of one accumulator then stay in one thread's program order, which is what makes the
+    // "first product of the tile overwrites" flag safe.
     if (lane == 0) {
+      const int w = warp - 1;
+      const int t_hi = 6 - w, t_lo = w == 0 ? -1 : w - 1;  // levels {6}, {5,0}, {4,1}, {3,2}
+      const int p_a = w, p_b = w == 0 ? -1 : 7 - w;          // A planes {0}, {1,6}, {2,5}, {3,4}
       uint32_t it = 0, tile_i = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tile_i) {
-        const Work wk = get_work(g, w);
-        mbar_wait(smem_u32(&tmem_empty_bar), (tile_i & 1) ^ 1);  // accumulators drained by the epilogue warps
+      for (int wi = blockIdx.x; wi < total_work; wi += gridDim.x, ++tile_i) {
+        const Work wk = get_work(g, wi);
+        // accumulators drained (A_TMEM: and zeroed, including once before the first tile) by the epilogue warps
+        mbar_wait(smem_u32(&tmem_empty_bar), A_TMEM ? (tile_i & 1) : ((tile_i & 1) ^ 1));
         tc_fence_after();
         for (int ks = wk.ks0; ks < wk.ks1; ++ks, ++it) {
           const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
@@ -543,25 +575,49 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel_i8(GemmParams g, typen
           tc_fence_after();
           const uint64_t da = smem_desc<LAYOUT>(smem_base + s * STAGE_BYTES);
           const uint64_t db = smem_desc<LAYOUT>(smem_base + s * STAGE_BYTES + A_STAGE);
+          if (A_TMEM) {
+#pragma unroll
+            for (int p = 0; p < S; ++p) {
+              if (p != p_a && p != p_b) continue;
+              tmem_cp_tile(tmem + (uint32_t)(S * TN + p * 8), da + (uint64_t)((p * A_TILE) >> 4));
+#pragma unroll
+              for (int q = 0; q < S; ++q)
+                if (p + q < S) umma_i8_ta(tmem + (uint32_t)((p + q) * TN), tmem + (uint32_t)(S * TN + p * 8), db + (uint64_t)((q * B_TILE) >> 4));
+            }
+          } else {
           const uint32_t acc0 = ks > wk.ks0 ? 1u : 0u;
 #pragma unroll
-          for (int p = 0; p < S; ++p)
+          for (int t = S - 1; t >= 0; --t) {
+            if (t != t_hi && t != t_lo) continue;
 #pragma unroll
-            for (int q = 0; p + q < S; ++q) {
-              // level t = p + q; its first product of the tile (p = 0) overwrites, everything else accumulates
-              umma_i8(tmem + (uint32_t)((p + q) * TN), da + (uint64_t)((p * A_TILE) >> 4), db + (uint64_t)((q * B_TILE) >> 4),
-                      p == 0 ? acc0 : 1u);
-            }
-          umma_commit(smem_u32(&empty_bar[s]));  // stage reusable once these MMAs have read it
+            for (int p = 0; p < S; ++p)
+              if (p <= t)  // level t = p + q; its first product of the tile (p = 0) overwrites, the rest accumulate
+                umma_i8(tmem + (uint32_t)(t * TN), da + (uint64_t)((p * A_TILE) >> 4), db + (uint64_t)(((t - p) * B_TILE) >> 4),
+                        p == 0 ? acc0 : 1u);
+          }
+          }
+          umma_commit(smem_u32(&empty_bar[s]));  // stage reusable once every issuer's MMAs have read it
         }
         umma_commit(smem_u32(&tmem_full_bar));
       }
     }
   } else {
-    const int e = warp - 2;
+    const int e = warp - 1 - NISSUE;
     const int quad = warp & 3;       // the TMEM lane quadrant this warp may access
     const int cb = (e >> 2) * 16;    // first of its 16 complex columns within the tile
     uint32_t tile_i = 0;
+    if (A_TMEM) {  // the first tile also starts from zeroed accumulators (fresh TMEM holds garbage)
+#pragma unroll
+      for (int t = 0; t < S; ++t) {
+        const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t * TN + cb);
+        tmem_st16_zero(taddr);
+        tmem_st16_zero(taddr + TN / 2);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar));
+    }
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tile_i) {
       const Work wk = get_work(g, w);
       mbar_wait(smem_u32(&tmem_full_bar), tile_i & 1);
@@ -576,6 +632,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel_i8(GemmParams g, typen
         tmem_ld16(taddr, ar);
         tmem_ld16(taddr + TN / 2, ai);
         tmem_ld_wait();
+        if (A_TMEM) {  // hand the accumulators back zeroed: every product of the next tile accumulates
+          tmem_st16_zero(taddr);
+          tmem_st16_zero(taddr + TN / 2);
+        }
         const double w = level_weight(t);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -583,6 +643,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel_i8(GemmParams g, typen
           si[j] = fma(i2d(ai[j]), w, si[j]);
         }
       }
+      if (A_TMEM) tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar));

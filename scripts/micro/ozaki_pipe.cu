@@ -31,7 +31,7 @@ struct Problem {
   std::vector<int> ex;
 };
 
-template <int LAYOUT>
+template <int LAYOUT, bool A_TMEM>
 static int run(Problem& pr, bool timing) {
   const int sms = 148;
   oz::basis_exponent_kernel<<<(pr.n_tiles * 32 + 7) / 8, 256>>>(pr.d_bt, pr.Np, pr.Dp, pr.D, pr.m, pr.n_tiles * 32, pr.eA, pr.d_ex, pr.d_cs);
@@ -42,12 +42,15 @@ static int run(Problem& pr, bool timing) {
   oz::GemmParams g{pr.d_a, pr.d_b, pr.nks, pr.row_blocks, pr.n_tiles, 0, pr.row_blocks * pr.n_tiles, 1, pr.nks, 0};
   const long long ld = pr.Np;
   oz::EpiStore::Params es{pr.rows, pr.m, pr.d_cs, pr.d_tr, pr.d_ti, ld};
-  CK(cudaFuncSetAttribute(oz::gemm_kernel_i8<LAYOUT, oz::EpiStore>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::SMEM_BYTES));
-  CK(cudaFuncSetAttribute(oz::gemm_kernel_i8<LAYOUT, oz::EpiProject>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(oz::gemm_kernel_i8<LAYOUT, oz::EpiStore, A_TMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(oz::gemm_kernel_i8<LAYOUT, oz::EpiProject, A_TMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::SMEM_BYTES));
   const int grid = (int)std::min<long long>((long long)pr.row_blocks * pr.n_tiles, sms);
   CK(cudaMemset(pr.d_tr, 0, (size_t)pr.rows * ld * 8));
   CK(cudaMemset(pr.d_ti, 0, (size_t)pr.rows * ld * 8));
-  oz::gemm_kernel_i8<LAYOUT, oz::EpiStore><<<grid, oz::THREADS, oz::SMEM_BYTES>>>(g, es);
+  if (A_TMEM)
+    oz::gemm_kernel_i8<LAYOUT, oz::EpiStore, true><<<grid, oz::THREADS, oz::SMEM_BYTES>>>(g, es);
+  else
+    oz::gemm_kernel_i8<LAYOUT, oz::EpiStore, false><<<grid, oz::THREADS, oz::SMEM_BYTES>>>(g, es);
   CK(cudaDeviceSynchronize());
   std::vector<double> tr((size_t)pr.rows * ld), ti((size_t)pr.rows * ld);
   CK(cudaMemcpy(tr.data(), pr.d_tr, tr.size() * 8, cudaMemcpyDeviceToHost));
@@ -102,7 +105,7 @@ static int run(Problem& pr, bool timing) {
     }
     worst = fmaxl(worst, fmaxl(fabsl(tr[(size_t)i * ld + j] - ref_r), fabsl(ti[(size_t)i * ld + j] - ref_i)) / bound);
   }
-  printf("layout %d: %d sampled entries, %lld differ from the host emulation; max |T - ref| / sum|a b| = %.2Le\n", LAYOUT, samples, mism, worst);
+  printf("A from %s, layout %d: %d sampled entries, %lld differ from the host emulation; max |T - ref| / sum|a b| = %.2Le\n", A_TMEM ? "TMEM" : "smem", LAYOUT, samples, mism, worst);
   if (timing) {
     cudaEvent_t e0, e1, e2, e3;
     cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
@@ -112,9 +115,9 @@ static int run(Problem& pr, bool timing) {
       cudaEventRecord(e0);
       oz::slice_rows_kernel<LAYOUT><<<sms * 16, 256>>>(pr.d_psi, 2LL * pr.Dp, pr.rows, pr.D, pr.Dp, scale, pr.nks, pr.row_blocks, pr.d_a);
       cudaEventRecord(e1);
-      oz::gemm_kernel_i8<LAYOUT, oz::EpiStore><<<grid, oz::THREADS, oz::SMEM_BYTES>>>(g, es);
+      oz::gemm_kernel_i8<LAYOUT, oz::EpiStore, A_TMEM><<<grid, oz::THREADS, oz::SMEM_BYTES>>>(g, es);
       cudaEventRecord(e2);
-      oz::gemm_kernel_i8<LAYOUT, oz::EpiProject><<<grid, oz::THREADS, oz::SMEM_BYTES>>>(g, epp);
+      oz::gemm_kernel_i8<LAYOUT, oz::EpiProject, A_TMEM><<<grid, oz::THREADS, oz::SMEM_BYTES>>>(g, epp);
       cudaEventRecord(e3);
       CK(cudaDeviceSynchronize());
       cudaEventElapsedTime(&ms_sl, e0, e1);
@@ -122,8 +125,8 @@ static int run(Problem& pr, bool timing) {
       cudaEventElapsedTime(&ms_pj, e2, e3);
     }
     const double flops = 8.0 * pr.rows * (double)pr.D * pr.m;
-    printf("layout %d: rows %d D %d m %d: slicing %.3f ms (%.0f GB/s), store-epilogue GEMM %.3f ms = %.1f TFLOP/s, project-epilogue GEMM %.3f ms = %.1f TFLOP/s FP64-equivalent (DMMA peak 37.1)\n",
-           LAYOUT, pr.rows, pr.D, pr.m, ms_sl, (pr.rows * 2.0 * pr.Dp * (8 + oz::S)) / ms_sl * 1e-6, ms_st, flops / ms_st * 1e-9, ms_pj, flops / ms_pj * 1e-9);
+    printf("A from %s, layout %d: rows %d D %d m %d: slicing %.3f ms (%.0f GB/s), store-epilogue GEMM %.3f ms = %.1f TFLOP/s, project-epilogue GEMM %.3f ms = %.1f TFLOP/s FP64-equivalent (DMMA peak 37.1)\n",
+           A_TMEM ? "TMEM" : "smem", LAYOUT, pr.rows, pr.D, pr.m, ms_sl, (pr.rows * 2.0 * pr.Dp * (8 + oz::S)) / ms_sl * 1e-6, ms_st, flops / ms_st * 1e-9, ms_pj, flops / ms_pj * 1e-9);
   }
   return mism == 0 ? 0 : 1;
 }
@@ -169,14 +172,14 @@ int main(int argc, char** argv) {
   {  // ragged: rows, D and m off every tile boundary
     Problem pr;
     make(pr, 1000, 100, 101);
-    rc |= run<6>(pr, false);
-    rc |= run<0>(pr, false) << 1;
+    rc |= run<6, true>(pr, false);
+    rc |= run<6, false>(pr, false) << 1;
   }
   {  // one projection chunk of C3
     Problem pr;
     make(pr, 32768, 1024, 1024);
-    rc |= run<6>(pr, true) << 2;
-    rc |= run<0>(pr, true) << 3;
+    rc |= run<6, true>(pr, true) << 2;
+    rc |= run<6, false>(pr, true) << 3;
   }
   printf("rc = %d\n", rc);
   return rc;
