@@ -497,7 +497,8 @@ def run_ours(args) -> None:
 
         api_fit(min(n, 50_000))  # warm-up: numba JIT of the host pre-pass, scratch allocation
         est, secs = api_fit(n)
-        fit_api = {"value": n / secs, "unit": "rows/s", "seconds": secs, "selected_gamma_index":
+        phases = dict(getattr(est, "fit_phases_", {}))
+        fit_api = {"value": n / secs, "unit": "rows/s", "seconds": secs, "phases_s": phases, "selected_gamma_index":
                    int(np.argmin(np.abs(est.γs_ - est.γ_))),
                    "includes": "validation, supervised affine pre-pass (host + GPU weighted-median kernels), ORF, "
                                "pageable H2D, stages 1-4c, D2H, conformal split"}

@@ -148,8 +148,7 @@ class PendingUpload:
         self._torch, self._X, self._scan, self._device = torch, X, scan_finite, device
         self._stream = torch.cuda.Stream(device)
         self._stream.wait_stream(torch.cuda.current_stream(device))  # the block may be recycled from queued work
-        self._Xd = torch.empty(X.shape, dtype=torch.float64, device=device)
-        self._finite = self._event = self._error = None
+        self._Xd = self._finite = self._event = self._error = None
         self._thread = threading.Thread(target=self._run, daemon=True)
         self._thread.start()
 
@@ -157,6 +156,8 @@ class PendingUpload:
         torch = self._torch
         try:
             with torch.cuda.stream(self._stream):
+                # allocated here, on the side stream: a fresh 2 GB cudaMalloc is not free either
+                self._Xd = torch.empty(self._X.shape, dtype=torch.float64, device=self._device)
                 src = torch.from_numpy(np.ascontiguousarray(self._X))
                 if src.dtype == torch.float64:
                     self._Xd.copy_(src)
@@ -175,6 +176,7 @@ class PendingUpload:
             if self._error is not None:
                 raise self._error
             self._torch.cuda.current_stream(self._device).wait_event(self._event)
+            self._Xd.record_stream(self._torch.cuda.current_stream(self._device))  # allocated on the side stream
             if self._scan and not bool(self._finite):
                 import sklearn
                 from sklearn.utils import assert_all_finite

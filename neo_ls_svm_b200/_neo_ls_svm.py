@@ -226,6 +226,9 @@ class NeoLSSVM(BaseEstimator):
     # ------------------------------------------------------------------------------------------
     def fit(self, X, y, sample_weight=None) -> "NeoLSSVM":
         """Fit this predictor."""
+        import time
+
+        marks = [("start", time.perf_counter())]  # host wall-clock marks of the phases, kept in `fit_phases_`
         # A large X is scanned for NaN/inf on the device, after the upload it needs anyway (0.2 s on the host at
         # n = 4M, d = 64); everything else about the validation, and the error raised, is sklearn's.
         device_scan = isinstance(X, np.ndarray) and X.size >= _DEVICE_FINITE_SCAN_MIN and X.dtype in (np.float64, np.float32)
@@ -259,6 +262,7 @@ class NeoLSSVM(BaseEstimator):
             y_ = y.astype(X.dtype)
         else:
             raise ValueError("Target type not supported")
+        marks.append(("validation", time.perf_counter()))
         self.dual_ = X.shape[0] <= 1024 if self.dual == "auto" else self.dual  # noqa: PLR2004
         self.primal_ = not self.dual_
         self.__dict__.pop(_DEVICE_STATE, None)
@@ -282,9 +286,12 @@ class NeoLSSVM(BaseEstimator):
             try:
                 # X, y and the weights were validated above; the nested transformers re-validate the same
                 # arrays, so their finiteness scans (0.7 s at n = 4M) are switched off for this scope.
+                marks.append(("upload_started", time.perf_counter()))
                 with sklearn.config_context(assume_finite=True):
                     self.primal_feature_map_.fit(X, y_, sample_weight_)
+                marks.append(("feature_map_fit", time.perf_counter()))
                 self.β̂_, self.γ_ = self._optimize_β̂_γ(X, y_, sample_weight_)
+                marks.append(("solve", time.perf_counter()))
             finally:
                 _affine.release_device_copy(X)
         else:
@@ -315,6 +322,8 @@ class NeoLSSVM(BaseEstimator):
         )
         self.conformal_l1_ = {"Δŷ": {}, "Δŷ/ŷ": {}}
         self.conformal_l2_ = {"Δŷ": {}, "Δŷ/ŷ": {}}
+        marks.append(("calibration_split", time.perf_counter()))
+        self.fit_phases_ = {name: t - marks[i][1] for i, (name, t) in enumerate(marks[1:])}  # seconds per phase
         return self
 
     # ------------------------------------------------------------------------------------------
