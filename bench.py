@@ -542,6 +542,7 @@ def run_ours(args) -> None:
         fit_tflops = n * flops_per_row(d, D, N_GAMMAS) * args.steps / (ms_total * 1e-3) / 1e12
         kernel_share = {k: v["ms"] for k, v in prof.items()}
         int8 = os.environ.get("NLS_GEMM", "ozaki") != "dmma"
+        int8_sweep = os.environ.get("NLS_GEMM", "ozaki") == "ozaki"
         # The three GEMM stages, each against the peak of the tensor path it runs on.  Algorithmic work (SURVEY.md §8d /
         # DESIGN.md §4): Gram 4m², projection 8m², sweep 4mG FP64 flop per row; on the INT8 core one FP64 multiply-add is
         # 28 exact INT8 digit-plane multiply-adds (7 planes per operand, levels p + q <= 6), so its INT8 work is 28 x that.
@@ -552,7 +553,9 @@ def run_ours(args) -> None:
                      1.6066e9 if int8 else None),
             "project": (8.0 * m * m, int8, "oz::gemm_kernel_i8<EpiProject> (T = φQ)" if int8 else "gemm_kernel<MODE_COMPLEX, OpProject> (T = φQ)",
                         1.0617e9 if int8 else 1.0895e9),
-            "sweep": (4.0 * m * N_GAMMAS, False, "gemm_kernel<MODE_DUAL_A, OpSweep> (fused LOO residual / reduction)", 0.8093e9),
+            "sweep": (4.0 * m * N_GAMMAS, int8_sweep,
+                      "oz::gemm_kernel_i8<EpiSweep> (fused LOO residual / reduction)" if int8_sweep
+                      else "gemm_kernel<MODE_DUAL_A, OpSweep> (fused LOO residual / reduction)", None if int8_sweep else 0.8093e9),
         }
         stages = {}
         for name, (fpr, on_int8, kernel, traffic) in stage_defs.items():

@@ -108,10 +108,11 @@ int nls_ctx_last_tridiagonal(nls_ctx* ctx, int n, double* d_host, double* e_host
  * 2 = auto (default) = 3 = the hand-written tridiagonalisation + divide and conquer + back-transformation
  * (csrc/hetrd.cuh, csrc/stedc.cuh).  Also selectable with NLS_EIG=jacobi|cusolver|dc. */
 int nls_ctx_set_eigensolver(nls_ctx* ctx, int kind);
-/* Which tensor-core path the eigenbasis projection T = phi Q of nls_primal_loo_sweep (_neo_ls_svm.py:134, :137) runs
- * on: 1 (default) = tcgen05.mma kind::i8 with TMEM accumulators, FP64-accurate through the Ozaki scheme (7 signed
- * base-128 digit planes per operand, 28 exact INT8 plane products, FP64 recombination; csrc/ozaki.cuh), 0 = FP64 DMMA
- * like every other stage.  Also selectable with NLS_GEMM=ozaki|dmma. */
+/* Which tensor-core path the GEMM stages run on.  2 (default) = the Gram (_neo_ls_svm.py:112-114), the eigenbasis
+ * projection T = phi Q (:134, :137), the gamma sweep (:147-161) and predict_std (:467-469) on tcgen05.mma kind::i8 with TMEM
+ * accumulators, FP64-accurate through the Ozaki scheme (7 balanced base-256 digit planes per operand, 28 exact INT8 plane
+ * products, FP64 recombination; csrc/ozaki.cuh); 1 = the same with the sweep on FP64 DMMA; 0 = FP64 DMMA everywhere.
+ * Also selectable with NLS_GEMM=ozaki|ozaki-dmma-sweep|dmma. */
 int nls_ctx_set_gemm_core(nls_ctx* ctx, int kind);
 /* Number of Jacobi sweeps the last nls_heev call needed (0 for cuSOLVER). */
 int nls_ctx_last_eig_sweeps(const nls_ctx* ctx);

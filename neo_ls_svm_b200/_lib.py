@@ -154,9 +154,9 @@ class Context:
         check(self.lib.nls_ctx_set_eigensolver(self.handle, {"jacobi": 0, "cusolver": 1, "auto": 2, "dc": 3}[kind]))
 
     def set_gemm_core(self, kind: str) -> None:
-        """'ozaki' (default): the projection T = φQ runs on the INT8 tensor cores (tcgen05, Ozaki scheme, FP64-accurate);
-        'dmma': FP64 DMMA like the other stages."""
-        check(self.lib.nls_ctx_set_gemm_core(self.handle, {"dmma": 0, "ozaki": 1}[kind]))
+        """'ozaki' (default): Gram, projection, γ sweep and predict_std run on the INT8 tensor cores (tcgen05, Ozaki scheme,
+        FP64-accurate); 'ozaki-dmma-sweep': the sweep stays on FP64 DMMA; 'dmma': FP64 DMMA everywhere."""
+        check(self.lib.nls_ctx_set_gemm_core(self.handle, {"dmma": 0, "ozaki-dmma-sweep": 1, "ozaki": 2}[kind]))
 
     def last_eig_sweeps(self) -> int:
         return int(self.lib.nls_ctx_last_eig_sweeps(self.handle))

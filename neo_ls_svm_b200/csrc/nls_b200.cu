@@ -112,8 +112,9 @@ struct nls_ctx {
   DevBuf d_xpad, d_xq, d_norm, d_fm, d_sq, d_sqt, d_g1, d_ab, d_ra, d_vec, d_ng, d_kq, d_btp;
   // INT8 (Ozaki) GEMM core of the projection (csrc/ozaki.cuh): digit planes of the chunk / of the basis, per-column
   // exponents and recombination scales
-  DevBuf oz_a, oz_b, oz_g, oz_small;
-  int gemm_core = 1;      // 1: projection on tcgen05 kind::i8 (Ozaki scheme, default), 0: everything on DMMA
+  DevBuf oz_a, oz_b, oz_g, oz_small, oz_sa, oz_sb, oz_ssmall;
+  int gemm_core = 2;      // 2 (default): Gram, projection, predict_std AND the γ sweep on tcgen05 kind::i8 (Ozaki scheme),
+                          // 1: the sweep stays on DMMA, 0: everything on DMMA
   bool oz_attr = false;   // dynamic shared memory opt-in of the INT8 kernels done on this device
   int dual_n = 0;
   const void* dual_y = nullptr;   // the y / sn the pending dual sweep was run with: nls_dual_finalize must be given
@@ -360,7 +361,8 @@ extern "C" int nls_ctx_create(int device, void* stream, nls_ctx** out) {
   if (env && strcmp(env, "dc") == 0) ctx->eig_kind = 3;
   env = getenv("NLS_GEMM");
   if (env && strcmp(env, "dmma") == 0) ctx->gemm_core = 0;
-  if (env && strcmp(env, "ozaki") == 0) ctx->gemm_core = 1;
+  if (env && strcmp(env, "ozaki") == 0) ctx->gemm_core = 2;
+  if (env && strcmp(env, "ozaki-dmma-sweep") == 0) ctx->gemm_core = 1;
   env = getenv("NLS_JACOBI_INNER");
   if (env && atoi(env) > 0) ctx->jac_inner = atoi(env);
   env = getenv("NLS_CHUNK_ROWS");
@@ -389,7 +391,7 @@ extern "C" int nls_ctx_destroy(nls_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->xc, &ctx->wt, &ctx->psi, &ctx->psiT, &ctx->pu, &ctx->bt, &ctx->rt, &ctx->small,
                     &ctx->part, &ctx->gram_ws, &ctx->border, &ctx->rowtmp, &ctx->solver_ws, &ctx->solver_mat,
                     &ctx->jac_mat, &ctx->jac_small, &ctx->bs_part, &ctx->bs_keys, &ctx->dotpart, &ctx->d_xpad, &ctx->d_xq, &ctx->d_norm, &ctx->d_fm, &ctx->d_sq, &ctx->d_sqt, &ctx->d_g1,
-                    &ctx->d_ab, &ctx->d_ra, &ctx->d_vec, &ctx->d_ng, &ctx->d_kq, &ctx->d_btp, &ctx->oz_a, &ctx->oz_b, &ctx->oz_g, &ctx->oz_small};
+                    &ctx->d_ab, &ctx->d_ra, &ctx->d_vec, &ctx->d_ng, &ctx->d_kq, &ctx->d_btp, &ctx->oz_a, &ctx->oz_b, &ctx->oz_g, &ctx->oz_small, &ctx->oz_sa, &ctx->oz_sb, &ctx->oz_ssmall};
   for (DevBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   {
@@ -562,7 +564,7 @@ static int gram_impl(nls_ctx* ctx, const double* X, const double* y, const doubl
   int n_tiles = 0;
   for (int kb = 0; kb < tiles_m; ++kb) n_tiles += std::max(0, tiles_n - 2 * kb);
   // INT8 (Ozaki) core: 128-feature row blocks x 32-feature column tiles, upper triangle only; the chunk's rows are K.
-  const bool use_oz = ctx->gemm_core == 1;
+  const bool use_oz = ctx->gemm_core >= 1;
   const int oz_rb = (D + oz::TM - 1) / oz::TM, oz_nt = (D + oz::TN / 2 - 1) / (oz::TN / 2);
   int oz_tiles = 0;
   for (int kb = 0; kb < oz_rb; ++kb) oz_tiles += oz_nt - 4 * kb;
@@ -606,7 +608,7 @@ static int gram_impl(nls_ctx* ctx, const double* X, const double* y, const doubl
       ProfScope scope(ctx, NLS_PROF_GRAM);
       const int ks_per_split = (2 * nksR + splits - 1) / splits;
       oz::GemmParams gp{(const int8_t*)ctx->oz_a.p, (const int8_t*)ctx->oz_g.p, 2 * nksR, oz_rb, oz_nt, 1, oz_tiles,
-                        (2 * nksR + ks_per_split - 1) / ks_per_split, ks_per_split, 0};
+                        (2 * nksR + ks_per_split - 1) / ks_per_split, ks_per_split, 0, 1, 1 << 30, 0};
       oz::EpiGram::Params ep{D, sc + 1, (double*)ctx->gram_ws.p};
       const int grid = (int)std::min<long long>((long long)gp.tiles * gp.splits, ctx->sm_count);
       oz::gemm_kernel_i8<oz::IMAGE, oz::EpiGram><<<grid, oz::THREADS, oz::SMEM_BYTES, ctx->stream>>>(gp, ep);
@@ -978,8 +980,9 @@ extern "C" int nls_ctx_set_eigensolver(nls_ctx* ctx, int kind) {
 extern "C" int nls_ctx_last_eig_sweeps(const nls_ctx* ctx) { return ctx ? ctx->eig_sweeps : 0; }
 
 extern "C" int nls_ctx_set_gemm_core(nls_ctx* ctx, int kind) {
-  if (!ctx || kind < 0 || kind > 1)
-    return fail(NLS_ERR_INVALID, "GEMM core must be 0 (FP64 DMMA everywhere) or 1 (projection on the INT8 tensor cores, Ozaki scheme)");
+  if (!ctx || kind < 0 || kind > 2)
+    return fail(NLS_ERR_INVALID, "GEMM core must be 0 (FP64 DMMA everywhere), 1 (Gram / projection / predict_std on the INT8 "
+                                 "tensor cores, Ozaki scheme) or 2 (the γ sweep as well)");
   ctx->gemm_core = kind;
   return NLS_OK;
 }
@@ -1189,12 +1192,14 @@ struct OzBasis {
 
 // The projection-type products run on the INT8 core when the context says so and K fits the INT32 accumulators.
 static bool oz_usable(const nls_ctx* ctx, const MapGeom& g) {
-  return ctx->gemm_core == 1 && oz::feature_ksteps(g.D) * oz::KS <= oz::MAX_K && tail_split(g.m) > 0;
+  return ctx->gemm_core >= 1 && oz::feature_ksteps(g.D) * oz::KS <= oz::MAX_K && tail_split(g.m) > 0;
 }
 
 static int oz_attr(nls_ctx* ctx) {
   if (ctx->oz_attr) return NLS_OK;
   CUDA_TRY(cudaFuncSetAttribute(oz::gemm_kernel_i8<oz::IMAGE, oz::EpiVariance>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                oz::SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(oz::gemm_kernel_i8<oz::IMAGE, oz::EpiSweep>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 oz::SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(oz::gemm_kernel_i8<oz::IMAGE, oz::EpiProject>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 oz::SMEM_BYTES));
@@ -1246,11 +1251,90 @@ static int oz_project_chunk(nls_ctx* ctx, const MapGeom& g, const BasisScratch& 
   const int row_blocks = (rows + oz::TM - 1) / oz::TM;
   NLS_TRY(oz_slice_chunk(ctx, g, ob, rows));
   ProfScope scope(ctx, NLS_PROF_PROJECT);
-  oz::GemmParams gp{(const int8_t*)ctx->oz_a.p, ob.planes, ob.nks, row_blocks, ob.n_tiles, 0, row_blocks * ob.n_tiles, 1, ob.nks, 0};
+  oz::GemmParams gp{(const int8_t*)ctx->oz_a.p, ob.planes, ob.nks, row_blocks, ob.n_tiles, 0, row_blocks * ob.n_tiles, 1, ob.nks, 0, 1, 1 << 30, 0};
   oz::EpiProject::Params ep{rows, cols, ob.colscale, bs.bias_r, bs.bias_i, bs.v_r, bs.v_i, inv_c, P, U, g.ldp};
   const int grid = (int)std::min<long long>((long long)row_blocks * ob.n_tiles, ctx->sm_count);
   oz::gemm_kernel_i8<oz::IMAGE, oz::EpiProject><<<grid, oz::THREADS, oz::SMEM_BYTES, ctx->stream>>>(gp, ep);
   return check_launch(ctx, "oz::gemm_kernel_i8");
+}
+
+// γ sweep on the INT8 core: operands that do not depend on the chunk (column scalings, digit planes of r').
+struct OzSweep {
+  int G, m, ngrp, rb_per_group, row_blocks, nks;
+  long long ldk;
+  const double *d, *inv_d, *ascale;
+  const int8_t* a_planes;
+  int* ex_pu;
+  double *pscale, *uscale;
+};
+constexpr int OZ_SWEEP_GROUPS = 2;  // γ groups with their own column scaling (scripts/sweep_int8_study.py: 1 already suffices)
+
+static int oz_prep_sweep(nls_ctx* ctx, const MapGeom& g, const double* gammas, const double* lam, int G, OzSweep* out) {
+  NLS_TRY(oz_attr(ctx));
+  OzSweep o{};
+  o.G = G;
+  o.m = g.m;
+  o.row_blocks = (G + oz::TM - 1) / oz::TM;
+  o.rb_per_group = (o.row_blocks + OZ_SWEEP_GROUPS - 1) / OZ_SWEEP_GROUPS;
+  o.ngrp = (o.row_blocks + o.rb_per_group - 1) / o.rb_per_group;
+  o.nks = (g.m + oz::KS - 1) / oz::KS;
+  o.ldk = (long long)o.nks * oz::KS;
+  const long long cap = ctx->chunk_rows;
+  // small arrays: d, inv_d [ngrp][ldk]; ascale [G]; pscale, uscale [cap][ngrp]; exA [G]; ex_pu [cap][ngrp][2]
+  const size_t n_d = (size_t)o.ngrp * o.ldk, n_g = (size_t)round_up(G, 2), n_pu = (size_t)cap * o.ngrp;
+  NLS_TRY(ensure(ctx, ctx->oz_ssmall, (2 * n_d + n_g + 2 * n_pu) * 8 + (n_g + 2 * n_pu) * 4));
+  double* base = (double*)ctx->oz_ssmall.p;
+  double* d = base;
+  double* inv_d = d + n_d;
+  double* ascale = inv_d + n_d;
+  o.pscale = ascale + n_g;
+  o.uscale = o.pscale + n_pu;
+  int* exA = (int*)(o.uscale + n_pu);
+  o.ex_pu = exA + n_g;
+  NLS_TRY(ensure(ctx, ctx->oz_sa, (size_t)o.row_blocks * o.nks * oz::A_STAGE));
+  NLS_TRY(ensure(ctx, ctx->oz_sb, (size_t)((cap + oz::TN / 2 - 1) / (oz::TN / 2)) * o.ngrp * o.nks * oz::B_STAGE));
+  ProfScope scope(ctx, NLS_PROF_SLICE);
+  oz::sweep_groups_kernel<<<o.ngrp, 256, 0, ctx->stream>>>(gammas, lam, G, g.m, o.ngrp, o.rb_per_group, o.ldk, d, inv_d);
+  NLS_TRY(check_launch(ctx, "oz::sweep_groups_kernel"));
+  oz::rgamma_exponent_kernel<<<(G + 7) / 8, 256, 0, ctx->stream>>>(gammas, lam, d, G, g.m, o.rb_per_group, o.ldk, exA, ascale);
+  NLS_TRY(check_launch(ctx, "oz::rgamma_exponent_kernel"));
+  oz::slice_rgamma_kernel<oz::IMAGE><<<grid_for((long long)o.row_blocks * o.nks * oz::TM * 2), 256, 0, ctx->stream>>>(
+      gammas, lam, d, exA, G, g.m, o.rb_per_group, o.ldk, o.nks, o.row_blocks, (int8_t*)ctx->oz_sa.p);
+  NLS_TRY(check_launch(ctx, "oz::slice_rgamma_kernel"));
+  o.d = d;
+  o.inv_d = inv_d;
+  o.ascale = ascale;
+  o.a_planes = (const int8_t*)ctx->oz_sa.p;
+  *out = o;
+  return NLS_OK;
+}
+
+// num / den / LOO error sums (and the σ² stash) of one chunk from its P, U (row pitch ldp).
+static int oz_sweep_chunk(nls_ctx* ctx, const MapGeom& g, const OzSweep& o, int rows, const double* P, const double* U,
+                          const double* y, const double* s, int is_classifier, double* den_out, double* sums_out) {
+  const int n_tiles = (rows + oz::TN / 2 - 1) / (oz::TN / 2);
+  NLS_TRY(ensure(ctx, ctx->part, (size_t)2 * ((ctx->chunk_rows + oz::TN / 2 - 1) / (oz::TN / 2)) * 3 * o.G * 8));
+  {
+    ProfScope scope(ctx, NLS_PROF_SLICE);
+    oz::pu_exponent_kernel<<<(rows + 7) / 8, 256, 0, ctx->stream>>>(P, U, g.ldp, rows, g.m, o.inv_d, o.ngrp, o.ldk, o.ex_pu, o.pscale,
+                                                                  o.uscale);
+    NLS_TRY(check_launch(ctx, "oz::pu_exponent_kernel"));
+    oz::slice_pu_kernel<oz::IMAGE><<<grid_for((long long)n_tiles * o.ngrp * o.nks * oz::TN * 2), 256, 0, ctx->stream>>>(
+        P, U, g.ldp, rows, g.m, o.inv_d, o.ex_pu, o.ngrp, o.ldk, o.nks, n_tiles, (int8_t*)ctx->oz_sb.p);
+    NLS_TRY(check_launch(ctx, "oz::slice_pu_kernel"));
+  }
+  {
+    ProfScope scope(ctx, NLS_PROF_SWEEP);
+    oz::GemmParams gp{o.a_planes, (const int8_t*)ctx->oz_sb.p, o.nks, o.row_blocks, n_tiles, 0, o.row_blocks * n_tiles, 1, o.nks, 0,
+                      o.ngrp, o.rb_per_group, 1};
+    oz::EpiSweep::Params ep{rows, o.G, o.ngrp, o.rb_per_group, o.ascale, o.pscale, o.uscale, y, s, is_classifier,
+                            (double*)ctx->part.p, den_out, (long long)o.G};
+    const int grid = (int)std::min<long long>((long long)gp.tiles, ctx->sm_count);
+    oz::gemm_kernel_i8<oz::IMAGE, oz::EpiSweep><<<grid, oz::THREADS, oz::SMEM_BYTES, ctx->stream>>>(gp, ep);
+    NLS_TRY(check_launch(ctx, "oz::gemm_kernel_i8<EpiSweep>"));
+  }
+  sweep_reduce_kernel<<<(3 * o.G + 255) / 256, 256, 0, ctx->stream>>>((const double*)ctx->part.p, 2 * n_tiles, o.G, sums_out);
+  return check_launch(ctx, "sweep_reduce_kernel");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1284,6 +1368,9 @@ extern "C" int nls_primal_loo_sweep(nls_ctx* ctx, const double* X, const double*
   const bool use_oz = oz_usable(ctx, g);
   OzBasis oz{};
   if (use_oz) NLS_TRY(oz_prep_basis(ctx, g, bs, tail_split(g.m), &oz));
+  const bool use_oz_sweep = ctx->gemm_core >= 2 && g.m <= oz::MAX_K;
+  OzSweep ozs{};
+  if (use_oz_sweep) NLS_TRY(oz_prep_sweep(ctx, g, gammas, lam, G, &ozs));
   for (int64_t i0 = 0; i0 < n; i0 += cap) {
     const int rows = (int)std::min<int64_t>(cap, n - i0);
     const int mtiles = (rows + BM - 1) / BM;
@@ -1335,6 +1422,11 @@ extern "C" int nls_primal_loo_sweep(nls_ctx* ctx, const double* X, const double*
           bs.v_r, bs.v_i, inv_c, P, U, g.ldp, nullptr, nullptr);
       NLS_TRY(check_launch(ctx, "project_tail_kernel"));
     }
+    if (use_oz_sweep) {
+      NLS_TRY(oz_sweep_chunk(ctx, g, ozs, rows, P, U, y + i0, s + i0, is_classifier, sigma2_stash ? sigma2_stash + i0 * G : nullptr,
+                             sums_out));
+      continue;
+    }
     OpSweep::Params sp;
     sp.A = Operand{P, g.ldp, (int)(cap + rows), g.m, (int)cap, 0};
     sp.B = Operand{(const double*)ctx->rt.p, g.ldp, G, g.m, 0, 0};
@@ -1370,7 +1462,7 @@ static int variance_chunk(nls_ctx* ctx, const MapGeom& g, const BasisScratch& bs
     {
       ProfScope scope(ctx, NLS_PROF_VARIANCE);
       oz::GemmParams gp{(const int8_t*)ctx->oz_a.p, ob->planes, ob->nks, row_blocks, ob->n_tiles, 0, row_blocks * ob->n_tiles,
-                        1, ob->nks, b_upper ? 1 : 0};
+                        1, ob->nks, b_upper ? 1 : 0, 1, 1 << 30, 0};
       oz::EpiVariance::Params ep{rows, full_cols, ob->colscale, bs.bias_r, bs.bias_i, bs.w, (double*)ctx->part.p, cap};
       const int grid = (int)std::min<long long>((long long)row_blocks * ob->n_tiles, ctx->sm_count);
       oz::gemm_kernel_i8<oz::IMAGE, oz::EpiVariance><<<grid, oz::THREADS, oz::SMEM_BYTES, ctx->stream>>>(gp, ep);

@@ -297,6 +297,150 @@ __global__ void __launch_bounds__(256) slice_gram_kernel(const double* __restric
   }
 }
 
+// ---- γ sweep operands --------------------------------------------------------------------------------
+// Column scaling per γ group: gref = the smallest γ of the group's 128-γ blocks, d[grp][k] = |λ_k| + gref.
+__global__ void sweep_groups_kernel(const double* __restrict__ gammas, const double* __restrict__ lam, int G, int m, int ngrp,
+                                    int rb_per_group, long long ldk, double* __restrict__ d, double* __restrict__ inv_d) {
+  const int grp = blockIdx.x;
+  const int g0 = grp * rb_per_group * TM, g1 = min(G, g0 + rb_per_group * TM);
+  double gref = gammas[g0];
+  for (int g = g0 + 1; g < g1; ++g) gref = fmin(gref, gammas[g]);
+  for (int k = threadIdx.x; k < ldk; k += blockDim.x) {
+    const double dk = k < m ? fabs(lam[k]) + gref : 1.0;
+    d[grp * ldk + k] = dk;
+    inv_d[grp * ldk + k] = 1.0 / dk;
+  }
+}
+
+// r'_kg = d_k / (γ_g + λ_k): one warp per γ finds the row exponent; ascale[g] = 2^e.
+__global__ void __launch_bounds__(256) rgamma_exponent_kernel(const double* __restrict__ gammas, const double* __restrict__ lam,
+                                                              const double* __restrict__ d, int G, int m, int rb_per_group,
+                                                              long long ldk, int* __restrict__ ex, double* __restrict__ ascale) {
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (g >= G) return;
+  const double* dg = d + (long long)(g / (rb_per_group * TM)) * ldk;
+  const double gam = gammas[g];
+  double amax = 0.0;
+  for (int k = lane; k < m; k += 32) amax = fmax(amax, fabs(dg[k] / (gam + lam[k])));
+#pragma unroll
+  for (int o = 16; o; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if (lane == 0) {
+    const int e = scale_exponent(amax);
+    ex[g] = e;
+    ascale[g] = ldexp(1.0, e);
+  }
+}
+
+// A side: digit planes of r' [γ block of 128][k step][plane][128 x 32 B]
+template <int LAYOUT>
+__global__ void __launch_bounds__(256) slice_rgamma_kernel(const double* __restrict__ gammas, const double* __restrict__ lam,
+                                                           const double* __restrict__ d, const int* __restrict__ ex, int G, int m,
+                                                           int rb_per_group, long long ldk, int nks, int row_blocks,
+                                                           int8_t* __restrict__ out) {
+  const long long items = (long long)row_blocks * nks * TM * 2;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(it & 1);
+    const int r = (int)((it >> 1) & (TM - 1));
+    const long long blk = it >> 8;
+    const int ks = (int)(blk % nks);
+    const int gb = (int)(blk / nks);
+    const int g = gb * TM + r;
+    const int k0 = ks * KS + c * 16;
+    uint32_t w[S][4];
+#pragma unroll
+    for (int p = 0; p < S; ++p)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[p][j] = 0;
+    if (g < G && k0 < m) {
+      const double* dg = d + (long long)(gb / rb_per_group) * ldk;
+      const double gam = gammas[g];
+      const double scale = ldexp(1.0, FRAC_BITS - ex[g]);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int k = k0 + i;
+        const double v = k < m ? dg[k] / (gam + lam[k]) : 0.0;
+        const unsigned long long q = digit_bytes(quantise(v, scale));
+#pragma unroll
+        for (int p = 0; p < S; ++p) w[p][i >> 2] |= ((uint32_t)(q >> (8 * (S - 1 - p))) & 0xff) << (8 * (i & 3));
+      }
+    }
+    int8_t* dst = out + (blk * S) * A_TILE + tile_off<LAYOUT>(r, c);
+#pragma unroll
+    for (int p = 0; p < S; ++p) *reinterpret_cast<uint4*>(dst + (long long)p * A_TILE) = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
+  }
+}
+
+// B side, pass 1: row exponents of P' = P / d and U' = U / d per (data row, group); one warp per data row.
+__global__ void __launch_bounds__(256) pu_exponent_kernel(const double* __restrict__ P, const double* __restrict__ U, long long ld, int rows,
+                                                          int m, const double* __restrict__ inv_d, int ngrp, long long ldk,
+                                                          int* __restrict__ ex /*[rows][ngrp][2]*/, double* __restrict__ pscale,
+                                                          double* __restrict__ uscale) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= rows) return;
+  for (int grp = 0; grp < ngrp; ++grp) {
+    const double* id = inv_d + grp * ldk;
+    double pm = 0.0, um = 0.0;
+    for (int k = lane; k < m; k += 32) {
+      pm = fmax(pm, fabs(P[(long long)i * ld + k] * id[k]));
+      um = fmax(um, fabs(U[(long long)i * ld + k] * id[k]));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      pm = fmax(pm, __shfl_xor_sync(0xffffffffu, pm, o));
+      um = fmax(um, __shfl_xor_sync(0xffffffffu, um, o));
+    }
+    if (lane == 0) {
+      const int ep = scale_exponent(pm), eu = scale_exponent(um);
+      ex[((long long)i * ngrp + grp) * 2] = ep;
+      ex[((long long)i * ngrp + grp) * 2 + 1] = eu;
+      pscale[(long long)i * ngrp + grp] = ldexp(1.0, ep);
+      uscale[(long long)i * ngrp + grp] = ldexp(1.0, eu);
+    }
+  }
+}
+
+// B side, pass 2: digit planes [tile of 32 data rows][group][k step][plane][64 x 32 B]; tile rows 0..31 = P', 32..63 = U'.
+template <int LAYOUT>
+__global__ void __launch_bounds__(256) slice_pu_kernel(const double* __restrict__ P, const double* __restrict__ U, long long ld, int rows,
+                                                       int m, const double* __restrict__ inv_d, const int* __restrict__ ex, int ngrp,
+                                                       long long ldk, int nks, int n_tiles, int8_t* __restrict__ out) {
+  const long long items = (long long)n_tiles * ngrp * nks * TN * 2;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(it & 1);
+    const int r = (int)((it >> 1) & (TN - 1));
+    const long long blk = it >> 7;  // (nb * ngrp + grp) * nks + ks
+    const int ks = (int)(blk % nks);
+    const long long tg = blk / nks;
+    const int grp = (int)(tg % ngrp);
+    const long long nb = tg / ngrp;
+    const long long i = nb * (TN / 2) + (r & (TN / 2 - 1));
+    const int which = r >> 5;  // 0: P', 1: U'
+    const int k0 = ks * KS + c * 16;
+    uint32_t w[S][4];
+#pragma unroll
+    for (int p = 0; p < S; ++p)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[p][j] = 0;
+    if (i < rows && k0 < m) {
+      const double* src = (which ? U : P) + i * ld + k0;
+      const double* id = inv_d + grp * ldk + k0;
+      const double scale = ldexp(1.0, FRAC_BITS - ex[(i * ngrp + grp) * 2 + which]);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const double v = k0 + j < m ? src[j] * id[j] : 0.0;
+        const unsigned long long q = digit_bytes(quantise(v, scale));
+#pragma unroll
+        for (int p = 0; p < S; ++p) w[p][j >> 2] |= ((uint32_t)(q >> (8 * (S - 1 - p))) & 0xff) << (8 * (j & 3));
+      }
+    }
+    int8_t* dst = out + (blk * S) * B_TILE + tile_off<LAYOUT>(r, c);
+#pragma unroll
+    for (int p = 0; p < S; ++p) *reinterpret_cast<uint4*>(dst + (long long)p * B_TILE) = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
+  }
+}
+
 // ---- pipeline primitives --------------------------------------------------------------------------
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
@@ -349,6 +493,9 @@ struct GemmParams {
   int splits;        // the K range is cut into `splits` work items per tile (each with its own epilogue slot) ...
   int ks_per_split;  // ... of this many k steps
   int upper_k;       // 1: B is upper triangular in (feature, column): column tile nb needs ks < 2 (nb + 1) only
+  int b_groups;      // B holds b_groups images per column tile; row block rb uses image rb / rb_per_group (γ sweep) ...
+  int rb_per_group;  // ... (1 image: b_groups = 1, rb_per_group >= row_blocks)
+  int rb_fastest;    // 1: work items run column tile by column tile with the row block fastest (few row blocks, many tiles)
 };
 
 struct Work {
@@ -360,7 +507,10 @@ __device__ __forceinline__ Work get_work(const GemmParams& g, int w) {
   Work k;
   k.split = w / g.tiles;
   int idx = w - k.split * g.tiles;
-  if (!g.upper) {
+  if (g.rb_fastest) {
+    k.nb = idx / g.row_blocks;
+    k.rb = idx - k.nb * g.row_blocks;
+  } else if (!g.upper) {
     k.rb = idx / g.n_tiles;
     k.nb = idx % g.n_tiles;
   } else {
@@ -503,6 +653,60 @@ struct EpiGram {
   }
 };
 
+// Stage 4b on the INT8 core.  Roles are transposed with respect to the DMMA sweep: the 128 tile rows (TMEM lanes) are
+// γ values, the B tile holds 32 data rows twice — rows 0..31 the scaled numerator operand P', rows 32..63 the scaled
+// leverage operand U' — so a thread owns num and den of its (γ, data row) pairs:
+//   num_ig = sum_k P'_ik r'_kg,  den_ig = sum_k U'_ik r'_kg,   P' = P / d,  U' = U / d,  r'_kg = d_k / (γ_g + λ_k),
+// d_k = |λ_k| + γ_ref(group of γ_g).  The two-sided scaling is what makes a fixed-point split FP64-accurate here: r'
+// lies in (γ_ref / γ_g, 1] and P'_ik is the k-th term of the prediction at γ_ref, so both operands are well scaled
+// along k (scripts/sweep_int8_study.py; the plain split loses 1e-10 on ill-conditioned fits).  Fused: LOO residual,
+// classifier clip, |.|, s-weighted partial sums over the thread's 16 data rows (fixed order; sweep_reduce_kernel adds
+// the (tile, half) partials in order), and the σ² stash.   reference: _neo_ls_svm.py:147-161.
+struct EpiSweep {
+  struct Params {
+    int n_rows, G, ngrp, rb_per_group;
+    const double* ascale;  // [G] 2^e of the r' row of every γ
+    const double* pscale;  // [rows][ngrp] 2^e of the P' row
+    const double* uscale;  // [rows][ngrp] 2^e of the U' row
+    const double* y;
+    const double* s;
+    int is_classifier;
+    double* part;          // [2 n_tiles][3][G]
+    double* den_out;       // optional σ² stash (U rγ), row pitch den_ld
+    long long den_ld;
+  };
+  static __device__ __forceinline__ void apply(const Params& p, const Work& wk, long long row, int col0, const double (&sr)[16],
+                                               const double (&si)[16]) {
+    const int g = (int)row;
+    if (g >= p.G) return;
+    const int grp = wk.rb / p.rb_per_group;
+    const double as = p.ascale[g];
+    double e_abs = 0.0, e_cnt = 0.0, e_hng = 0.0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int i = col0 + j;
+      if (i < p.n_rows) {
+        const double num = sr[j] * (as * p.pscale[(long long)i * p.ngrp + grp]);
+        const double den = si[j] * (as * p.uscale[(long long)i * p.ngrp + grp]);
+        if (p.den_out) p.den_out[(long long)i * p.den_ld + g] = den;
+        const double yi = p.y[i], wi = p.s[i];
+        double loo = (num - yi) / (1.0 - wi * wi * den);
+        if (p.is_classifier && ((yi > 0.0 && loo > 0.0) || (yi < 0.0 && loo < 0.0))) loo = 0.0;
+        const double a = fabs(loo);
+        e_abs += wi * a;
+        if (p.is_classifier) {
+          e_cnt += (a >= 1.0) ? wi : 0.0;
+          e_hng += wi * fmax(0.0, a - 1.0);
+        }
+      }
+    }
+    double* o = p.part + (long long)(2 * wk.nb + ((col0 >> 4) & 1)) * 3 * p.G + g;
+    o[0] = e_abs;
+    o[p.G] = e_cnt;
+    o[2 * p.G] = e_hng;
+  }
+};
+
 // A_TMEM: the MMAs take their A operand from tensor memory.  At M = 128, N = 64 with both operands in shared memory a
 // k step moves 210 KB through the SM's 128 B/clk shared-memory port (28 x 6 KB of operand reads + the 42 KB the bulk
 // copies write) — the measured bound of the plain variant.  Copying each A plane once per k step into TMEM
@@ -543,7 +747,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel_i8(GemmParams g, typen
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const Work wk = get_work(g, w);
         const int8_t* a = g.A + (long long)wk.rb * g.nks * (long long)A_STAGE;
-        const int8_t* b = g.B + (long long)wk.nb * g.nks * (long long)B_STAGE;
+        const int8_t* b = g.B + ((long long)wk.nb * g.b_groups + wk.rb / g.rb_per_group) * g.nks * (long long)B_STAGE;
         for (int ks = wk.ks0; ks < wk.ks1; ++ks, ++it) {
           const uint32_t s = it % NSTAGE, ph = (it / NSTAGE) & 1;
           mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);

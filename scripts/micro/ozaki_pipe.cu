@@ -39,7 +39,7 @@ static int run(Problem& pr, bool timing) {
   const double scale = ldexp(1.0, oz::FRAC_BITS - pr.eA);
   oz::slice_rows_kernel<LAYOUT><<<sms * 16, 256>>>(pr.d_psi, 2LL * pr.Dp, pr.rows, pr.D, pr.Dp, scale, pr.nks, pr.row_blocks, pr.d_a);
   CK(cudaDeviceSynchronize());
-  oz::GemmParams g{pr.d_a, pr.d_b, pr.nks, pr.row_blocks, pr.n_tiles, 0, pr.row_blocks * pr.n_tiles, 1, pr.nks, 0};
+  oz::GemmParams g{pr.d_a, pr.d_b, pr.nks, pr.row_blocks, pr.n_tiles, 0, pr.row_blocks * pr.n_tiles, 1, pr.nks, 0, 1, 1 << 30, 0};
   const long long ld = pr.Np;
   oz::EpiStore::Params es{pr.rows, pr.m, pr.d_cs, pr.d_tr, pr.d_ti, ld};
   CK(cudaFuncSetAttribute(oz::gemm_kernel_i8<LAYOUT, oz::EpiStore, A_TMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::SMEM_BYTES));
