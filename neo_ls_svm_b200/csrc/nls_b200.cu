@@ -1267,6 +1267,7 @@ struct OzSweep {
   int* ex_pu;
   double *pscale, *uscale;
 };
+static_assert(oz::MAX_SWEEP_GROUPS >= 2, "");
 constexpr int OZ_SWEEP_GROUPS = 2;  // γ groups with their own column scaling (scripts/sweep_int8_study.py: 1 already suffices)
 
 static int oz_prep_sweep(nls_ctx* ctx, const MapGeom& g, const double* gammas, const double* lam, int G, OzSweep* out) {
@@ -1333,8 +1334,8 @@ static int oz_sweep_chunk(nls_ctx* ctx, const MapGeom& g, const OzSweep& o, int 
     oz::gemm_kernel_i8<oz::IMAGE, oz::EpiSweep><<<grid, oz::THREADS, oz::SMEM_BYTES, ctx->stream>>>(gp, ep);
     NLS_TRY(check_launch(ctx, "oz::gemm_kernel_i8<EpiSweep>"));
   }
-  sweep_reduce_kernel<<<(3 * o.G + 255) / 256, 256, 0, ctx->stream>>>((const double*)ctx->part.p, 2 * n_tiles, o.G, sums_out);
-  return check_launch(ctx, "sweep_reduce_kernel");
+  sweep_reduce_wide_kernel<<<(3 * o.G + 31) / 32, dim3(32, 32), 0, ctx->stream>>>((const double*)ctx->part.p, 2 * n_tiles, o.G, sums_out);
+  return check_launch(ctx, "sweep_reduce_wide_kernel");
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -372,6 +372,7 @@ __global__ void __launch_bounds__(256) slice_rgamma_kernel(const double* __restr
 }
 
 // B side, pass 1: row exponents of P' = P / d and U' = U / d per (data row, group); one warp per data row.
+constexpr int MAX_SWEEP_GROUPS = 4;
 __global__ void __launch_bounds__(256) pu_exponent_kernel(const double* __restrict__ P, const double* __restrict__ U, long long ld, int rows,
                                                           int m, const double* __restrict__ inv_d, int ngrp, long long ldk,
                                                           int* __restrict__ ex /*[rows][ngrp][2]*/, double* __restrict__ pscale,
@@ -379,26 +380,39 @@ __global__ void __launch_bounds__(256) pu_exponent_kernel(const double* __restri
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (i >= rows) return;
-  for (int grp = 0; grp < ngrp; ++grp) {
-    const double* id = inv_d + grp * ldk;
-    double pm = 0.0, um = 0.0;
-    for (int k = lane; k < m; k += 32) {
-      pm = fmax(pm, fabs(P[(long long)i * ld + k] * id[k]));
-      um = fmax(um, fabs(U[(long long)i * ld + k] * id[k]));
-    }
+  double pm[MAX_SWEEP_GROUPS], um[MAX_SWEEP_GROUPS];
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      pm = fmax(pm, __shfl_xor_sync(0xffffffffu, pm, o));
-      um = fmax(um, __shfl_xor_sync(0xffffffffu, um, o));
-    }
-    if (lane == 0) {
-      const int ep = scale_exponent(pm), eu = scale_exponent(um);
-      ex[((long long)i * ngrp + grp) * 2] = ep;
-      ex[((long long)i * ngrp + grp) * 2 + 1] = eu;
-      pscale[(long long)i * ngrp + grp] = ldexp(1.0, ep);
-      uscale[(long long)i * ngrp + grp] = ldexp(1.0, eu);
-    }
+  for (int grp = 0; grp < MAX_SWEEP_GROUPS; ++grp) pm[grp] = um[grp] = 0.0;
+  // the row is read once (16-byte loads; ld and ldk are multiples of 16), every group's scaling applied on the fly
+  for (int k = 2 * lane; k < m; k += 64) {
+    const double2 pv = *reinterpret_cast<const double2*>(P + (long long)i * ld + k);
+    const double2 uv = *reinterpret_cast<const double2*>(U + (long long)i * ld + k);
+    const bool two = k + 1 < m;
+#pragma unroll
+    for (int grp = 0; grp < MAX_SWEEP_GROUPS; ++grp)
+      if (grp < ngrp) {
+        const double2 id = *reinterpret_cast<const double2*>(inv_d + grp * ldk + k);
+        pm[grp] = fmax(pm[grp], fmax(fabs(pv.x * id.x), two ? fabs(pv.y * id.y) : 0.0));
+        um[grp] = fmax(um[grp], fmax(fabs(uv.x * id.x), two ? fabs(uv.y * id.y) : 0.0));
+      }
   }
+#pragma unroll
+  for (int grp = 0; grp < MAX_SWEEP_GROUPS; ++grp)
+    if (grp < ngrp) {
+      double a = pm[grp], b = um[grp];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
+        b = fmax(b, __shfl_xor_sync(0xffffffffu, b, o));
+      }
+      if (lane == 0) {
+        const int ep = scale_exponent(a), eu = scale_exponent(b);
+        ex[((long long)i * ngrp + grp) * 2] = ep;
+        ex[((long long)i * ngrp + grp) * 2 + 1] = eu;
+        pscale[(long long)i * ngrp + grp] = ldexp(1.0, ep);
+        uscale[(long long)i * ngrp + grp] = ldexp(1.0, eu);
+      }
+    }
 }
 
 // B side, pass 2: digit planes [tile of 32 data rows][group][k step][plane][64 x 32 B]; tile rows 0..31 = P', 32..63 = U'.
@@ -428,11 +442,16 @@ __global__ void __launch_bounds__(256) slice_pu_kernel(const double* __restrict_
       const double* id = inv_d + grp * ldk + k0;
       const double scale = ldexp(1.0, FRAC_BITS - ex[(i * ngrp + grp) * 2 + which]);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const double v = k0 + j < m ? src[j] * id[j] : 0.0;
-        const unsigned long long q = digit_bytes(quantise(v, scale));
+      for (int j = 0; j < 16; j += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(src + j);  // pads of the P / U rows are never used: masked below
+        const double2 dd = *reinterpret_cast<const double2*>(id + j);
+        const unsigned long long q0 = digit_bytes(quantise(k0 + j < m ? v.x * dd.x : 0.0, scale));
+        const unsigned long long q1 = digit_bytes(quantise(k0 + j + 1 < m ? v.y * dd.y : 0.0, scale));
 #pragma unroll
-        for (int p = 0; p < S; ++p) w[p][j >> 2] |= ((uint32_t)(q >> (8 * (S - 1 - p))) & 0xff) << (8 * (j & 3));
+        for (int p = 0; p < S; ++p) {
+          const uint32_t b0 = (uint32_t)(q0 >> (8 * (S - 1 - p))) & 0xff, b1 = (uint32_t)(q1 >> (8 * (S - 1 - p))) & 0xff;
+          w[p][j >> 2] |= (b0 | (b1 << 8)) << (16 * ((j >> 1) & 1));
+        }
       }
     }
     int8_t* dst = out + (blk * S) * B_TILE + tile_off<LAYOUT>(r, c);

@@ -193,6 +193,27 @@ __global__ void sweep_reduce_kernel(const double* __restrict__ part, int n_tiles
   sums[e] += acc;
 }
 
+// The same for many partials (the INT8 sweep writes 2 per 32 data rows): blockDim.y slices of the tile range are summed
+// side by side and combined in slice order — fixed order, so still bitwise reproducible.
+__global__ void __launch_bounds__(1024) sweep_reduce_wide_kernel(const double* __restrict__ part, int n_tiles, int G,
+                                                                 double* __restrict__ sums) {
+  __shared__ double red[32][33];
+  const int e = blockIdx.x * 32 + threadIdx.x;
+  const int per = (n_tiles + 31) / 32;
+  const int t0 = threadIdx.y * per, t1 = min(n_tiles, t0 + per);
+  double acc = 0.0;
+  if (e < 3 * G)
+    for (int t = t0; t < t1; ++t) acc += part[(long long)t * 3 * G + e];
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && e < 3 * G) {
+    double tot = 0.0;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) tot += red[q][threadIdx.x];
+    sums[e] += tot;
+  }
+}
+
 // out[row] = sum_t part[t, row].
 __global__ void rowsum_reduce_kernel(const double* __restrict__ part, int n_tiles, long long ld, int rows,
                                      double* __restrict__ out) {
