@@ -40,6 +40,7 @@ constexpr int A_STAGE = S * A_TILE;
 constexpr int B_STAGE = S * B_TILE;
 constexpr int STAGE_BYTES = A_STAGE + B_STAGE;  // 43008
 constexpr int SMEM_BYTES = 1024 + NSTAGE * STAGE_BYTES;
+constexpr int DEFAULT_TMEM_PLANES = 7;  // leading A planes that go through tensor memory (A_TMEM kernels)
 constexpr int NISSUE = 4;          // MMA-issuing warps: issuer w owns the levels {6}, {5,0}, {4,1}, {3,2} (7 products each)
 constexpr int THREADS = 32 * (1 + NISSUE + 8);  // producer warp, MMA issuers, 8 epilogue warps
 constexpr int RADIX_BITS = 8;      // balanced base-256 digits
@@ -733,7 +734,7 @@ struct EpiSweep {
 // PLANES {0}, {1,6}, {2,5}, {3,4} (7 products each) instead of whole levels: its tcgen05.cp and the MMAs that read the
 // plane stay in one thread's program order, which is the only ordering tcgen05 guarantees.  Levels are then shared
 // between issuers, so no product may overwrite: the epilogue warps zero the accumulators (tcgen05.st) after draining.
-template <int LAYOUT, class Epi, bool A_TMEM = true>
+template <int LAYOUT, class Epi, bool A_TMEM = true, int TMEM_PLANES = DEFAULT_TMEM_PLANES>
 __global__ void __launch_bounds__(THREADS, 1) gemm_kernel_i8(GemmParams g, typename Epi::Params ep) {
   extern __shared__ uint8_t oz_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -802,10 +803,18 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel_i8(GemmParams g, typen
 #pragma unroll
             for (int p = 0; p < S; ++p) {
               if (p != p_a && p != p_b) continue;
-              tmem_cp_tile(tmem + (uint32_t)(S * TN + p * 8), da + (uint64_t)((p * A_TILE) >> 4));
+              // a plane feeds 7 - p products: the copy (64 cycles of the tensor pipe) pays off against the 16 cycles it
+              // saves per product only for the leading planes; the others are read from shared memory directly
+              if (p < TMEM_PLANES) {
+                tmem_cp_tile(tmem + (uint32_t)(S * TN + p * 8), da + (uint64_t)((p * A_TILE) >> 4));
 #pragma unroll
-              for (int q = 0; q < S; ++q)
-                if (p + q < S) umma_i8_ta(tmem + (uint32_t)((p + q) * TN), tmem + (uint32_t)(S * TN + p * 8), db + (uint64_t)((q * B_TILE) >> 4));
+                for (int q = 0; q < S; ++q)
+                  if (p + q < S) umma_i8_ta(tmem + (uint32_t)((p + q) * TN), tmem + (uint32_t)(S * TN + p * 8), db + (uint64_t)((q * B_TILE) >> 4));
+              } else {
+#pragma unroll
+                for (int q = 0; q < S; ++q)
+                  if (p + q < S) umma_i8(tmem + (uint32_t)((p + q) * TN), da + (uint64_t)((p * A_TILE) >> 4), db + (uint64_t)((q * B_TILE) >> 4), 1u);
+              }
             }
           } else {
           const uint32_t acc0 = ks > wk.ks0 ? 1u : 0u;

@@ -124,6 +124,29 @@ static int run(Problem& pr, bool timing) {
       cudaEventElapsedTime(&ms_st, e1, e2);
       cudaEventElapsedTime(&ms_pj, e2, e3);
     }
+    if (A_TMEM) {
+      float ms_v[4] = {0, 0, 0, 0};
+      CK(cudaFuncSetAttribute(oz::gemm_kernel_i8<LAYOUT, oz::EpiProject, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::SMEM_BYTES));
+      CK(cudaFuncSetAttribute(oz::gemm_kernel_i8<LAYOUT, oz::EpiProject, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::SMEM_BYTES));
+      CK(cudaFuncSetAttribute(oz::gemm_kernel_i8<LAYOUT, oz::EpiProject, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::SMEM_BYTES));
+      CK(cudaFuncSetAttribute(oz::gemm_kernel_i8<LAYOUT, oz::EpiProject, true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::SMEM_BYTES));
+      for (int rep = 0; rep < 3; ++rep) {
+        cudaEvent_t ev[5];
+        for (auto& e : ev) cudaEventCreate(&e);
+        cudaEventRecord(ev[0]);
+        oz::gemm_kernel_i8<LAYOUT, oz::EpiProject, true, 2><<<grid, oz::THREADS, oz::SMEM_BYTES>>>(g, epp);
+        cudaEventRecord(ev[1]);
+        oz::gemm_kernel_i8<LAYOUT, oz::EpiProject, true, 3><<<grid, oz::THREADS, oz::SMEM_BYTES>>>(g, epp);
+        cudaEventRecord(ev[2]);
+        oz::gemm_kernel_i8<LAYOUT, oz::EpiProject, true, 4><<<grid, oz::THREADS, oz::SMEM_BYTES>>>(g, epp);
+        cudaEventRecord(ev[3]);
+        oz::gemm_kernel_i8<LAYOUT, oz::EpiProject, true, 5><<<grid, oz::THREADS, oz::SMEM_BYTES>>>(g, epp);
+        cudaEventRecord(ev[4]);
+        CK(cudaDeviceSynchronize());
+        for (int v = 0; v < 4; ++v) cudaEventElapsedTime(&ms_v[v], ev[v], ev[v + 1]);
+      }
+      printf("  leading planes through TMEM: 2 -> %.3f ms, 3 -> %.3f ms, 4 -> %.3f ms, 5 -> %.3f ms (7 -> %.3f ms)\n", ms_v[0], ms_v[1], ms_v[2], ms_v[3], ms_pj);
+    }
     const double flops = 8.0 * pr.rows * (double)pr.D * pr.m;
     printf("A from %s, layout %d: rows %d D %d m %d: slicing %.3f ms (%.0f GB/s), store-epilogue GEMM %.3f ms = %.1f TFLOP/s, project-epilogue GEMM %.3f ms = %.1f TFLOP/s FP64-equivalent (DMMA peak 37.1)\n",
            A_TMEM ? "TMEM" : "smem", LAYOUT, pr.rows, pr.D, pr.m, ms_sl, (pr.rows * 2.0 * pr.Dp * (8 + oz::S)) / ms_sl * 1e-6, ms_st, flops / ms_st * 1e-9, ms_pj, flops / ms_pj * 1e-9);
