@@ -486,7 +486,6 @@ def run_ours(args) -> None:
         from neo_ls_svm_b200 import NeoLSSVM, OrthogonalRandomFourierFeatures
 
         del Xh, yh, sh
-        torch.cuda.empty_cache()
 
         def api_fit(rows):
             est = NeoLSSVM(primal_feature_map=OrthogonalRandomFourierFeatures(num_features=D), dual=False)
@@ -495,10 +494,13 @@ def run_ours(args) -> None:
             torch.cuda.synchronize()
             return est, time.perf_counter() - t0
 
-        api_fit(min(n, 50_000))  # warm-up: numba JIT of the host pre-pass, scratch allocation
-        est, secs = api_fit(n)
+        api_fit(min(n, 50_000))  # warm-up: numba JIT of the host pre-pass
+        est, secs_first = api_fit(n)  # first full-size call of the process: also allocates ~40 GB of device scratch
+        del est
+        est, secs = api_fit(n)        # steady state, like the W warm-up steps of the solve arm
         phases = dict(getattr(est, "fit_phases_", {}))
-        fit_api = {"value": n / secs, "unit": "rows/s", "seconds": secs, "phases_s": phases, "selected_gamma_index":
+        fit_api = {"value": n / secs, "unit": "rows/s", "seconds": secs, "first_call_seconds": secs_first,
+                   "phases_s": phases, "selected_gamma_index":
                    int(np.argmin(np.abs(est.γs_ - est.γ_))),
                    "includes": "validation, supervised affine pre-pass (host + GPU weighted-median kernels), ORF, "
                                "pageable H2D, stages 1-4c, D2H, conformal split"}

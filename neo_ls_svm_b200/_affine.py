@@ -146,32 +146,49 @@ class PendingUpload:
         import torch
 
         self._torch, self._X, self._scan, self._device = torch, X, scan_finite, device
-        self._stream = torch.cuda.Stream(device)
-        self._stream.wait_stream(torch.cuda.current_stream(device))  # the block may be recycled from queued work
-        self._Xd = self._finite = self._event = self._error = None
+        self._caller_stream = torch.cuda.current_stream(device)
+        self._Xd = self._finite = self._event = self._error = self._stream = None
+        self.alloc_s = self.total_s = self.waited_s = 0.0
         self._thread = threading.Thread(target=self._run, daemon=True)
         self._thread.start()
 
     def _run(self) -> None:
         torch = self._torch
         try:
+            import time
+
+            t0 = time.perf_counter()
+            self._stream = torch.cuda.Stream(self._device)
+            self._stream.wait_stream(self._caller_stream)  # the block may be recycled from work queued by the caller
             with torch.cuda.stream(self._stream):
                 # allocated here, on the side stream: a fresh 2 GB cudaMalloc is not free either
                 self._Xd = torch.empty(self._X.shape, dtype=torch.float64, device=self._device)
+                self.alloc_s = time.perf_counter() - t0
                 src = torch.from_numpy(np.ascontiguousarray(self._X))
-                if src.dtype == torch.float64:
-                    self._Xd.copy_(src)
-                else:  # float32 rows cross the bus as they are and are widened on the device
-                    self._Xd.copy_(src.to(self._device))
+                # In pieces of ~64 MB: the copy engine serves the streams in issue order, and the pre-pass running on
+                # the caller's stream has small transfers of its own (the target vector) that must not queue behind 2 GB.
+                step = max(1, (64 << 20) // max(1, src.shape[1] * src.element_size()))
+                for r0 in range(0, src.shape[0], step):
+                    piece = src[r0 : r0 + step]
+                    if src.dtype == torch.float64:
+                        self._Xd[r0 : r0 + step].copy_(piece)
+                    else:  # float32 rows cross the bus as they are and are widened on the device
+                        self._Xd[r0 : r0 + step].copy_(piece.to(self._device))
                 if self._scan:
                     self._finite = torch.isfinite(self._Xd).all()
                 self._event = self._stream.record_event()
+                self._event.synchronize()
+                self.total_s = time.perf_counter() - t0
         except BaseException as exc:  # noqa: BLE001  (re-raised by result() on the caller's thread)
             self._error = exc
 
     def result(self):
         if self._thread is not None:
+            import time
+
+            t0 = time.perf_counter()
             self._thread.join()
+            self.waited_s = time.perf_counter() - t0  # how long the consumer stood still for the copy
             self._thread = None
             if self._error is not None:
                 raise self._error

@@ -272,10 +272,12 @@ class NeoLSSVM(BaseEstimator):
             )
             # One host→device copy of X serves the supervised affine pre-pass and the solver.
             ctx, torch, dev = self._gpu()
+            marks.append(("feature_map_clone_and_context", time.perf_counter()))
             if X.nbytes >= _ASYNC_UPLOAD_MIN_BYTES:
                 # the copy (and the finiteness scan behind it) runs on a side stream underneath the host part of the
                 # supervised pre-pass; whoever asks for the device copy first waits for it and sees the scan's verdict
-                _affine.register_device_copy(X, _affine.PendingUpload(X, dev, device_scan))
+                pending = _affine.PendingUpload(X, dev, device_scan)
+                _affine.register_device_copy(X, pending)
             else:
                 Xd = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).to(dev)
                 if device_scan and not bool(torch.isfinite(Xd).all()):
@@ -324,6 +326,8 @@ class NeoLSSVM(BaseEstimator):
         self.conformal_l2_ = {"Δŷ": {}, "Δŷ/ŷ": {}}
         marks.append(("calibration_split", time.perf_counter()))
         self.fit_phases_ = {name: t - marks[i][1] for i, (name, t) in enumerate(marks[1:])}  # seconds per phase
+        if self.primal_ and "pending" in locals():
+            self.fit_phases_.update(upload_alloc=pending.alloc_s, upload_total=pending.total_s, upload_waited_for=pending.waited_s)
         return self
 
     # ------------------------------------------------------------------------------------------
