@@ -1184,6 +1184,16 @@ extern "C" int nls_cholesky_solve(nls_ctx* ctx, const double* A, int m, double d
 // ---------------------------------------------------------------------------------------------
 // Projection on the INT8 tensor cores (csrc/ozaki.cuh)
 // ---------------------------------------------------------------------------------------------
+struct OzSweep {
+  int G, m, ngrp, rb_per_group, row_blocks, nks;
+  long long ldk;
+  const double *d, *inv_d, *ascale;
+  const int8_t* a_planes;
+  int* ex_pu;
+  double *pscale, *uscale;
+  double *qscale, *gscale;  // [ngrp][2] global quantisation / recombination scales of P', U' (fused projection -> planes)
+};
+
 struct OzBasis {
   const int8_t* planes;    // [n_tiles][nks][S][64 x 32 B]
   const double* colscale;  // 2^(eA + eB_j) per complex column
@@ -1200,6 +1210,8 @@ static int oz_attr(nls_ctx* ctx) {
   CUDA_TRY(cudaFuncSetAttribute(oz::gemm_kernel_i8<oz::IMAGE, oz::EpiVariance>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 oz::SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(oz::gemm_kernel_i8<oz::IMAGE, oz::EpiSweep>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                oz::SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(oz::gemm_kernel_i8<oz::IMAGE, oz::EpiProjectPlanes>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 oz::SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(oz::gemm_kernel_i8<oz::IMAGE, oz::EpiProject>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 oz::SMEM_BYTES));
@@ -1247,10 +1259,18 @@ static int oz_slice_chunk(nls_ctx* ctx, const MapGeom& g, const OzBasis& ob, int
 
 // P = Re(T v), U = |T|^2 / c for the first `cols` columns of T = phi Q, phi = the planar chunk in ctx->psi.
 static int oz_project_chunk(nls_ctx* ctx, const MapGeom& g, const BasisScratch& bs, const OzBasis& ob, int rows, int cols,
-                            double inv_c, double* P, double* U) {
+                            double inv_c, double* P, double* U, const OzSweep* sw = nullptr) {
   const int row_blocks = (rows + oz::TM - 1) / oz::TM;
   NLS_TRY(oz_slice_chunk(ctx, g, ob, rows));
   ProfScope scope(ctx, NLS_PROF_PROJECT);
+  if (sw) {  // straight into the digit planes of the INT8 sweep's B operand (no FP64 P, U)
+    oz::GemmParams gp{(const int8_t*)ctx->oz_a.p, ob.planes, ob.nks, row_blocks, ob.n_tiles, 0, row_blocks * ob.n_tiles, 1, ob.nks, 0, 1, 1 << 30, 0};
+    oz::EpiProjectPlanes::Params ep{rows, cols, ob.colscale, bs.bias_r, bs.bias_i, bs.v_r, bs.v_i, inv_c, sw->inv_d, sw->qscale,
+                                    sw->ngrp, sw->nks, sw->ldk, (int8_t*)ctx->oz_sb.p};
+    const int grid = (int)std::min<long long>((long long)row_blocks * ob.n_tiles, ctx->sm_count);
+    oz::gemm_kernel_i8<oz::IMAGE, oz::EpiProjectPlanes><<<grid, oz::THREADS, oz::SMEM_BYTES, ctx->stream>>>(gp, ep);
+    return check_launch(ctx, "oz::gemm_kernel_i8<EpiProjectPlanes>");
+  }
   oz::GemmParams gp{(const int8_t*)ctx->oz_a.p, ob.planes, ob.nks, row_blocks, ob.n_tiles, 0, row_blocks * ob.n_tiles, 1, ob.nks, 0, 1, 1 << 30, 0};
   oz::EpiProject::Params ep{rows, cols, ob.colscale, bs.bias_r, bs.bias_i, bs.v_r, bs.v_i, inv_c, P, U, g.ldp};
   const int grid = (int)std::min<long long>((long long)row_blocks * ob.n_tiles, ctx->sm_count);
@@ -1259,18 +1279,11 @@ static int oz_project_chunk(nls_ctx* ctx, const MapGeom& g, const BasisScratch& 
 }
 
 // γ sweep on the INT8 core: operands that do not depend on the chunk (column scalings, digit planes of r').
-struct OzSweep {
-  int G, m, ngrp, rb_per_group, row_blocks, nks;
-  long long ldk;
-  const double *d, *inv_d, *ascale;
-  const int8_t* a_planes;
-  int* ex_pu;
-  double *pscale, *uscale;
-};
 static_assert(oz::MAX_SWEEP_GROUPS >= 2, "");
 constexpr int OZ_SWEEP_GROUPS = 2;  // γ groups with their own column scaling (scripts/sweep_int8_study.py: 1 already suffices)
 
-static int oz_prep_sweep(nls_ctx* ctx, const MapGeom& g, const double* gammas, const double* lam, int G, OzSweep* out) {
+static int oz_prep_sweep(nls_ctx* ctx, const MapGeom& g, const double* gammas, const double* lam, int G, const double* v_r,
+                         const double* v_i, double inv_c, OzSweep* out) {
   NLS_TRY(oz_attr(ctx));
   OzSweep o{};
   o.G = G;
@@ -1283,9 +1296,11 @@ static int oz_prep_sweep(nls_ctx* ctx, const MapGeom& g, const double* gammas, c
   const long long cap = ctx->chunk_rows;
   // small arrays: d, inv_d [ngrp][ldk]; ascale [G]; pscale, uscale [cap][ngrp]; exA [G]; ex_pu [cap][ngrp][2]
   const size_t n_d = (size_t)o.ngrp * o.ldk, n_g = (size_t)round_up(G, 2), n_pu = (size_t)cap * o.ngrp;
-  NLS_TRY(ensure(ctx, ctx->oz_ssmall, (2 * n_d + n_g + 2 * n_pu) * 8 + (n_g + 2 * n_pu) * 4));
+  NLS_TRY(ensure(ctx, ctx->oz_ssmall, (2 * n_d + n_g + 2 * n_pu + 4 * (size_t)o.ngrp) * 8 + (n_g + 2 * n_pu) * 4));
   double* base = (double*)ctx->oz_ssmall.p;
-  double* d = base;
+  o.qscale = base;
+  o.gscale = base + 2 * o.ngrp;
+  double* d = base + 4 * o.ngrp;
   double* inv_d = d + n_d;
   double* ascale = inv_d + n_d;
   o.pscale = ascale + n_g;
@@ -1302,6 +1317,8 @@ static int oz_prep_sweep(nls_ctx* ctx, const MapGeom& g, const double* gammas, c
   oz::slice_rgamma_kernel<oz::IMAGE><<<grid_for((long long)o.row_blocks * o.nks * oz::TM * 2), 256, 0, ctx->stream>>>(
       gammas, lam, d, exA, G, g.m, o.rb_per_group, o.ldk, o.nks, o.row_blocks, (int8_t*)ctx->oz_sa.p);
   NLS_TRY(check_launch(ctx, "oz::slice_rgamma_kernel"));
+  oz::sweep_bounds_kernel<<<o.ngrp, 256, 0, ctx->stream>>>(v_r, v_i, inv_d, g.m, o.ldk, inv_c, o.qscale, o.gscale);
+  NLS_TRY(check_launch(ctx, "oz::sweep_bounds_kernel"));
   o.d = d;
   o.inv_d = inv_d;
   o.ascale = ascale;
@@ -1311,25 +1328,35 @@ static int oz_prep_sweep(nls_ctx* ctx, const MapGeom& g, const double* gammas, c
 }
 
 // num / den / LOO error sums (and the σ² stash) of one chunk from its P, U (row pitch ldp).
+// `planes_from`: >= 0 when the projection epilogue already wrote the planes of the k steps below it with the global scales
+// (then only the spill columns' k steps are sliced here, from the FP64 P, U the spill kernels wrote); -1: everything from P, U.
 static int oz_sweep_chunk(nls_ctx* ctx, const MapGeom& g, const OzSweep& o, int rows, const double* P, const double* U,
-                          const double* y, const double* s, int is_classifier, double* den_out, double* sums_out) {
+                          const double* y, const double* s, int is_classifier, double* den_out, double* sums_out,
+                          int planes_from = -1) {
   const int n_tiles = (rows + oz::TN / 2 - 1) / (oz::TN / 2);
   NLS_TRY(ensure(ctx, ctx->part, (size_t)2 * ((ctx->chunk_rows + oz::TN / 2 - 1) / (oz::TN / 2)) * 3 * o.G * 8));
-  {
+  if (planes_from >= 0) {
+    if (planes_from < o.nks) {
+      ProfScope scope(ctx, NLS_PROF_SLICE);
+      oz::slice_pu_kernel<oz::IMAGE><<<grid_for((long long)n_tiles * o.ngrp * (o.nks - planes_from) * oz::TN * 2), 256, 0, ctx->stream>>>(
+          P, U, g.ldp, rows, g.m, o.inv_d, nullptr, o.qscale, o.ngrp, o.ldk, planes_from, o.nks, n_tiles, (int8_t*)ctx->oz_sb.p);
+      NLS_TRY(check_launch(ctx, "oz::slice_pu_kernel"));
+    }
+  } else {
     ProfScope scope(ctx, NLS_PROF_SLICE);
     oz::pu_exponent_kernel<<<(rows + 7) / 8, 256, 0, ctx->stream>>>(P, U, g.ldp, rows, g.m, o.inv_d, o.ngrp, o.ldk, o.ex_pu, o.pscale,
                                                                   o.uscale);
     NLS_TRY(check_launch(ctx, "oz::pu_exponent_kernel"));
     oz::slice_pu_kernel<oz::IMAGE><<<grid_for((long long)n_tiles * o.ngrp * o.nks * oz::TN * 2), 256, 0, ctx->stream>>>(
-        P, U, g.ldp, rows, g.m, o.inv_d, o.ex_pu, o.ngrp, o.ldk, o.nks, n_tiles, (int8_t*)ctx->oz_sb.p);
+        P, U, g.ldp, rows, g.m, o.inv_d, o.ex_pu, nullptr, o.ngrp, o.ldk, 0, o.nks, n_tiles, (int8_t*)ctx->oz_sb.p);
     NLS_TRY(check_launch(ctx, "oz::slice_pu_kernel"));
   }
   {
     ProfScope scope(ctx, NLS_PROF_SWEEP);
     oz::GemmParams gp{o.a_planes, (const int8_t*)ctx->oz_sb.p, o.nks, o.row_blocks, n_tiles, 0, o.row_blocks * n_tiles, 1, o.nks, 0,
                       o.ngrp, o.rb_per_group, 1};
-    oz::EpiSweep::Params ep{rows, o.G, o.ngrp, o.rb_per_group, o.ascale, o.pscale, o.uscale, y, s, is_classifier,
-                            (double*)ctx->part.p, den_out, (long long)o.G};
+    oz::EpiSweep::Params ep{rows, o.G, o.ngrp, o.rb_per_group, o.ascale, o.pscale, o.uscale, planes_from >= 0 ? o.gscale : nullptr,
+                            y, s, is_classifier, (double*)ctx->part.p, den_out, (long long)o.G};
     const int grid = (int)std::min<long long>((long long)gp.tiles, ctx->sm_count);
     oz::gemm_kernel_i8<oz::IMAGE, oz::EpiSweep><<<grid, oz::THREADS, oz::SMEM_BYTES, ctx->stream>>>(gp, ep);
     NLS_TRY(check_launch(ctx, "oz::gemm_kernel_i8<EpiSweep>"));
@@ -1371,7 +1398,9 @@ extern "C" int nls_primal_loo_sweep(nls_ctx* ctx, const double* X, const double*
   if (use_oz) NLS_TRY(oz_prep_basis(ctx, g, bs, tail_split(g.m), &oz));
   const bool use_oz_sweep = ctx->gemm_core >= 2 && g.m <= oz::MAX_K;
   OzSweep ozs{};
-  if (use_oz_sweep) NLS_TRY(oz_prep_sweep(ctx, g, gammas, lam, G, &ozs));
+  if (use_oz_sweep) NLS_TRY(oz_prep_sweep(ctx, g, gammas, lam, G, bs.v_r, bs.v_i, inv_c, &ozs));
+  // projection and sweep both on the INT8 core: the projection epilogue writes the sweep's operand planes itself
+  const bool fused_planes = use_oz && use_oz_sweep && tail_split(g.m) % (oz::TN / 2) == 0;
   for (int64_t i0 = 0; i0 < n; i0 += cap) {
     const int rows = (int)std::min<int64_t>(cap, n - i0);
     const int mtiles = (rows + BM - 1) / BM;
@@ -1391,7 +1420,7 @@ extern "C" int nls_primal_loo_sweep(nls_ctx* ctx, const double* X, const double*
     NLS_TRY(feature_chunk(ctx, g, X + i0 * d, shift, rows, FM_PLANAR, (double*)ctx->psi.p, 2LL * g.Dp, g.Dp, nullptr,
                           fused_spill ? &dots : nullptr));
     if (use_oz) {
-      NLS_TRY(oz_project_chunk(ctx, g, bs, oz, rows, full_cols, inv_c, P, U));
+      NLS_TRY(oz_project_chunk(ctx, g, bs, oz, rows, full_cols, inv_c, P, U, fused_planes ? &ozs : nullptr));
     } else {
     OpProject::Params pp;
     pp.A = psi_operand(ctx, g, rows);
@@ -1425,7 +1454,7 @@ extern "C" int nls_primal_loo_sweep(nls_ctx* ctx, const double* X, const double*
     }
     if (use_oz_sweep) {
       NLS_TRY(oz_sweep_chunk(ctx, g, ozs, rows, P, U, y + i0, s + i0, is_classifier, sigma2_stash ? sigma2_stash + i0 * G : nullptr,
-                             sums_out));
+                             sums_out, fused_planes ? full_cols / oz::KS : -1));
       continue;
     }
     OpSweep::Params sp;

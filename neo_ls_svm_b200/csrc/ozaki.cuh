@@ -416,18 +416,59 @@ __global__ void __launch_bounds__(256) pu_exponent_kernel(const double* __restri
     }
 }
 
+// Global exponents of P' and U' per γ group from the bounds of EpiProjectPlanes: qscale[grp][2] = 2^(56 - e), gscale = 2^e.
+__global__ void __launch_bounds__(256) sweep_bounds_kernel(const double* __restrict__ v_r, const double* __restrict__ v_i,
+                                                           const double* __restrict__ inv_d, int m, long long ldk, double inv_c,
+                                                           double* __restrict__ qscale, double* __restrict__ gscale) {
+  __shared__ double red[2][8];
+  const int grp = blockIdx.x;
+  double bp = 0.0, bu = 0.0;
+  for (int k = threadIdx.x; k < m; k += blockDim.x) {
+    const double id = inv_d[grp * ldk + k];
+    bp = fmax(bp, hypot(v_r[k], v_i[k]) * id);
+    bu = fmax(bu, id);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    bp = fmax(bp, __shfl_xor_sync(0xffffffffu, bp, o));
+    bu = fmax(bu, __shfl_xor_sync(0xffffffffu, bu, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = bp;
+    red[1][threadIdx.x >> 5] = bu;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      bp = fmax(bp, red[0][w]);
+      bu = fmax(bu, red[1][w]);
+    }
+    // |T| <= |phi| |q| = sqrt(2) up to rounding, |T|^2 <= 2
+    const int ep = scale_exponent(1.41422 * bp), eu = scale_exponent(2.0001 * inv_c * bu);
+    qscale[2 * grp] = ldexp(1.0, FRAC_BITS - ep);
+    qscale[2 * grp + 1] = ldexp(1.0, FRAC_BITS - eu);
+    gscale[2 * grp] = ldexp(1.0, ep);
+    gscale[2 * grp + 1] = ldexp(1.0, eu);
+  }
+}
+
 // B side, pass 2: digit planes [tile of 32 data rows][group][k step][plane][64 x 32 B]; tile rows 0..31 = P', 32..63 = U'.
+// k steps [ks_begin, nks) only (the spill columns when the projection epilogue wrote the others); with qscale != null
+// the global scales of sweep_bounds_kernel are used instead of the row exponents.
 template <int LAYOUT>
 __global__ void __launch_bounds__(256) slice_pu_kernel(const double* __restrict__ P, const double* __restrict__ U, long long ld, int rows,
-                                                       int m, const double* __restrict__ inv_d, const int* __restrict__ ex, int ngrp,
-                                                       long long ldk, int nks, int n_tiles, int8_t* __restrict__ out) {
-  const long long items = (long long)n_tiles * ngrp * nks * TN * 2;
+                                                       int m, const double* __restrict__ inv_d, const int* __restrict__ ex,
+                                                       const double* __restrict__ qscale, int ngrp, long long ldk, int ks_begin,
+                                                       int nks, int n_tiles, int8_t* __restrict__ out) {
+  const int nk = nks - ks_begin;
+  const long long items = (long long)n_tiles * ngrp * nk * TN * 2;
   for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(it & 1);
     const int r = (int)((it >> 1) & (TN - 1));
-    const long long blk = it >> 7;  // (nb * ngrp + grp) * nks + ks
-    const int ks = (int)(blk % nks);
-    const long long tg = blk / nks;
+    const long long sub = it >> 7;  // (nb * ngrp + grp) * nk + (ks - ks_begin)
+    const int ks = ks_begin + (int)(sub % nk);
+    const long long tg = sub / nk;
+    const long long blk = tg * nks + ks;
     const int grp = (int)(tg % ngrp);
     const long long nb = tg / ngrp;
     const long long i = nb * (TN / 2) + (r & (TN / 2 - 1));
@@ -441,7 +482,7 @@ __global__ void __launch_bounds__(256) slice_pu_kernel(const double* __restrict_
     if (i < rows && k0 < m) {
       const double* src = (which ? U : P) + i * ld + k0;
       const double* id = inv_d + grp * ldk + k0;
-      const double scale = ldexp(1.0, FRAC_BITS - ex[(i * ngrp + grp) * 2 + which]);
+      const double scale = qscale ? qscale[2 * grp + which] : ldexp(1.0, FRAC_BITS - ex[(i * ngrp + grp) * 2 + which]);
 #pragma unroll
       for (int j = 0; j < 16; j += 2) {
         const double2 v = *reinterpret_cast<const double2*>(src + j);  // pads of the P / U rows are never used: masked below
@@ -596,6 +637,69 @@ struct EpiProject {  // P = Re(T v), U = |T|^2 / c   (what OpProject writes; ref
   }
 };
 
+// The projection feeding the INT8 sweep directly: instead of P and U in FP64 it writes the digit planes of the sweep's B
+// operand, P' = P / d and U' = U / d for every γ group.  A thread owns one data row and 16 consecutive columns k — exactly
+// one 16-byte chunk of one k step of the sweep — so every (group, operand, plane) is one 16-byte store and the FP64 round
+// trip (write P, U; row maxima; read twice; write planes) disappears.  The exponents cannot come from row maxima here (a
+// row is spread over all column tiles), so they come from BOUNDS: |T_ik| <= |phi_i| |q_k| = sqrt(2), hence
+// |P'_ik| <= sqrt(2) |v_k| / d_k and U'_ik <= 2 / (c d_k), maximised over k per group (sweep_bounds_kernel).  Typical entries are
+// sqrt(m) (P') and m (U') below the bounds, i.e. 51 and 46 of the 56 bits stay significant: still FP64-level for the sums.
+struct EpiProjectPlanes {
+  struct Params {
+    int n_rows, m;  // valid rows, valid complex columns (columns >= m are written as zeros)
+    const double* colscale;
+    const double* bias_r;
+    const double* bias_i;
+    const double* v_r;
+    const double* v_i;
+    double inv_c;
+    const double* inv_d;   // [ngrp][ldk]
+    const double* qscale;  // [ngrp][2] 2^(56 - e) of P' / U'
+    int ngrp, nks;         // groups, k steps of the sweep (per (row tile, group): nks stages of 7 x [64 x 32 B])
+    long long ldk;
+    int8_t* B;             // [row tile of 32][group][k step][plane][64 x 32 B]
+  };
+  static __device__ __forceinline__ void apply(const Params& p, const Work&, long long row, int col0, const double (&sr)[16],
+                                               const double (&si)[16]) {
+    double pv[16], uv[16];
+    const bool live = row < p.n_rows;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int col = col0 + j;
+      const bool ok = live && col < p.m;
+      const double cs = ok ? p.colscale[col] : 0.0;
+      const double tr = sr[j] * cs + (ok ? p.bias_r[col] : 0.0);
+      const double ti = (ok ? p.bias_i[col] : 0.0) - si[j] * cs;
+      pv[j] = ok ? tr * p.v_r[col] - ti * p.v_i[col] : 0.0;
+      uv[j] = ok ? (tr * tr + ti * ti) * p.inv_c : 0.0;
+    }
+    const long long tb = row >> 5;
+    const int r32 = (int)(row & 31), ks = col0 >> 5, c = (col0 >> 4) & 1;
+    for (int grp = 0; grp < p.ngrp; ++grp) {
+      const double* id = p.inv_d + grp * p.ldk + col0;
+      int8_t* base = p.B + (((tb * p.ngrp + grp) * p.nks + ks) * S) * (long long)B_TILE;
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        const double scale = p.qscale[2 * grp + which];
+        uint32_t w[S][4];
+#pragma unroll
+        for (int q = 0; q < S; ++q)
+#pragma unroll
+          for (int x = 0; x < 4; ++x) w[q][x] = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const unsigned long long d = digit_bytes(quantise((which ? uv[j] : pv[j]) * id[j], scale));
+#pragma unroll
+          for (int q = 0; q < S; ++q) w[q][j >> 2] |= ((uint32_t)(d >> (8 * (S - 1 - q))) & 0xff) << (8 * (j & 3));
+        }
+        int8_t* dst = base + tile_off<IMAGE>(r32 + 32 * which, c);
+#pragma unroll
+        for (int q = 0; q < S; ++q) *reinterpret_cast<uint4*>(dst + (long long)q * B_TILE) = make_uint4(w[q][0], w[q][1], w[q][2], w[q][3]);
+      }
+    }
+  }
+};
+
 struct EpiStore {  // raw T planes (probe / tests): Tr[row][col] = sr * colscale, Ti likewise
   struct Params {
     int n_rows, m;
@@ -688,6 +792,7 @@ struct EpiSweep {
     const double* ascale;  // [G] 2^e of the r' row of every γ
     const double* pscale;  // [rows][ngrp] 2^e of the P' row
     const double* uscale;  // [rows][ngrp] 2^e of the U' row
+    const double* gscale;  // when not null: [ngrp][2] global 2^e of P' / U' (planes written by EpiProjectPlanes), rows ignored
     const double* y;
     const double* s;
     int is_classifier;
@@ -701,13 +806,14 @@ struct EpiSweep {
     if (g >= p.G) return;
     const int grp = wk.rb / p.rb_per_group;
     const double as = p.ascale[g];
+    const double gp = p.gscale ? as * p.gscale[2 * grp] : 0.0, gu = p.gscale ? as * p.gscale[2 * grp + 1] : 0.0;
     double e_abs = 0.0, e_cnt = 0.0, e_hng = 0.0;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const int i = col0 + j;
       if (i < p.n_rows) {
-        const double num = sr[j] * (as * p.pscale[(long long)i * p.ngrp + grp]);
-        const double den = si[j] * (as * p.uscale[(long long)i * p.ngrp + grp]);
+        const double num = sr[j] * (p.gscale ? gp : as * p.pscale[(long long)i * p.ngrp + grp]);
+        const double den = si[j] * (p.gscale ? gu : as * p.uscale[(long long)i * p.ngrp + grp]);
         if (p.den_out) p.den_out[(long long)i * p.den_ld + g] = den;
         const double yi = p.y[i], wi = p.s[i];
         double loo = (num - yi) / (1.0 - wi * wi * den);
