@@ -160,6 +160,18 @@ def test_device_unique_matches_numpy():
     y = rng.standard_normal(n)
     codes = sample_bins_quantized_ecdf(y)
     assert codes.min() == 0 and 4 <= codes.max() + 1 <= 64 and np.all(np.diff(codes[np.argsort(y, kind="stable")]) >= 0)
+    # the all-device route (sort, counts and binning on the GPU) returns the host recipe's bins, ties and few-valued targets included
+    import neo_ls_svm_b200._quantizer as qz
+
+    for x in (y, np.round(y, 2), rng.integers(0, 7, n).astype(np.float64), y.astype(np.float32)):
+        dev_bins = sample_bins_quantized_ecdf(x)
+        threshold = qz.MIN_SAMPLES_FOR_DEVICE_UNIQUE
+        try:
+            qz.MIN_SAMPLES_FOR_DEVICE_UNIQUE = 1 << 62  # host recipe
+            host_bins = sample_bins_quantized_ecdf(x)
+        finally:
+            qz.MIN_SAMPLES_FOR_DEVICE_UNIQUE = threshold
+        assert dev_bins.dtype == host_bins.dtype and np.array_equal(dev_bins, host_bins)
 
 
 @pytest.mark.gpu
