@@ -78,7 +78,10 @@ constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >
 // of W with its top bit flipped.  `scale` = 2^(56 - e); the product x * scale is exact, the conversion rounds once.
 __host__ __device__ __forceinline__ long long quantise(double x, double scale) {
 #ifdef __CUDA_ARCH__
-  return __double2ll_rn(x * scale);
+  // saturate instead of wrapping if a caller ever breaks the |x| 2^-e <= 0.495 contract (e.g. a non-unitary basis handed to
+  // the C ABI): the result is then inaccurate, not garbage
+  constexpr long long LIM = (127LL << 48) | 0x7f7f7f7f7f7fLL;  // largest value the seven balanced digits represent
+  return max(min(__double2ll_rn(x * scale), LIM), -LIM);
 #else
   return (long long)__builtin_llrint(x * scale);
 #endif

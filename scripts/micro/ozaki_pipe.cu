@@ -198,6 +198,10 @@ int main(int argc, char** argv) {
     rc |= run<6, true>(pr, false);
     rc |= run<6, false>(pr, false) << 1;
   }
+  if (argc > 1) {  // "small": the ragged case only (for compute-sanitizer)
+    printf("rc = %d\n", rc);
+    return rc;
+  }
   {  // one projection chunk of C3
     Problem pr;
     make(pr, 32768, 1024, 1024);
