@@ -222,7 +222,48 @@ def test_error_paths(gpu):
     with pytest.raises(_lib.NlsError):
         _lib.check(ctx.lib.nls_feature_map(ctx.handle, None, 4, 2, None, None, 8, None))
     assert b"null" in ctx.lib.nls_last_error()
+    with pytest.raises(_lib.NlsError):
+        _lib.check(ctx.lib.nls_ctx_set_gemm_core(ctx.handle, 7))
+    with pytest.raises(KeyError):
+        ctx.set_gemm_core("fp8")
     del X
+
+
+def test_int8_sweep_variants_agree(golden, gpu):
+    """The three INT8 routes of the sweep — projection epilogue writing the sweep's operand planes (spill column at a k-step
+    boundary: m = 1025), planes sliced from FP64 P / U with row exponents (m = 130: no spill), and the DMMA sweep behind the
+    INT8 projection — give the same LOO curve and σ² to FP64 rounding."""
+    from neo_ls_svm_b200 import _lib
+
+    _, dev, _primal, _ = gpu
+    g = golden("c3_small")
+    X, y_, s, Xt, classifier, shift, W = _case("c3_small", g)
+    fits = {}
+    for core in ("ozaki", "ozaki-dmma-sweep"):
+        ctx = _lib.Context(0)
+        ctx.set_gemm_core(core)
+        ctx.set_chunk_rows(2048)
+        fits[core] = _primal.primal_fit(dev(X), dev(y_), dev(s), dev(shift), dev(W), classifier, ctx=ctx)
+        assert fits[core].opt == int(g["opt"])
+    a, b = fits["ozaki"], fits["ozaki-dmma-sweep"]
+    assert rel_err(a.loo_errors, b.loo_errors) < 1e-12
+    assert rel_err(a.rows["loo_std"].cpu().numpy(), b.rows["loo_std"].cpu().numpy()) < 1e-12
+    assert rel_err(a.rows["loo_leverage"].cpu().numpy(), b.rows["loo_leverage"].cpu().numpy()) < 1e-12
+    # a width whose column count is no multiple of 32 and has no spill column takes the unfused slicing route
+    rng = np.random.default_rng(3)
+    Xr = rng.standard_normal((3000, 5))
+    yr = np.sin(Xr[:, 0]) + 0.1 * rng.standard_normal(3000)
+    sr = np.full(3000, 1.0 / 3000)
+    Wr = rng.standard_normal((5, 129)) * 0.5
+    out = {}
+    for core in ("ozaki", "dmma"):
+        ctx = _lib.Context(0)
+        ctx.set_gemm_core(core)
+        ctx.set_chunk_rows(1024)
+        out[core] = _primal.primal_fit(dev(Xr), dev(yr), dev(sr), dev(np.zeros(5)), dev(Wr), False, ctx=ctx)
+    assert out["ozaki"].opt == out["dmma"].opt
+    assert rel_err(out["ozaki"].loo_errors, out["dmma"].loo_errors) < 1e-11
+    assert rel_err(out["ozaki"].rows["loo_residuals"].cpu().numpy(), out["dmma"].rows["loo_residuals"].cpu().numpy()) < 1e-10
 
 
 @pytest.mark.parametrize("kind", ["dc", "jacobi", "cusolver"])
