@@ -1400,7 +1400,8 @@ extern "C" int nls_primal_loo_sweep(nls_ctx* ctx, const double* X, const double*
   OzSweep ozs{};
   if (use_oz_sweep) NLS_TRY(oz_prep_sweep(ctx, g, gammas, lam, G, bs.v_r, bs.v_i, inv_c, &ozs));
   // projection and sweep both on the INT8 core: the projection epilogue writes the sweep's operand planes itself
-  const bool fused_planes = use_oz && use_oz_sweep && tail_split(g.m) % (oz::TN / 2) == 0;
+  const char* fuse_env = getenv("NLS_OZ_FUSE");  // NLS_OZ_FUSE=0: planes sliced from FP64 P, U instead (A/B timing)
+  const bool fused_planes = use_oz && use_oz_sweep && tail_split(g.m) % (oz::TN / 2) == 0 && !(fuse_env && fuse_env[0] == '0');
   for (int64_t i0 = 0; i0 < n; i0 += cap) {
     const int rows = (int)std::min<int64_t>(cap, n - i0);
     const int mtiles = (rows + BM - 1) / BM;
