@@ -131,30 +131,58 @@ struct OpCholUpdate {
 
 // ---- triangular solves with one right-hand side --------------------------------------------------------------
 // Diagonal block: forward (U_kk^H y = b_k) or backward (U_kk x = y_k), one CTA of 64 threads, column-oriented.
+// Thread c first pulls the block entries it will need into registers (forward: column c above the diagonal, backward:
+// row c right of it; all loads in flight at once), so the 64 dependent steps run on registers and one shared-memory
+// broadcast each instead of a global load per step (40 -> ~8 us per block, 34 blocks per solve at m = 1025).
 template <bool C>
 __global__ void __launch_bounds__(64) chol_solve_diag_kernel(const typename HS<C>::T* __restrict__ U, long long ld, int k0,
                                                              int nb, int backward, typename HS<C>::T* __restrict__ v) {
   using H = HS<C>;
   using T = typename H::T;
   __shared__ T xs[CNB];
+  __shared__ T xp;
   const int c = threadIdx.x;
-  if (c < nb) xs[c] = v[k0 + c];
+  T u[CNB];
+  double dinv = 0.0;
+  if (c < nb) {
+    xs[c] = v[k0 + c];
+    dinv = 1.0 / H::re(U[(long long)(k0 + c) * ld + k0 + c]);
+#pragma unroll
+    for (int p = 0; p < CNB; ++p) {
+      u[p] = H::zero();
+      if (p < nb) {
+        if (!backward && p < c) u[p] = U[(long long)(k0 + p) * ld + k0 + c];  // U[p][c]
+        if (backward && p > c) u[p] = U[(long long)(k0 + c) * ld + k0 + p];   // U[c][p]
+      }
+    }
+  }
   __syncthreads();
   if (!backward) {
-    for (int p = 0; p < nb; ++p) {
-      const T x = H::scale(1.0 / H::re(U[(long long)(k0 + p) * ld + k0 + p]), xs[p]);
-      __syncthreads();
-      if (c == p) xs[p] = x;
-      if (c > p && c < nb) xs[c] = H::sub(xs[c], H::cmul(U[(long long)(k0 + p) * ld + k0 + c], x));  // conj(U[p][c]) y_p
-      __syncthreads();
+#pragma unroll
+    for (int p = 0; p < CNB; ++p) {
+      if (p < nb) {
+        if (c == p) {
+          xs[p] = H::scale(dinv, xs[p]);
+          xp = xs[p];
+        }
+        __syncthreads();
+        if (c > p && c < nb) xs[c] = H::sub(xs[c], H::cmul(u[p], xp));  // conj(U[p][c]) y_p
+        __syncthreads();
+      }
     }
   } else {
-    for (int p = nb - 1; p >= 0; --p) {
-      const T x = H::scale(1.0 / H::re(U[(long long)(k0 + p) * ld + k0 + p]), xs[p]);
-      __syncthreads();
-      if (c == p) xs[p] = x;
-      if (c < p) xs[c] = H::sub(xs[c], H::mul(U[(long long)(k0 + c) * ld + k0 + p], x));  // U[c][p] x_p
-      __syncthreads();
+#pragma unroll
+    for (int q = 0; q < CNB; ++q) {
+      const int p = CNB - 1 - q;
+      if (p < nb) {
+        if (c == p) {
+          xs[p] = H::scale(dinv, xs[p]);
+          xp = xs[p];
+        }
+        __syncthreads();
+        if (c < p) xs[c] = H::sub(xs[c], H::mul(u[p], xp));  // U[c][p] x_p
+        __syncthreads();
+      }
     }
   }
   if (c < nb) v[k0 + c] = xs[c];
