@@ -440,8 +440,12 @@ def run_ours(args) -> None:
         fit = solve(Xd, yd, sd)
     peak_sustained = ctx.dmma_peak_tflops(20000) if rank == 0 else 0.0  # same loop right after the warm-up fits
     peak_tflops = max(peak_burst, peak_sustained)
-    i8_peak = ctx.i8_peak_tops(20000, 256) if rank == 0 else 0.0
+    i8_peak_burst = ctx.i8_peak_tops(20000, 256) if rank == 0 else 0.0
     i8_peak_n64 = ctx.i8_peak_tops(20000, 64) if rank == 0 else 0.0
+    # The INT8 stages run inside a long step at the board's power cap, so their denominator is the SUSTAINED rate of the
+    # same resident-tile loop: ~0.5 s of back-to-back launches, the lowest of the last five readings.
+    i8_peak_sustained = min([ctx.i8_peak_tops(20000, 256) for _ in range(20)][-5:]) if rank == 0 else 0.0
+    i8_peak = i8_peak_sustained
     sampler = ClockSampler(local_rank)
     launches0 = ctx.launch_count()
     if rank == 0:
@@ -606,10 +610,13 @@ def run_ours(args) -> None:
                 "peak_source": "FP64: DMMA register-resident loop measured in this run (nls_bench_dmma_peak), the larger of a "
                                "cold-start burst and a post-warm-up reading (148 SMs x 64 FMA/clk x 1.965 GHz = 37.2 TFLOP/s "
                                "nominal). INT8: resident-tile tcgen05.mma kind::i8 loop measured in this run "
-                               "(nls_bench_i8_peak, M = 128, N = 256; 148 SMs x 8192 MAC/clk = 4.76 POP/s nominal at 1.965 GHz). "
+                               "(nls_bench_i8_peak, M = 128, N = 256; 148 SMs x 8192 MAC/clk = 4.76 POP/s nominal at 1.965 GHz), the "
+                               "sustained reading after 0.5 s of back-to-back launches (the INT8 stages run at the power cap "
+                               "inside a long step; the burst reading is reported next to it). "
                                "MEASURED_PEAKS.json has neither figure",
                 "peak_fp64_dmma": peak_tflops, "peak_burst": peak_burst, "peak_sustained": peak_sustained,
-                "peak_int8": i8_peak, "peak_int8_at_tile_shape_n64": i8_peak_n64,
+                "peak_int8": i8_peak, "peak_int8_burst": i8_peak_burst, "peak_int8_sustained": i8_peak_sustained,
+                "peak_int8_at_tile_shape_n64": i8_peak_n64,
                 "stages": stages,
                 "fit_tflops": fit_tflops, "fit_frac": fit_tflops / (peak_tflops * world) if peak_tflops else None,
                 "fit_frac_note": "whole-fit algorithmic FP64 flop rate over the FP64 DMMA peak; above 1 means the INT8 "

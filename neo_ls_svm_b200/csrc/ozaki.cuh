@@ -1010,7 +1010,19 @@ __global__ void __launch_bounds__(128, 1) i8_peak_kernel(int iters) {
   constexpr uint32_t COLS = N <= 64 ? 64 : N <= 128 ? 128 : 256;
   constexpr uint32_t IDESC_N = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
   const int tid = threadIdx.x;
-  for (int e = tid; e < (TM + N) * 128 / 16; e += 128) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+  // pseudo-random operand bytes: the power a tensor-core loop draws (and with it the sustained clock) depends on the data
+  for (int e = tid; e < (TM + N) * 128 / 16; e += 128) {
+    uint32_t h = (uint32_t)e * 2654435761u + 0x9e3779b9u * (blockIdx.x + 1);
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      h ^= h << 13;
+      h ^= h >> 17;
+      h ^= h << 5;
+      w[q] = h;
+    }
+    reinterpret_cast<uint4*>(smem)[e] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
   if (tid < 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
