@@ -645,7 +645,8 @@ def main() -> None:
     ap.add_argument("--skip-configs", action="store_true", help="skip the C1/C2/C4/C5-shaped/stage-5 timings (N=1 arm)")
     ap.add_argument("--skip-api", action="store_true", help="skip the public-API NeoLSSVM.fit timing (N=1 arm)")
     ap.add_argument("--eig", choices=["auto", "dc", "jacobi", "cusolver"], default="auto",
-                    help="stage-3 eigensolver: hand-written block Jacobi (auto for m<=1100) or the cuSOLVER comparator")
+                    help="stage-3 eigensolver: auto = dc = hand-written tridiagonalisation + divide and conquer; jacobi = hand-written block "
+                         "Jacobi; cusolver = library comparator")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
