@@ -555,12 +555,14 @@ def run_ours(args) -> None:
         # DESIGN.md §4): Gram 4m², projection 8m², sweep 4mG FP64 flop per row; on the INT8 core one FP64 multiply-add is
         # 28 exact INT8 digit-plane multiply-adds (7 planes per operand, levels p + q <= 6), so its INT8 work is 28 x that.
         # `traffic`: dram__bytes_read.sum + dram__bytes_write.sum per launch (one 32,768-row chunk) from the `ncu --set full`
-        # captures summarised in profiles/r2g_ncu_full_int8.md (INT8 kernels, sweep) and profiles/r1_ncu_full_gemm_kernels.md.
+        # captures summarised in profiles/r2q_ncu_full_int8.md (final INT8 Gram / projection; the projection writes the sweep's
+        # operand planes: 550 MB in, 915 MB out), profiles/r2g_ncu_full_int8.md (first INT8 version, DMMA sweep) and
+        # profiles/r1_ncu_full_gemm_kernels.md (DMMA kernels).
         stage_defs = {
             "gram": (4.0 * m * m, int8, "oz::gemm_kernel_i8<EpiGram>" if int8 else "gemm_kernel<MODE_COMPLEX, OpGram>",
-                     1.6066e9 if int8 else None),
+                     1.8838e9 if int8 else None),
             "project": (8.0 * m * m, int8, "oz::gemm_kernel_i8<EpiProject> (T = φQ)" if int8 else "gemm_kernel<MODE_COMPLEX, OpProject> (T = φQ)",
-                        1.0617e9 if int8 else 1.0895e9),
+                        (1.4641e9 if int8_sweep else 1.0617e9) if int8 else 1.0895e9),
             "sweep": (4.0 * m * N_GAMMAS, int8_sweep,
                       "oz::gemm_kernel_i8<EpiSweep> (fused LOO residual / reduction)" if int8_sweep
                       else "gemm_kernel<MODE_DUAL_A, OpSweep> (fused LOO residual / reduction)", None if int8_sweep else 0.8093e9),
