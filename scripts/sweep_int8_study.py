@@ -35,8 +35,9 @@ def rel(a, b):
     return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
 
 
-def main():
-    cases = sys.argv[1:] or ["c1", "c3_small", "clf_small", "reg_small", "ragged:130:3:40", "ragged:1000:7:100", "ragged:2049:5:129"]
+def study(cases, group_counts=(0, 1, 8), verbose=True):
+    """results[name][groups] = {"opt_equal", "curve", "num", "den", "loo", "elementwise"} against the all-FP64 sweep."""
+    results = {}
     for name in cases:
         if name.startswith("ragged"):  # the shapes of tests/test_gpu_primal.py::test_ragged_shapes_match_oracle
             _, n_, d_, D_ = name.split(":")
@@ -84,8 +85,10 @@ def main():
             return loo, err, int(np.argmin(obj))
 
         loo0, err0, opt0 = curve(num0, den0)
-        print(f"== {name}: n={n} m={m} classifier={classifier} opt={opt0} (golden {int(g['opt'])}); λ in [{lam.min():.2e}, {lam.max():.2e}]")
-        for groups in (0, 1, 8):
+        if verbose:
+            print(f"== {name}: n={n} m={m} classifier={classifier} opt={opt0} (golden {int(g['opt'])}); λ in [{lam.min():.2e}, {lam.max():.2e}]")
+        results[name] = {}
+        for groups in group_counts:
             num, den = np.empty_like(num0), np.empty_like(den0)
             if groups == 0:  # plain fixed point: no column scaling at all
                 rq = quantise_rows(rg.T).T
@@ -98,9 +101,20 @@ def main():
                 rq = quantise_rows((d[:, None] / (gammas[None, sl] + lam[:, None])).T).T
                 num[:, sl], den[:, sl] = Pq @ rq, Uq @ rq
             loo, err, opt = curve(num, den)
-            print(f"   groups={groups:2d}: opt={opt}  LOO curve rel {rel(err, err0):.1e}  num rel {rel(num, num0):.1e}  den rel {rel(den, den0):.1e}  "
-                  f"LOO residuals at opt rel {rel(loo[:, opt0], loo0[:, opt0]):.1e}  elementwise worst |Δ|/(1e-9|ref|+1e-12 max) "
-                  f"{float(np.max(np.abs(loo[:, opt0] - loo0[:, opt0]) / (1e-9 * np.abs(loo0[:, opt0]) + 1e-12 * np.max(np.abs(loo0[:, opt0]))))):.2f}")
+            results[name][groups] = {
+                "opt_equal": opt == opt0, "curve": rel(err, err0), "num": rel(num, num0), "den": rel(den, den0),
+                "loo": rel(loo[:, opt0], loo0[:, opt0]),
+                "elementwise": float(np.max(np.abs(loo[:, opt0] - loo0[:, opt0]) / (1e-9 * np.abs(loo0[:, opt0]) + 1e-12 * np.max(np.abs(loo0[:, opt0]))))),
+            }
+            if verbose:
+                print(f"   groups={groups:2d}: opt={opt}  LOO curve rel {rel(err, err0):.1e}  num rel {rel(num, num0):.1e}  den rel {rel(den, den0):.1e}  "
+                      f"LOO residuals at opt rel {rel(loo[:, opt0], loo0[:, opt0]):.1e}  elementwise worst |Δ|/(1e-9|ref|+1e-12 max) "
+                      f"{float(np.max(np.abs(loo[:, opt0] - loo0[:, opt0]) / (1e-9 * np.abs(loo0[:, opt0]) + 1e-12 * np.max(np.abs(loo0[:, opt0]))))):.2f}")
+    return results
+
+
+def main():
+    study(sys.argv[1:] or ["c1", "c3_small", "clf_small", "reg_small", "ragged:130:3:40", "ragged:1000:7:100", "ragged:2049:5:129"])
 
 
 if __name__ == "__main__":
