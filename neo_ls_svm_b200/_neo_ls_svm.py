@@ -247,9 +247,9 @@ class NeoLSSVM(BaseEstimator):
         )
         check_consistent_length(y, sample_weight_)
         # Task type from the target (:351-373).
-        # Only "exactly two distinct values" matters here; three distinct values in a prefix settle it without sorting
-        # all of a large target vector (0.1 s at n = 4M).
-        head = np.unique(y[:4096]) if len(y) > (1 << 20) else ()
+        # For the inference only "exactly two distinct values" matters: three distinct values in a prefix settle it without
+        # sorting all of a large target vector (0.1 s at n = 4M).  A forced classifier needs the full set for `classes_`.
+        head = np.unique(y[:4096]) if len(y) > (1 << 20) and self.estimator_type != "classifier" else ()
         distinct = head if len(head) > 2 else unique_values(y)  # noqa: PLR2004
         inferred = None
         if len(distinct) == 2:  # noqa: PLR2004
